@@ -1,0 +1,152 @@
+/*
+ * nbk_b200 -- C ABI of the B200-native FFTPower hot path (libnbk_b200.so).
+ *
+ * The reference (bccp/nbodykit) has no C ABI of its own: its seam for this path is the
+ * duck-typed Python interface of the un-vendored `pmesh` package.  Each entry point
+ * below names the reference call site(s) whose arithmetic it replaces (paths relative to
+ * the nbodykit tree).  All pointers are DEVICE pointers unless marked `host`; sizes are
+ * element counts; every call is asynchronous and ordered on `stream` (a cudaStream_t
+ * passed as void*, NULL = legacy default stream).  Return value: 0 on success, negative
+ * on error (nbk_last_error() gives the text).  No torch types, no C++ exceptions cross
+ * this boundary.
+ */
+#ifndef NBK_B200_H
+#define NBK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* scalar type codes */
+#define NBK_F4 4
+#define NBK_F8 8
+
+/* resampling windows: value == support (pmesh.window.methods[...].support,
+ * source/mesh/catalog.py:194,271-273) */
+#define NBK_WINDOW_NNB 1
+#define NBK_WINDOW_CIC 2
+#define NBK_WINDOW_TSC 3
+#define NBK_WINDOW_PCS 4
+
+/* compensation transfer functions (source/mesh/catalog.py:449-594) */
+#define NBK_COMP_NONE 0
+#define NBK_COMP_CIC 1           /* CompensateCIC            :513-535 */
+#define NBK_COMP_TSC 2           /* CompensateTSC            :449-473 */
+#define NBK_COMP_PCS 3           /* CompensatePCS            :475-500 */
+#define NBK_COMP_CIC_SHOTNOISE 4 /* CompensateCICShotnoise   :573-594 */
+#define NBK_COMP_TSC_SHOTNOISE 5 /* CompensateTSCShotnoise   :537-559 */
+#define NBK_COMP_PCS_SHOTNOISE 6 /* CompensatePCSShotnoise   :561-571 */
+
+/* error codes */
+#define NBK_OK 0
+#define NBK_ERR_ARG -1
+#define NBK_ERR_CUDA -2
+#define NBK_ERR_UNSUPPORTED -3
+
+int nbk_version(void);
+const char *nbk_last_error(void);
+/* number of kernels this library has launched since load (bench.py's "gpu_launches") */
+int64_t nbk_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Layout of a (slab of a) mesh.  Real field: x-major C order [x_n][Ny][Nz].  Complex field:
+ * Hermitian-compressed on the last axis, Nzc = Nz/2+1.  `transposed == 0`: [x_n][Ny][Nzc]
+ * holding x planes [x_start, x_start+x_n);  `transposed == 1`: [y_n][Nx][Nzc] holding y rows
+ * [y_start, y_start+y_n) of every x (what the slab FFT leaves on each GPU when P > 1).
+ * ------------------------------------------------------------------------------------- */
+
+/* pm.paint(pos, mass=, resampler=, transform=pm.affine[.shift(s)], hold=True, out=)
+ * -- source/mesh/catalog.py:287,295-296 (pmesh window scatter).
+ * pos: [n][3] row-major, pos_dtype F4|F8.  mass: [n] or NULL (unit), mass_dtype F4|F8.
+ * Grid coordinate g_d = fl(fl(double(pos_d)*fl(N_d/L_d)) + shift) (no FMA), periodic wrap in
+ * grid units; stencil points whose x plane is outside [x_start, x_start+x_n) are dropped
+ * (pmesh ghost semantics).  Always accumulates into `mesh` (hold=True); zero it first
+ * with nbk_fill for hold=False.  mesh_dtype F4|F8. */
+int nbk_paint(const void *pos, int pos_dtype, int64_t n, const void *mass, int mass_dtype,
+              int window, double shift, const double *boxsize_host, const int64_t *nmesh_host,
+              int64_t x_start, int64_t x_n, void *mesh, int mesh_dtype, void *stream);
+
+/* same, painting the un-shifted and the +0.5-cell shifted mesh in one pass over the particles
+ * (the interlaced branch, source/mesh/catalog.py:289-296) */
+int nbk_paint_interlaced(const void *pos, int pos_dtype, int64_t n, const void *mass,
+                         int mass_dtype, int window, const double *boxsize_host,
+                         const int64_t *nmesh_host, int64_t x_start, int64_t x_n, void *mesh1,
+                         void *mesh2, int mesh_dtype, void *stream);
+
+/* leftmost stencil cell (wrapped) of every particle, [n][3] int32 -- the bit-exact part of the
+ * paint contract, exported for parity tests and for pm.decompose (catalog.py:271-273) */
+int nbk_cell_index(const void *pos, int pos_dtype, int64_t n, int window, double shift,
+                   const double *boxsize_host, const int64_t *nmesh_host, int32_t *cell_out,
+                   void *stream);
+
+/* Wlocal = sum w, W2local = sum w^2 (source/mesh/catalog.py:265-267); out2: device double[2],
+ * accumulated into (zero it first). */
+int nbk_sum_w_w2(const void *w, int dtype, int64_t n, double *out2, void *stream);
+
+/* RealField.r2c / ComplexField.c2r (base/mesh.py:228,237; source/mesh/catalog.py:341-351).
+ * Forward is normalised by 1/(Nx*Ny*Nz), backward unnormalised (source/mesh/array.py:36-37).
+ * Single-GPU whole-mesh transforms; real [Nx][Ny][Nz], cplx [Nx][Ny][Nzc].  Out of place. */
+int nbk_r2c(const void *real, void *cplx, int dtype, const int64_t *nmesh_host, void *stream);
+int nbk_c2r(const void *cplx, void *real, int dtype, const int64_t *nmesh_host, void *work,
+            void *stream);
+
+/* the three 1-D passes of the slab-decomposed transform, for the multi-GPU path (P > 1):
+ *   zy pass : real slab [x_n][Ny][Nz] -> cplx slab [x_n][Ny][Nzc], r2c along z then FFT along y
+ *   pack    : cplx slab [x_n][Ny][Nzc] -> send buffer [P][y_n][x_n][Nzc] (block p = y rows of rank p)
+ *   x pass  : after the all-to-all the receive buffer [P][y_n][x_n][Nzc] IS [y_n][Nx][Nzc] re-ordered;
+ *             unpack -> [y_n][Nx][Nzc], FFT along x, scale by `scale`.
+ * and their inverses for c2r. */
+int nbk_fft_zy_forward(const void *real, void *cplx, int dtype, int64_t x_n, int64_t Ny, int64_t Nz,
+                       void *stream);
+int nbk_fft_zy_backward(void *cplx, void *real, int dtype, int64_t x_n, int64_t Ny, int64_t Nz,
+                        void *stream);
+int nbk_fft_lines(void *cplx, int dtype, int64_t n_line, int64_t line_stride, int64_t n_inner,
+                  int64_t n_outer, int64_t outer_stride, int inverse, double scale, void *stream);
+int nbk_transpose_pack(const void *src, void *dst, int dtype, int64_t x_n, int64_t Ny, int64_t Nzc,
+                       int64_t P, void *stream);
+int nbk_transpose_unpack(const void *src, void *dst, int dtype, int64_t y_n, int64_t Nx,
+                         int64_t Nzc, int64_t P, void *stream);
+int nbk_transpose_pack_back(const void *src, void *dst, int dtype, int64_t y_n, int64_t Nx,
+                            int64_t Nzc, int64_t P, void *stream);
+int nbk_transpose_unpack_back(const void *src, void *dst, int dtype, int64_t x_n, int64_t Ny,
+                              int64_t Nzc, int64_t P, void *stream);
+
+/* Field.apply(func=Compensate*, kind='circular', out=Ellipsis) -- base/mesh.py:306-313 with
+ * source/mesh/catalog.py:449-594.  In place on a complex slab. */
+int nbk_compensate(void *cplx, int dtype, int kind, const int64_t *nmesh_host, int transposed,
+                   int64_t start, int64_t count, void *stream);
+
+/* s1 = 0.5*s1 + 0.5*s2*exp(0.5j * sum_i k_i H_i) -- source/mesh/catalog.py:345-347 */
+int nbk_interlace_combine(void *c1, const void *c2, int dtype, const int64_t *nmesh_host,
+                          const double *boxsize_host, int transposed, int64_t start, int64_t count,
+                          void *stream);
+
+/* FFTBase._compute_3d_power (algorithms/fftpower.py:115-128: c1*conj(c2), zero mode, *V) fused
+ * with project_to_basis (:507-701) and MeshSlab.norm2/mu/hermitian_weights (meshtools.py:104-215).
+ * c2 == NULL -> auto power.  If is_p3d != 0 the input is taken as an already-formed 3-D statistic
+ * y3d (project_to_basis semantics only; c2, volume, clear_zero ignored).
+ * k2edges: host double[Nx+1] = kedges**2; muedges: host double[Nmu+1]; ells: host int[Nell]
+ * (ells[0] must be 0).  coord_dtype NBK_F4 (fixture-faithful) | NBK_F8.
+ * Outputs (device, ACCUMULATED into; zero first), nb = (Nx+2)*(Nmu+2):
+ *   nsum int64[nb]; xsum, musum double[nb]; ysum double[Nell][nb][2] (re, im). */
+int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume,
+                  int clear_zero, const int64_t *nmesh_host, const double *boxsize_host,
+                  int transposed, int64_t start, int64_t count, int coord_dtype,
+                  const double *k2edges_host, int Nx, const double *muedges_host, int Nmu,
+                  const double *los_host, const int *ells_host, int Nell, int hermitian,
+                  int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
+
+/* elementwise helpers behind RealField/ComplexField `[...] = v`, `*= a`, `+= other`
+ * (source/mesh/catalog.py:203,354,396-398; fftpower.py:128).  n counts REAL scalars. */
+int nbk_fill(void *x, int dtype, int64_t n, double value, void *stream);
+int nbk_scale(void *x, int dtype, int64_t n, double a, void *stream);
+int nbk_axpy(void *y, const void *x, int dtype, int64_t n, double a, void *stream);
+/* csum (source/mesh/catalog.py:388): out1 device double[1], accumulated into */
+int nbk_sum(const void *x, int dtype, int64_t n, double *out1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,482 @@
+// cuFFT-free 3-D real<->complex FFT (RealField.r2c / ComplexField.c2r: base/mesh.py:228,237;
+// source/mesh/catalog.py:341-351).  Forward is normalised by 1/prod(N), backward is not
+// (source/mesh/array.py:36-37, fftpower.py:126-128).
+//
+// Structure: three shared-memory line passes, each one read + one write of the field (HBM-bound):
+//   z pass  : rows are contiguous; real row of Nz -> packed complex FFT of Nz/2 -> Nz/2+1 modes
+//   y pass  : lines strided by Nzc, tiles of B adjacent kz columns  (B*sizeof(cplx) >= 64 B runs)
+//   x pass  : lines strided by Ny*Nzc, tiles of B adjacent (y,kz) elements
+// Every pass stages a [N][B] tile (pitch B+1: conflict-free both for the butterfly access and for
+// the transposed fill of the z pass) in shared memory, runs an in-place radix-4 (+ one radix-2)
+// decimation-in-frequency FFT, and writes frequencies out through the digit-reversal map, so no
+// ping-pong buffer is needed.  Twiddles come from an f8-accurate table built on the device with
+// sincospi.  Sizes: powers of two.
+#include "common.cuh"
+#include <map>
+#include <mutex>
+#include <tuple>
+
+template <typename T> struct C2;
+template <> struct C2<float> { typedef float2 type; };
+template <> struct C2<double> { typedef double2 type; };
+
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { return C{a.x + b.x, a.y + b.y}; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { return C{a.x - b.x, a.y - b.y}; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    return C{a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+template <typename C> __device__ __forceinline__ C cconj(C a) { return C{a.x, -a.y}; }
+template <typename C> __device__ __forceinline__ C cmuli_neg(C a) { return C{a.y, -a.x}; }  // a * (-i)
+
+// position (in the in-place DIF output) of frequency k
+__device__ __forceinline__ int pos_of_freq(int k, int N, int log2n) {
+    int rem = k, base = N, pos = 0;
+    for (int s = 0; s < (log2n >> 1); s++) {
+        int d = rem & 3;
+        rem >>= 2;
+        base >>= 2;
+        pos += d * base;
+    }
+    if (log2n & 1) pos += (rem & 1);
+    return pos;
+}
+
+// In-place forward DIF FFT of B side-by-side lines of length N held in sm[n*pitch + b].
+// tw[k] = exp(-2 pi i k / N), k < N.  All threads of the CTA must call.
+template <typename C>
+__device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N, int log2n, int B, int pitch) {
+    const int T = blockDim.x;
+    int Ns = N;
+    for (int s = 0; s < (log2n >> 1); s++) {
+        const int Q = Ns >> 2;
+        const int tws = N / Ns;
+        const int work = (N >> 2) * B;
+        for (int w = threadIdx.x; w < work; w += T) {
+            int b = w % B;
+            int t = w / B;
+            int blk = t / Q, q = t - blk * Q;
+            C *p = sm + (blk * Ns + q) * pitch + b;
+            const int st = Q * pitch;
+            C a0 = p[0], a1 = p[st], a2 = p[2 * st], a3 = p[3 * st];
+            C t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmuli_neg(csub(a1, a3));
+            C y0 = cadd(t0, t2), y1 = cadd(t1, t3), y2 = csub(t0, t2), y3 = csub(t1, t3);
+            if (Q > 1) {
+                int ti = q * tws;
+                y1 = cmul(y1, tw[ti]);
+                y2 = cmul(y2, tw[2 * ti]);
+                y3 = cmul(y3, tw[3 * ti]);
+            }
+            p[0] = y0; p[st] = y1; p[2 * st] = y2; p[3 * st] = y3;
+        }
+        __syncthreads();
+        Ns = Q;
+    }
+    if (log2n & 1) {  // Ns == 2
+        const int work = (N >> 1) * B;
+        for (int w = threadIdx.x; w < work; w += T) {
+            int b = w % B;
+            int t = w / B;
+            C *p = sm + (2 * t) * pitch + b;
+            C a0 = p[0], a1 = p[pitch];
+            p[0] = cadd(a0, a1);
+            p[pitch] = csub(a0, a1);
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// strided line pass (y and x passes), in place.  element(outer, n, inner) =
+//   data[outer*outer_stride + n*line_stride + inner],  inner < n_inner contiguous.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type *__restrict__ tw, int N, int log2n,
+            int B, int64_t line_stride, int64_t n_inner, int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride,
+            int inverse, T scale) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    const int pitch = B + 1;
+    const int T_ = blockDim.x;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t outer = tile / tiles_inner;
+        int64_t inner0 = (tile - outer * tiles_inner) * B;
+        C *base = data + outer * outer_stride + inner0;
+        int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+        for (int w = threadIdx.x; w < N * B; w += T_) {
+            int b = w % B, n = w / B;
+            C v = C{0, 0};
+            if (b < bvalid) v = base[(int64_t)n * line_stride + b];
+            if (inverse) v.y = -v.y;
+            sm[n * pitch + b] = v;
+        }
+        __syncthreads();
+        fft_tile<C>(sm, tw, N, log2n, B, pitch);
+        for (int w = threadIdx.x; w < N * B; w += T_) {
+            int b = w % B, k = w / B;
+            if (b < bvalid) {
+                C v = sm[pos_of_freq(k, N, log2n) * pitch + b];
+                if (inverse) v.y = -v.y;
+                v.x *= scale;
+                v.y *= scale;
+                base[(int64_t)k * line_stride + b] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// z pass forward: real rows [rows][Nz] -> complex rows [rows][Nz/2+1]
+// packed trick: z[n] = x[2n] + i x[2n+1], Z = FFT_M(z), M = Nz/2,
+//   X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k]) ],  k = 0..M  (Z[M] := Z[0])
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
+            const typename C2<T>::type *__restrict__ twM, const typename C2<T>::type *__restrict__ twN, int Nz,
+            int log2m, int B, int64_t rows, T scale) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    const int M = Nz >> 1;
+    const int Nzc = M + 1;
+    const int pitch = B + 1;
+    const int T_ = blockDim.x;
+    const int64_t n_tiles = (rows + B - 1) / B;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t row0 = tile * B;
+        int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
+        const C *src = reinterpret_cast<const C *>(real + row0 * Nz);  // rows of M packed pairs, 2*sizeof(T) aligned
+        for (int w = threadIdx.x; w < M * B; w += T_) {
+            int n = w % M, b = w / M;  // lanes run along the contiguous row
+            C v = C{0, 0};
+            if (b < bvalid) v = src[(int64_t)b * M + n];
+            sm[n * pitch + b] = v;
+        }
+        __syncthreads();
+        fft_tile<C>(sm, twM, M, log2m, B, pitch);
+        C *dst = cplx + row0 * Nzc;
+        for (int w = threadIdx.x; w < Nzc * B; w += T_) {
+            int k = w % Nzc, b = w / Nzc;
+            if (b < bvalid) {
+                C zk = sm[pos_of_freq(k & (M - 1), M, log2m) * pitch + b];
+                C zm = cconj(sm[pos_of_freq((M - k) & (M - 1), M, log2m) * pitch + b]);
+                C e = cadd(zk, zm), o = csub(zk, zm);
+                C wo = cmul(twN[k], o);          // W_N^k (Z[k] - conj Z[M-k])
+                C x = C{e.x + wo.y, e.y - wo.x};  // e - i*wo
+                T h = (T)0.5 * scale;
+                dst[(int64_t)b * Nzc + k] = C{x.x * h, x.y * h};
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// z pass backward: complex rows [rows][Nz/2+1] -> real rows [rows][Nz], unnormalised
+//   E = (X[k] + conj X[M-k])/2, O = conj(W_N^k) (X[k] - conj X[M-k])/2, Z[k] = E + i O, k < M
+//   x[2n] + i x[2n+1] = 2 * sum_k Z[k] e^{+2 pi i k n / M} = 2 * conj(FFT_M(conj Z))[n]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
+            const typename C2<T>::type *__restrict__ twM, const typename C2<T>::type *__restrict__ twN, int Nz,
+            int log2m, int B, int64_t rows) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    const int M = Nz >> 1;
+    const int Nzc = M + 1;
+    const int pitch = B + 1;
+    const int T_ = blockDim.x;
+    const int64_t n_tiles = (rows + B - 1) / B;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t row0 = tile * B;
+        int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
+        const C *src = cplx + row0 * Nzc;
+        for (int w = threadIdx.x; w < M * B; w += T_) {
+            int k = w % M, b = w / M;
+            C v = C{0, 0};
+            if (b < bvalid) {
+                C xk = src[(int64_t)b * Nzc + k];
+                C xm = cconj(src[(int64_t)b * Nzc + (M - k)]);
+                C e = cadd(xk, xm), d = csub(xk, xm);
+                C o = cmul(cconj(twN[k]), d);
+                // Z = (e + i o)/2 ; the factor 2 of the unnormalised inverse cancels the 1/2
+                C z = C{e.x - o.y, e.y + o.x};
+                v = cconj(z);
+            }
+            sm[k * pitch + b] = v;
+        }
+        __syncthreads();
+        fft_tile<C>(sm, twM, M, log2m, B, pitch);
+        C *dst = reinterpret_cast<C *>(real + row0 * Nz);
+        for (int w = threadIdx.x; w < M * B; w += T_) {
+            int n = w % M, b = w / M;
+            if (b < bvalid) {
+                C v = cconj(sm[pos_of_freq(n, M, log2m) * pitch + b]);
+                dst[(int64_t)b * M + n] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// twiddle tables, cached per (device, N, dtype)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_twiddle(typename C2<T>::type *tw, int N) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < N) {
+        double s, c;
+        sincospi(-2.0 * (double)k / (double)N, &s, &c);
+        tw[k].x = (T)c;
+        tw[k].y = (T)s;
+    }
+}
+
+static std::mutex g_tw_mutex;
+static std::map<std::tuple<int, int, int>, void *> g_tw;
+
+static int get_twiddle(int N, int dtype, cudaStream_t s, void **out) {
+    int dev = 0;
+    NBK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_tw_mutex);
+    auto key = std::make_tuple(dev, N, dtype);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) { *out = it->second; return NBK_OK; }
+    void *p = nullptr;
+    size_t bytes = (size_t)(N > 0 ? N : 1) * (dtype == NBK_F4 ? 8 : 16);
+    NBK_CUDA(cudaMalloc(&p, bytes));
+    int g = (N + 255) / 256;
+    if (g < 1) g = 1;
+    if (dtype == NBK_F4) k_twiddle<float><<<g, 256, 0, s>>>((float2 *)p, N);
+    else k_twiddle<double><<<g, 256, 0, s>>>((double2 *)p, N);
+    NBK_LAUNCHED();
+    // table must be visible to later launches on other streams as well
+    NBK_CUDA(cudaStreamSynchronize(s));
+    g_tw[key] = p;
+    *out = p;
+    return NBK_OK;
+}
+
+static int ilog2(int64_t n) {
+    int l = 0;
+    while (((int64_t)1 << l) < n) l++;
+    return l;
+}
+static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
+
+// pick the number of side-by-side lines: >= 64 B contiguous runs, tile <= ~96 KB (2 CTAs / SM)
+static int pick_B(int N, int csize, int64_t n_inner) {
+    int B = 128 / csize;  // 128-byte runs: 16 (c8) or 8 (c16)
+    while (B > 1 && (size_t)N * (B + 1) * csize > 98304) B >>= 1;
+    while (B > 1 && B / 2 >= n_inner) B >>= 1;
+    return B;
+}
+
+template <typename T>
+static int launch_lines(void *data, int N, int64_t line_stride, int64_t n_inner, int64_t n_outer,
+                        int64_t outer_stride, int inverse, double scale, cudaStream_t s) {
+    typedef typename C2<T>::type C;
+    int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
+    if (N == 1) {
+        if (scale != 1.0) {
+            nbk_set_error("fft_lines: N == 1 with scale is not supported");
+            return NBK_ERR_UNSUPPORTED;
+        }
+        return NBK_OK;
+    }
+    void *tw;
+    int rc = get_twiddle(N, dtype, s, &tw);
+    if (rc) return rc;
+    int B = pick_B(N, (int)sizeof(C), n_inner);
+    size_t smem = (size_t)N * (B + 1) * sizeof(C);
+    NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: N=%d does not fit in shared memory", N);
+    NBK_CUDA(cudaFuncSetAttribute(k_fft_lines<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t tiles_inner = (n_inner + B - 1) / B;
+    int64_t n_tiles = tiles_inner * n_outer;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+    k_fft_lines<T><<<(int)g, 256, smem, s>>>((C *)data, (const C *)tw, N, ilog2(N), B, line_stride, n_inner,
+                                             tiles_inner, n_tiles, outer_stride, inverse, (T)scale);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+extern "C" int nbk_fft_lines(void *cplx, int dtype, int64_t n_line, int64_t line_stride, int64_t n_inner,
+                             int64_t n_outer, int64_t outer_stride, int inverse, double scale, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "fft_lines: bad dtype %d", dtype);
+    NBK_CHECK_ARG(is_pow2(n_line) && n_line <= 8192, "fft_lines: line length %lld is not a supported power of two",
+                  (long long)n_line);
+    if (n_inner <= 0 || n_outer <= 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4)
+        return launch_lines<float>(cplx, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+    return launch_lines<double>(cplx, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+}
+
+template <typename T>
+static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forward, double scale, cudaStream_t s) {
+    typedef typename C2<T>::type C;
+    int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
+    int M = Nz / 2;
+    void *twM, *twN;
+    int rc = get_twiddle(M, dtype, s, &twM);
+    if (rc) return rc;
+    rc = get_twiddle(Nz, dtype, s, &twN);
+    if (rc) return rc;
+    int B = pick_B(M, (int)sizeof(C), rows);
+    size_t smem = (size_t)M * (B + 1) * sizeof(C);
+    NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);
+    int64_t n_tiles = (rows + B - 1) / B;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+    if (forward) {
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_z_r2c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fft_z_r2c<T><<<(int)g, 256, smem, s>>>((const T *)in, (C *)out, (const C *)twM, (const C *)twN, Nz,
+                                                 ilog2(M), B, rows, (T)scale);
+    } else {
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_z_c2r<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_fft_z_c2r<T><<<(int)g, 256, smem, s>>>((const C *)in, (T *)out, (const C *)twM, (const C *)twN, Nz,
+                                                 ilog2(M), B, rows);
+    }
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+static int check_dims(const char *who, int dtype, int64_t Nx, int64_t Ny, int64_t Nz) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "%s: bad dtype %d", who, dtype);
+    NBK_CHECK_ARG(is_pow2(Nx) && is_pow2(Ny) && is_pow2(Nz) && Nz >= 4 && Nx <= 8192 && Ny <= 8192 && Nz <= 16384,
+                  "%s: Nmesh (%lld,%lld,%lld) unsupported: each side must be a power of two (Nz >= 4)", who,
+                  (long long)Nx, (long long)Ny, (long long)Nz);
+    return NBK_OK;
+}
+
+extern "C" int nbk_fft_zy_forward(const void *real, void *cplx, int dtype, int64_t x_n, int64_t Ny, int64_t Nz,
+                                  void *stream) {
+    int rc = check_dims("fft_zy_forward", dtype, 1, Ny, Nz);
+    if (rc) return rc;
+    if (x_n <= 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t Nzc = Nz / 2 + 1;
+    rc = (dtype == NBK_F4) ? launch_z<float>(real, cplx, x_n * Ny, (int)Nz, true, 1.0, s)
+                           : launch_z<double>(real, cplx, x_n * Ny, (int)Nz, true, 1.0, s);
+    if (rc) return rc;
+    return nbk_fft_lines(cplx, dtype, Ny, Nzc, Nzc, x_n, Ny * Nzc, 0, 1.0, stream);
+}
+
+extern "C" int nbk_fft_zy_backward(void *cplx, void *real, int dtype, int64_t x_n, int64_t Ny, int64_t Nz,
+                                   void *stream) {
+    int rc = check_dims("fft_zy_backward", dtype, 1, Ny, Nz);
+    if (rc) return rc;
+    if (x_n <= 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t Nzc = Nz / 2 + 1;
+    rc = nbk_fft_lines(cplx, dtype, Ny, Nzc, Nzc, x_n, Ny * Nzc, 1, 1.0, stream);
+    if (rc) return rc;
+    return (dtype == NBK_F4) ? launch_z<float>(cplx, real, x_n * Ny, (int)Nz, false, 1.0, s)
+                             : launch_z<double>(cplx, real, x_n * Ny, (int)Nz, false, 1.0, s);
+}
+
+extern "C" int nbk_r2c(const void *real, void *cplx, int dtype, const int64_t *nmesh, void *stream) {
+    int rc = check_dims("r2c", dtype, nmesh[0], nmesh[1], nmesh[2]);
+    if (rc) return rc;
+    int64_t Nx = nmesh[0], Ny = nmesh[1], Nz = nmesh[2], Nzc = Nz / 2 + 1;
+    rc = nbk_fft_zy_forward(real, cplx, dtype, Nx, Ny, Nz, stream);
+    if (rc) return rc;
+    double scale = 1.0 / ((double)Nx * (double)Ny * (double)Nz);
+    if (Nx == 1) return nbk_scale(cplx, dtype, 2 * Ny * Nzc, scale, stream);
+    return nbk_fft_lines(cplx, dtype, Nx, Ny * Nzc, Ny * Nzc, 1, 0, 0, scale, stream);
+}
+
+// c2r destroys its complex input unless `work` (same size as cplx) is given
+extern "C" int nbk_c2r(const void *cplx, void *real, int dtype, const int64_t *nmesh, void *work, void *stream) {
+    int rc = check_dims("c2r", dtype, nmesh[0], nmesh[1], nmesh[2]);
+    if (rc) return rc;
+    int64_t Nx = nmesh[0], Ny = nmesh[1], Nz = nmesh[2], Nzc = Nz / 2 + 1;
+    void *c = const_cast<void *>(cplx);
+    if (work && work != cplx) {
+        size_t bytes = (size_t)Nx * Ny * Nzc * (dtype == NBK_F4 ? 8 : 16);
+        NBK_CUDA(cudaMemcpyAsync(work, cplx, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        c = work;
+    }
+    rc = nbk_fft_lines(c, dtype, Nx, Ny * Nzc, Ny * Nzc, 1, 0, 1, 1.0, stream);
+    if (rc) return rc;
+    return nbk_fft_zy_backward(c, real, dtype, Nx, Ny, Nz, stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// slab <-> pencil transposes for P > 1 (row copies of Nzc complex, coalesced along kz)
+// ---------------------------------------------------------------------------------------------
+// generic: dst[(a*nb + b)*row + k] = src[(b*na + a)*row + k] with an extra block split described by the callers
+template <typename C>
+__global__ void __launch_bounds__(256)
+k_row_permute(const C *__restrict__ src, C *__restrict__ dst, int64_t n_rows, int row, int64_t d0, int64_t d1,
+              int64_t d2, int64_t s0, int64_t s1, int64_t s2) {
+    // destination row index r = (i0*d1 + i1)*d2 + i2  ->  source row = i0*s0 + i1*s1 + i2*s2
+    int lanes_per_row = 32;
+    int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / lanes_per_row;
+    int lane = threadIdx.x % lanes_per_row;
+    int64_t nw = ((int64_t)gridDim.x * blockDim.x) / lanes_per_row;
+    for (int64_t r = wid; r < n_rows; r += nw) {
+        int64_t i2 = r % d2;
+        int64_t i1 = (r / d2) % d1;
+        int64_t i0 = r / (d2 * d1);
+        const C *sp = src + (i0 * s0 + i1 * s1 + i2 * s2) * row;
+        C *dp = dst + r * row;
+        for (int k = lane; k < row; k += lanes_per_row) dp[k] = sp[k];
+    }
+}
+
+template <typename C>
+static int launch_permute(const void *src, void *dst, int64_t d0, int64_t d1, int64_t d2, int64_t s0, int64_t s1,
+                          int64_t s2, int row, cudaStream_t s) {
+    int64_t n_rows = d0 * d1 * d2;
+    if (n_rows == 0) return NBK_OK;
+    int g = nbk_grid_for(n_rows * 32, 256, 8);
+    k_row_permute<C><<<g, 256, 0, s>>>((const C *)src, (C *)dst, n_rows, row, d0, d1, d2, s0, s1, s2);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+#define PERMUTE(dtype, ...)                                                          \
+    ((dtype) == NBK_F4 ? launch_permute<float2>(__VA_ARGS__) : launch_permute<double2>(__VA_ARGS__))
+
+// [x_n][Ny][Nzc] -> [P][y_n][x_n][Nzc]   (dst rows (p, yl, x) <- src row (x, p*y_n + yl))
+extern "C" int nbk_transpose_pack(const void *src, void *dst, int dtype, int64_t x_n, int64_t Ny, int64_t Nzc,
+                                  int64_t P, void *stream) {
+    NBK_CHECK_ARG(P > 0 && Ny % P == 0, "transpose_pack: Ny %% P != 0");
+    int64_t y_n = Ny / P;
+    // dst index (i0=p, i1=yl, i2=x): src row = x*Ny + p*y_n + yl
+    return PERMUTE(dtype, src, dst, P, y_n, x_n, y_n, 1, Ny, (int)Nzc, (cudaStream_t)stream);
+}
+// [P][y_n][x_n][Nzc] (block q came from rank q) -> [y_n][Nx][Nzc], Nx = P*x_n
+extern "C" int nbk_transpose_unpack(const void *src, void *dst, int dtype, int64_t y_n, int64_t Nx, int64_t Nzc,
+                                    int64_t P, void *stream) {
+    NBK_CHECK_ARG(P > 0 && Nx % P == 0, "transpose_unpack: Nx %% P != 0");
+    int64_t x_n = Nx / P;
+    // dst (i0=yl, i1=q, i2=xl): src row = (q*y_n + yl)*x_n + xl
+    return PERMUTE(dtype, src, dst, y_n, P, x_n, x_n, y_n * x_n, 1, (int)Nzc, (cudaStream_t)stream);
+}
+// inverse of unpack: [y_n][Nx][Nzc] -> [P][y_n][x_n][Nzc]
+extern "C" int nbk_transpose_pack_back(const void *src, void *dst, int dtype, int64_t y_n, int64_t Nx, int64_t Nzc,
+                                       int64_t P, void *stream) {
+    NBK_CHECK_ARG(P > 0 && Nx % P == 0, "transpose_pack_back: Nx %% P != 0");
+    int64_t x_n = Nx / P;
+    // dst (i0=q, i1=yl, i2=xl): src row = yl*Nx + q*x_n + xl
+    return PERMUTE(dtype, src, dst, P, y_n, x_n, x_n, Nx, 1, (int)Nzc, (cudaStream_t)stream);
+}
+// inverse of pack: [P][y_n][x_n][Nzc] -> [x_n][Ny][Nzc]
+extern "C" int nbk_transpose_unpack_back(const void *src, void *dst, int dtype, int64_t x_n, int64_t Ny, int64_t Nzc,
+                                         int64_t P, void *stream) {
+    NBK_CHECK_ARG(P > 0 && Ny % P == 0, "transpose_unpack_back: Ny %% P != 0");
+    int64_t y_n = Ny / P;
+    // dst (i0=x, i1=p, i2=yl): src row = (p*y_n + yl)*x_n + x
+    return PERMUTE(dtype, src, dst, x_n, P, y_n, 1, y_n * x_n, x_n, (int)Nzc, (cudaStream_t)stream);
+}

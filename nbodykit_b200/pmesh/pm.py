@@ -1,0 +1,653 @@
+"""
+`pmesh.pm` surface used by the FFTPower path, backed by libnbk_b200.so.
+
+  ParticleMesh(BoxSize, Nmesh, dtype, comm)   base/mesh.py:50
+     .paint(pos, mass=, resampler=, transform=, hold=, out=)   source/mesh/catalog.py:287-296
+     .decompose(pos, smoothing) -> Layout(.recvlength, .exchange)           :271-284
+     .affine.shift(0.5), .create(type=, value=), .reshape(Nmesh=), .x/.k/.w coordinate lists
+  RealField / ComplexField: device-resident fields with r2c/c2r, apply, slabs, csum/cmean ...
+
+Decomposition (P = comm.size GPUs): the real field is split in x slabs [x_start, x_start+x_n);
+the complex field that r2c leaves behind is split in y slabs and stored transposed,
+[y_n][Nx][Nzc] (`ComplexField.transposed`), exactly one NCCL all-to-all per transform.
+With P == 1 the complex field is the plain [Nx][Ny][Nzc] array.
+"""
+import ctypes
+import math
+
+import numpy
+import torch
+
+from .. import _lib
+from .._lib import F4, F8, check, darr, iarr, lib
+from . import window as _window
+
+_TORCH_REAL = {"f4": torch.float32, "f8": torch.float64}
+_TORCH_CPLX = {"f4": torch.complex64, "f8": torch.complex128}
+_CODE = {"f4": F4, "f8": F8}
+
+
+def _real_typestr(dtype):
+    """'f4'/'f8' for any real or complex dtype spec"""
+    dt = numpy.dtype(dtype)
+    if dt.kind == "c":
+        return "f4" if dt.itemsize == 8 else "f8"
+    if dt.kind == "f" and dt.itemsize in (4, 8):
+        return "f%d" % dt.itemsize
+    raise TypeError("unsupported mesh dtype %s" % str(dtype))
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else None)
+
+
+def current_device():
+    if not torch.cuda.is_available():
+        raise _lib.NbkError("nbodykit_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def as_device_tensor(a, dtype=None, device=None):
+    """numpy array / torch tensor / scalar column -> contiguous device tensor (no copy if already there)"""
+    device = device or current_device()
+    if isinstance(a, torch.Tensor):
+        t = a
+    else:
+        a = numpy.ascontiguousarray(a)
+        t = torch.from_numpy(a)
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device, non_blocking=True).contiguous()
+
+
+class Affine(object):
+    """pm.affine: grid = pos * scale + translate; .shift(s) adds s cells (catalog.py:292)"""
+
+    def __init__(self, ndim, scale, translate=0.0, period=None):
+        self.ndim = ndim
+        self.scale = scale
+        self.translate = translate
+        self.period = period
+
+    def shift(self, amount):
+        return Affine(self.ndim, self.scale, self.translate + amount, self.period)
+
+
+class Layout(object):
+    """result of pm.decompose: which local particles go to which rank (ghosts duplicated)"""
+
+    def __init__(self, comm, indices, sendcounts, recvcounts):
+        self.comm = comm
+        self.indices = indices            # device int64: local particle index per send slot, grouped by dest
+        self.sendcounts = sendcounts      # python ints, len P
+        self.recvcounts = recvcounts
+        self.sendlength = int(sum(sendcounts))
+        self.recvlength = int(sum(recvcounts))
+
+    def exchange(self, data):
+        """route a per-particle column (n, ...) -> (recvlength, ...).  Returns a new device tensor."""
+        t = as_device_tensor(data) if not isinstance(data, torch.Tensor) else data
+        if self.comm.size == 1 and self.indices is None:
+            return t
+        send = t.index_select(0, self.indices)
+        if self.comm.size == 1:
+            return send
+        out = torch.empty((self.recvlength,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.comm.all_to_all_single(out, send, list(self.recvcounts), list(self.sendcounts))
+        return out
+
+
+class ParticleMesh(object):
+    def __init__(self, BoxSize, Nmesh, dtype="f4", comm=None, np=None, plan_method=None, resampler="cic"):
+        from .. import CurrentMPIComm
+        self.comm = comm if comm is not None else CurrentMPIComm.get()
+        Nm = numpy.array(Nmesh)
+        ndim = 3 if Nm.ndim == 0 else len(Nm)
+        if ndim != 3:
+            raise NotImplementedError("only 3-D meshes are supported by the B200 FFTPower path")
+        self.Nmesh = numpy.empty(3, dtype="i8")
+        self.Nmesh[:] = Nmesh
+        self.BoxSize = numpy.empty(3, dtype="f8")
+        self.BoxSize[:] = BoxSize
+        self.ndim = 3
+        self._dtype_in = numpy.dtype(dtype)
+        if self._dtype_in.kind == "c":
+            raise NotImplementedError(
+                "complex-typed meshes (dtype='c8'/'c16', full c2c transforms) are not implemented; "
+                "use dtype='f4'/'f8' (Hermitian-compressed r2c), e.g. FKPCatalog.to_mesh(dtype='f8')")
+        self.dtype = numpy.dtype(_real_typestr(dtype))
+        self.typestr = _real_typestr(dtype)
+        self.resampler = _window.FindResampler(resampler)
+        self.affine = Affine(3, self.Nmesh / self.BoxSize, 0.0, self.Nmesh.copy())
+
+        P = self.comm.size
+        self.np = [P]
+        Nx, Ny, Nz = [int(v) for v in self.Nmesh]
+        if P > 1 and (Nx % P or Ny % P):
+            raise ValueError("Nmesh[0] and Nmesh[1] must be divisible by the number of GPUs (%d)" % P)
+        self.x_n = Nx // P
+        self.x_start = self.comm.rank * self.x_n
+        self.y_n = Ny // P
+        self.y_start = self.comm.rank * self.y_n
+        self.Nzc = Nz // 2 + 1
+        self.transposed = P > 1
+        self._nmesh_c = iarr(self.Nmesh)
+        self._box_c = darr(self.BoxSize)
+        self._coords = {}
+
+    # ---- shapes
+    @property
+    def real_shape(self):
+        return (self.x_n, int(self.Nmesh[1]), int(self.Nmesh[2]))
+
+    @property
+    def complex_shape(self):
+        if self.transposed:
+            return (self.y_n, int(self.Nmesh[0]), self.Nzc)
+        return (int(self.Nmesh[0]), int(self.Nmesh[1]), self.Nzc)
+
+    def reshape(self, Nmesh=None, BoxSize=None, dtype=None):
+        if Nmesh is None:
+            Nmesh = self.Nmesh
+        if BoxSize is None:
+            BoxSize = self.BoxSize
+        if dtype is None:
+            dtype = self.dtype
+        Nm = numpy.empty(3, dtype="i8")
+        Nm[:] = Nmesh
+        if (Nm == self.Nmesh).all() and numpy.allclose(BoxSize, self.BoxSize) and numpy.dtype(dtype) == self.dtype:
+            return self
+        return ParticleMesh(BoxSize=BoxSize, Nmesh=Nm, dtype=dtype, comm=self.comm)
+
+    def create(self, type=None, base=None, value=None, mode=None):
+        type = _typestr_to_type(type if type is not None else mode)
+        f = type(self)
+        if value is not None:
+            f[...] = value
+        return f
+
+    # ---- coordinates (host numpy, float32 by default: SURVEY B.5 / A12)
+    def create_coords(self, field_type, return_indices=False, dtype="f4"):
+        """three broadcastable host arrays for this rank's part of a real / complex field"""
+        ct = numpy.dtype(dtype).type
+        N = [int(v) for v in self.Nmesh]
+        out, ind = [], []
+        if field_type in ("real", RealField):
+            ranges = [numpy.arange(self.x_start, self.x_start + self.x_n), numpy.arange(N[1]), numpy.arange(N[2])]
+            for d in range(3):
+                i = ranges[d].copy()
+                i[i >= (N[d] + 1) // 2] -= N[d]      # wrapped to [-L/2, L/2)
+                x = i.astype(ct) * ct(self.BoxSize[d] / N[d])
+                shape = [1, 1, 1]; shape[d] = len(x)
+                out.append(x.reshape(shape)); ind.append(ranges[d].reshape(shape))
+        else:
+            if self.transposed:
+                # stored [y_n][Nx][Nzc]: the iteration axis 0 is y -- coordinate arrays follow STORAGE order
+                ranges = [numpy.arange(N[0]), numpy.arange(self.y_start, self.y_start + self.y_n), numpy.arange(self.Nzc)]
+                shapes = [(1, N[0], 1), (self.y_n, 1, 1), (1, 1, self.Nzc)]
+            else:
+                ranges = [numpy.arange(N[0]), numpy.arange(N[1]), numpy.arange(self.Nzc)]
+                shapes = [(N[0], 1, 1), (1, N[1], 1), (1, 1, self.Nzc)]
+            for d in range(3):
+                j = ranges[d].copy()
+                j[j >= (N[d] + 1) // 2] -= N[d]
+                k = j.astype(ct) * ct(2 * numpy.pi / self.BoxSize[d])
+                out.append(k.reshape(shapes[d])); ind.append(ranges[d].reshape(shapes[d]))
+        return (out, ind) if return_indices else out
+
+    @property
+    def x(self):
+        return self.create_coords("real")
+
+    @property
+    def k(self):
+        return self.create_coords("complex")
+
+    # ---- particle routing (source/mesh/catalog.py:271-284)
+    def decompose(self, pos, smoothing=None, transform=None):
+        """destination slab(s) of every particle: every rank whose x planes lie within `smoothing`
+        cells of the particle (ghosts duplicated, periodic)."""
+        P = self.comm.size
+        if smoothing is None:
+            smoothing = 0.5 * self.resampler.support
+        if P == 1:
+            n = int(pos.shape[0])
+            return Layout(self.comm, None, [n], [n])
+        pos = pos if isinstance(pos, torch.Tensor) else torch.as_tensor(numpy.asarray(pos))
+        Nx = int(self.Nmesh[0])
+        gx = pos[:, 0].to(torch.float64) * float(self.Nmesh[0] / self.BoxSize[0])
+        lo = torch.floor(gx - smoothing).to(torch.int64)
+        hi = torch.floor(gx + smoothing).to(torch.int64)
+        # slabs touched by cells lo..hi (at most 2 when smoothing < x_n, the only supported case)
+        if 2 * smoothing + 1 > self.x_n:
+            raise ValueError("x slab of %d planes is thinner than the window reach" % self.x_n)
+        r_lo = torch.remainder(lo, Nx) // self.x_n
+        r_hi = torch.remainder(hi, Nx) // self.x_n
+        idx = torch.arange(pos.shape[0], device=pos.device, dtype=torch.int64)
+        dup = r_hi != r_lo
+        dest = torch.cat([r_lo, r_hi[dup]])
+        src = torch.cat([idx, idx[dup]])
+        order = torch.argsort(dest, stable=True)
+        counts = torch.bincount(dest, minlength=P).cpu().tolist()
+        recv = self.comm.alltoall(counts)
+        return Layout(self.comm, src[order], counts, recv)
+
+    # ---- paint (source/mesh/catalog.py:287,295-296)
+    def paint(self, pos, mass=1.0, resampler=None, transform=None, hold=False, gradient=None, layout=None, out=None):
+        if gradient is not None:
+            raise NotImplementedError("gradient painting is not part of the FFTPower path")
+        if out is None:
+            out = RealField(self)
+            hold = False
+        if not isinstance(out, RealField):
+            raise TypeError("paint: `out` must be a RealField")
+        res = self.resampler if resampler is None else _window.FindResampler(resampler)
+        if res.code is None:
+            raise NotImplementedError("no CUDA scatter kernel for window '%s'" % res.name)
+        shift = 0.0
+        if transform is not None:
+            shift = float(numpy.atleast_1d(transform.translate - self.affine.translate).ravel()[0])
+        if layout is not None:
+            pos = layout.exchange(pos)
+            if not numpy.isscalar(mass):
+                mass = layout.exchange(mass)
+        dev = out.value.device
+        p = as_device_tensor(pos, device=dev)
+        if p.dtype not in (torch.float32, torch.float64):
+            p = p.to(torch.float64)
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise ValueError("paint: position must have shape (n, 3)")
+        m = None
+        scale_after = None
+        if numpy.isscalar(mass):
+            if float(mass) != 1.0:
+                scale_after = float(mass)
+        else:
+            m = as_device_tensor(mass, device=dev)
+            if m.dtype not in (torch.float32, torch.float64):
+                m = m.to(torch.float64)
+            if m.shape[0] != p.shape[0]:
+                raise ValueError("paint: mass and position length mismatch")
+        if not hold:
+            out[...] = 0
+        target = out
+        if scale_after is not None:
+            target = RealField(self)
+            target[...] = 0
+        check(lib().nbk_paint(_ptr(p), F4 if p.dtype == torch.float32 else F8, p.shape[0],
+                              _ptr(m), (F4 if m.dtype == torch.float32 else F8) if m is not None else F8,
+                              res.code, shift, self._box_c, self._nmesh_c, self.x_start, self.x_n,
+                              _ptr(target.value), _CODE[self.typestr], _stream()), "nbk_paint")
+        if scale_after is not None:
+            out.axpy(target, scale_after)
+        return out
+
+    def paint_interlaced(self, pos, mass, resampler, out1, out2):
+        """both meshes of the interlaced branch (catalog.py:289-296) in one pass over the particles"""
+        res = _window.FindResampler(resampler)
+        if res.code is None:
+            raise NotImplementedError("no CUDA scatter kernel for window '%s'" % res.name)
+        dev = out1.value.device
+        p = as_device_tensor(pos, device=dev)
+        if p.dtype not in (torch.float32, torch.float64):
+            p = p.to(torch.float64)
+        m = None
+        if mass is not None and not numpy.isscalar(mass):
+            m = as_device_tensor(mass, device=dev)
+            if m.dtype not in (torch.float32, torch.float64):
+                m = m.to(torch.float64)
+        check(lib().nbk_paint_interlaced(_ptr(p), F4 if p.dtype == torch.float32 else F8, p.shape[0],
+                                         _ptr(m), (F4 if m.dtype == torch.float32 else F8) if m is not None else F8,
+                                         res.code, self._box_c, self._nmesh_c, self.x_start, self.x_n,
+                                         _ptr(out1.value), _ptr(out2.value), _CODE[self.typestr], _stream()),
+              "nbk_paint_interlaced")
+
+    def cell_index(self, pos, resampler="cic", shift=0.0):
+        """wrapped leftmost stencil cell of every particle, (n,3) int32 device tensor"""
+        res = _window.FindResampler(resampler)
+        p = as_device_tensor(pos)
+        out = torch.empty((p.shape[0], 3), dtype=torch.int32, device=p.device)
+        check(lib().nbk_cell_index(_ptr(p), F4 if p.dtype == torch.float32 else F8, p.shape[0], res.code,
+                                   float(shift), self._box_c, self._nmesh_c, _ptr(out), _stream()), "nbk_cell_index")
+        return out
+
+
+class _Slabs(object):
+    """field.slabs: iterate over planes of the first stored axis; .x / .i / .optx give per-plane coords"""
+
+    def __init__(self, field):
+        self.field = field
+
+    def __len__(self):
+        return self.field.value.shape[0]
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self.field.value[i]
+
+    def _coords(self, want_index):
+        f = self.field
+        kind = "real" if isinstance(f, RealField) else "complex"
+        xs, ind = f.pm.create_coords(kind, return_indices=True)
+        src = ind if want_index else xs
+        ax0 = self._axis0()
+        for i in range(len(self)):
+            yield [src[d][i] if d == ax0 else src[d][0] for d in range(3)]
+
+    def _axis0(self):
+        """physical dimension that runs along the first STORED axis"""
+        f = self.field
+        return 1 if (isinstance(f, ComplexField) and f.pm.transposed) else 0
+
+    @property
+    def x(self):
+        return self._coords(False)
+
+    @property
+    def optx(self):
+        return self._coords(False)
+
+    @property
+    def i(self):
+        return self._coords(True)
+
+
+class Field(object):
+    """base of RealField / ComplexField: a device tensor + its ParticleMesh"""
+
+    def __init__(self, pm, value=None):
+        self.pm = pm
+        self.attrs = {}
+        shape, tdt = self._layout(pm)
+        if value is None:
+            value = torch.empty(shape, dtype=tdt, device=current_device())
+        self.value = value
+
+    # -- pmesh-compatible members
+    @property
+    def Nmesh(self):
+        return self.pm.Nmesh
+
+    @property
+    def BoxSize(self):
+        return self.pm.BoxSize
+
+    @property
+    def shape(self):
+        return tuple(self.value.shape)
+
+    @property
+    def cshape(self):
+        N = [int(v) for v in self.pm.Nmesh]
+        return tuple(N) if isinstance(self, RealField) else (N[0], N[1], self.pm.Nzc)
+
+    @property
+    def size(self):
+        return self.value.numel()
+
+    @property
+    def csize(self):
+        return int(numpy.prod(self.cshape))
+
+    @property
+    def slabs(self):
+        return _Slabs(self)
+
+    @property
+    def x(self):
+        return self.pm.create_coords("real" if isinstance(self, RealField) else "complex")
+
+    def _flat_real(self):
+        v = self.value
+        return torch.view_as_real(v).reshape(-1) if v.is_complex() else v.reshape(-1)
+
+    def __getitem__(self, idx):
+        return self.value[idx]
+
+    def __setitem__(self, idx, val):
+        whole = idx is Ellipsis or (isinstance(idx, slice) and idx == slice(None))
+        if whole and numpy.isscalar(val) and not isinstance(val, complex):
+            flat = self._flat_real()
+            if self.value.is_complex():
+                # real scalar into a complex field: fill real part, zero imaginary
+                if float(val) == 0.0:
+                    check(lib().nbk_fill(_ptr(flat), _CODE[self.pm.typestr], flat.numel(), 0.0, _stream()), "nbk_fill")
+                else:
+                    self.value[...] = val
+            else:
+                check(lib().nbk_fill(_ptr(flat), _CODE[self.pm.typestr], flat.numel(), float(val), _stream()), "nbk_fill")
+            return
+        if isinstance(val, Field):
+            val = val.value
+        elif isinstance(val, numpy.ndarray):
+            val = torch.from_numpy(val).to(self.value.device)
+        self.value[idx] = val
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.value.detach().cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def numpy(self):
+        return self.__array__()
+
+    def copy(self):
+        out = type(self)(self.pm, self.value.clone())
+        out.attrs = dict(self.attrs)
+        return out
+
+    # -- in-place arithmetic on the whole field (kernels in csrc/core.cu)
+    def scale(self, a):
+        flat = self._flat_real()
+        check(lib().nbk_scale(_ptr(flat), _CODE[self.pm.typestr], flat.numel(), float(a), _stream()), "nbk_scale")
+        return self
+
+    def axpy(self, other, a=1.0):
+        """self += a * other"""
+        flat = self._flat_real()
+        o = other._flat_real()
+        if o.numel() != flat.numel():
+            raise ValueError("field shape mismatch")
+        check(lib().nbk_axpy(_ptr(flat), _ptr(o), _CODE[self.pm.typestr], flat.numel(), float(a), _stream()), "nbk_axpy")
+        return self
+
+    def __imul__(self, a):
+        if numpy.isscalar(a) and not isinstance(a, complex):
+            return self.scale(a)
+        self.value *= (a.value if isinstance(a, Field) else a)
+        return self
+
+    def __itruediv__(self, a):
+        if numpy.isscalar(a) and not isinstance(a, complex):
+            return self.scale(1.0 / a)
+        self.value /= (a.value if isinstance(a, Field) else a)
+        return self
+
+    def __iadd__(self, a):
+        if isinstance(a, Field):
+            return self.axpy(a, 1.0)
+        self.value += a
+        return self
+
+    def __isub__(self, a):
+        if isinstance(a, Field):
+            return self.axpy(a, -1.0)
+        self.value -= a
+        return self
+
+    def csum(self):
+        """collective sum of all elements (catalog.py:388)"""
+        if self.value.is_complex():
+            return complex(self.pm.comm.allreduce(complex(self.value.sum().item())))
+        acc = torch.zeros(1, dtype=torch.float64, device=self.value.device)
+        flat = self._flat_real()
+        check(lib().nbk_sum(_ptr(flat), _CODE[self.pm.typestr], flat.numel(), _ptr(acc), _stream()), "nbk_sum")
+        return float(self.pm.comm.allreduce(acc.item()))
+
+    def cmean(self):
+        return self.csum() / float(numpy.prod(self.cshape if isinstance(self, RealField) else self.pm.Nmesh))
+
+    def cast(self, type=None, out=None):
+        type = _typestr_to_type(type) if type is not None else self.__class__
+        if isinstance(self, type):
+            return self
+        if issubclass(type, BaseComplexField):
+            return self.r2c(out=None if out is self else out)
+        return self.c2r(out=None if out is self else out)
+
+    def apply(self, func, kind="wavenumber", out=None):
+        """apply func(coords, value) plane by plane (contract: base/mesh.py:126-145).
+
+        The reference's own window-compensation transfer functions run as one CUDA pass
+        (nbk_compensate).  Any other Python callback is evaluated the way pmesh evaluates it -- as
+        host NumPy code, one x-plane at a time -- because it *is* host code."""
+        if out is Ellipsis or out is self:
+            target = self
+        elif out is None:
+            target = self.copy()
+        else:
+            target = out
+            target.value.copy_(self.value)
+        name = getattr(func, "__name__", "")
+        if isinstance(target, ComplexField) and kind == "circular" and name in _lib.COMP \
+                and getattr(func, "__module__", "").startswith("nbodykit_b200"):
+            target.compensate(name)
+            return target
+        target._apply_host(func, kind)
+        return target
+
+    def _apply_host(self, func, kind):
+        pm = self.pm
+        is_real = isinstance(self, RealField)
+        coords, ind = pm.create_coords("real" if is_real else "complex", return_indices=True)
+        N = [float(v) for v in pm.Nmesh]
+        if kind == "index":
+            use = ind
+        elif kind == "relative" and is_real:
+            use = coords
+        elif kind == "circular" and not is_real:
+            order = [0, 1, 2]
+            use = [(c.astype("f8") * (pm.BoxSize[d] / N[d])).astype(c.dtype) for d, c in zip(order, coords)]
+        elif kind in ("wavenumber", "relative"):
+            use = coords
+        else:
+            raise ValueError("unknown kind %s" % kind)
+        ax0 = self.slabs._axis0()
+        for i in range(self.value.shape[0]):
+            plane = self.value[i].cpu().numpy()
+            cs = [c[i:i + 1] if d == ax0 else c for d, c in enumerate(use)]
+            res = numpy.asarray(func(cs, plane[None, ...]))[0]
+            self.value[i] = torch.from_numpy(numpy.ascontiguousarray(res.astype(plane.dtype))).to(self.value.device)
+
+
+class RealField(Field):
+    @staticmethod
+    def _layout(pm):
+        return pm.real_shape, _TORCH_REAL[pm.typestr]
+
+    @property
+    def dtype(self):
+        return self.pm.dtype
+
+    def r2c(self, out=None):
+        """forward FFT, normalised by 1/prod(N).  out=Ellipsis has no in-place meaning here (the
+        transform is out of place); the real buffer stays valid."""
+        pm = self.pm
+        if out is None or out is Ellipsis:
+            out = ComplexField(pm)
+        code = _CODE[pm.typestr]
+        P = pm.comm.size
+        Nx, Ny, Nz = [int(v) for v in pm.Nmesh]
+        if P == 1:
+            check(lib().nbk_r2c(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, _stream()), "nbk_r2c")
+        else:
+            Nzc = pm.Nzc
+            work = torch.empty((pm.x_n, Ny, Nzc), dtype=out.value.dtype, device=out.value.device)
+            send = torch.empty_like(work)
+            check(lib().nbk_fft_zy_forward(_ptr(self.value), _ptr(work), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_forward")
+            check(lib().nbk_transpose_pack(_ptr(work), _ptr(send), code, pm.x_n, Ny, Nzc, P, _stream()), "transpose_pack")
+            recv = work.view(-1)
+            pm.comm.all_to_all_single(recv, send.view(-1))
+            check(lib().nbk_transpose_unpack(_ptr(recv), _ptr(out.value), code, pm.y_n, Nx, Nzc, P, _stream()), "transpose_unpack")
+            scale = 1.0 / (float(Nx) * Ny * Nz)
+            check(lib().nbk_fft_lines(_ptr(out.value), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 0, scale, _stream()), "fft_lines(x)")
+        out.attrs = dict(self.attrs)
+        return out
+
+
+class BaseComplexField(Field):
+    pass
+
+
+class ComplexField(BaseComplexField):
+    compressed = True     # Hermitian-compressed last axis (fftpower.py:572)
+
+    @staticmethod
+    def _layout(pm):
+        return pm.complex_shape, _TORCH_CPLX[pm.typestr]
+
+    @property
+    def dtype(self):
+        return numpy.dtype("c8" if self.pm.typestr == "f4" else "c16")
+
+    @property
+    def transposed(self):
+        return self.pm.transposed
+
+    def _slab(self):
+        pm = self.pm
+        return (1, pm.y_start, pm.y_n) if pm.transposed else (0, 0, int(pm.Nmesh[0]))
+
+    def c2r(self, out=None):
+        """backward FFT, unnormalised.  The complex buffer is preserved."""
+        pm = self.pm
+        if out is None or out is Ellipsis:
+            out = RealField(pm)
+        code = _CODE[pm.typestr]
+        P = pm.comm.size
+        Nx, Ny, Nz = [int(v) for v in pm.Nmesh]
+        work = torch.empty_like(self.value)
+        if P == 1:
+            check(lib().nbk_c2r(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, _ptr(work), _stream()), "nbk_c2r")
+        else:
+            Nzc = pm.Nzc
+            work.copy_(self.value)
+            check(lib().nbk_fft_lines(_ptr(work), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 1, 1.0, _stream()), "fft_lines(x)")
+            send = torch.empty_like(work)
+            check(lib().nbk_transpose_pack_back(_ptr(work), _ptr(send), code, pm.y_n, Nx, Nzc, P, _stream()), "pack_back")
+            recv = work.view(-1)
+            pm.comm.all_to_all_single(recv, send.view(-1))
+            slab = send.view(-1)
+            check(lib().nbk_transpose_unpack_back(_ptr(recv), _ptr(slab), code, pm.x_n, Ny, Nzc, P, _stream()), "unpack_back")
+            check(lib().nbk_fft_zy_backward(_ptr(slab), _ptr(out.value), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_backward")
+        out.attrs = dict(self.attrs)
+        return out
+
+    def compensate(self, name):
+        """v /= window transfer function (source/mesh/catalog.py:449-594), in place"""
+        pm = self.pm
+        tr, start, count = self._slab()
+        check(lib().nbk_compensate(_ptr(self.value), _CODE[pm.typestr], _lib.COMP[name], pm._nmesh_c, tr, start, count,
+                                   _stream()), "nbk_compensate")
+        return self
+
+    def interlace_combine(self, other):
+        """self = 0.5 self + 0.5 other exp(0.5j k.H)  (source/mesh/catalog.py:345-347)"""
+        pm = self.pm
+        tr, start, count = self._slab()
+        check(lib().nbk_interlace_combine(_ptr(self.value), _ptr(other.value), _CODE[pm.typestr], pm._nmesh_c, pm._box_c,
+                                          tr, start, count, _stream()), "nbk_interlace_combine")
+        return self
+
+
+def _typestr_to_type(typestr):
+    if typestr in (RealField, ComplexField):
+        return typestr
+    if typestr in ("real", None):
+        return RealField
+    if typestr in ("complex", "transposedcomplex", "untransposedcomplex"):
+        return ComplexField
+    raise ValueError("unknown field type %s" % str(typestr))

@@ -1,0 +1,262 @@
+"""
+Parity of each CUDA kernel (through the C ABI, via the pmesh shim) against the CPU oracle.
+Bit-exact for indices and mode counts; float tolerances are written at each assert.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pmesh_oracle as po
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _pm(N, L, dtype):
+    from nbodykit_b200.pmesh.pm import ParticleMesh
+    from nbodykit_b200.comm import SelfComm
+    return ParticleMesh(BoxSize=L, Nmesh=N, dtype=dtype, comm=SelfComm())
+
+
+def _particles(n, L, dtype, seed=7, outside=True):
+    rng = np.random.RandomState(seed)
+    pos = rng.uniform(0, 1, size=(n, 3)) * np.asarray(L)
+    if outside:  # a few particles outside the box and exactly on nodes / the upper edge: wrap semantics
+        pos[:5] += np.asarray(L)
+        pos[5:10] -= np.asarray(L) * 2
+        pos[10] = 0.0
+        pos[11] = np.asarray(L) * (1 - 1e-12)
+        pos[12] = np.asarray(L) / 2
+    return pos.astype(dtype)
+
+
+@pytest.mark.parametrize("resampler", ["nnb", "cic", "tsc", "pcs"])
+@pytest.mark.parametrize("pos_dtype", ["f4", "f8"])
+@pytest.mark.parametrize("shift", [0.0, 0.5])
+def test_cell_index_bit_exact(cuda, resampler, pos_dtype, shift):
+    N, L = [32, 16, 64], [100., 50., 731.]
+    pos = _particles(20000, L, pos_dtype)
+    pm = _pm(N, L, "f8")
+    got = pm.cell_index(pos, resampler, shift).cpu().numpy()
+    want = po.cell_index(pos, N, L, resampler, shift)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("resampler", ["nnb", "cic", "tsc", "pcs"])
+@pytest.mark.parametrize("mesh_dtype,pos_dtype,tol", [("f8", "f8", 1e-12), ("f8", "f4", 1e-12), ("f4", "f4", 2e-5)])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_paint_vs_oracle(cuda, resampler, mesh_dtype, pos_dtype, tol, weighted):
+    N, L = [16, 32, 8], [64., 128., 10.]
+    pos = _particles(30000, L, pos_dtype)
+    mass = np.random.RandomState(3).uniform(0.5, 1.5, size=len(pos)) if weighted else None
+    pm = _pm(N, L, mesh_dtype)
+    got = pm.paint(pos, mass=mass if weighted else 1.0, resampler=resampler).numpy()
+    want = po.paint(pos, mass, N, L, resampler, dtype="f8")
+    # mass is conserved and every cell agrees: |diff| <= tol * max cell (f4: order-dependent adds)
+    assert got.dtype == np.dtype(mesh_dtype)
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol * want.max())
+    np.testing.assert_allclose(got.sum(dtype="f8"), (mass.sum() if weighted else len(pos)), rtol=1e-6)
+
+
+def test_paint_hold_shift_and_scalar_mass(cuda):
+    N, L = 16, 32.
+    pos = _particles(5000, [L] * 3, "f8")
+    pm = _pm(N, L, "f8")
+    from nbodykit_b200.pmesh.pm import RealField
+    out = RealField(pm)
+    out[...] = 1.0
+    pm.paint(pos, mass=2.5, resampler="tsc", transform=pm.affine.shift(0.5), hold=True, out=out)
+    want = 1.0 + 2.5 * po.paint(pos, None, N, L, "tsc", shift=0.5)
+    np.testing.assert_allclose(out.numpy(), want, rtol=0, atol=1e-12 * want.max())
+
+
+def test_paint_slab_drops_ghost_planes(cuda):
+    """x_start/x_n: stencil points outside the slab are dropped (pmesh ghost semantics)"""
+    import ctypes
+    import torch
+    from nbodykit_b200 import _lib
+    N, L = [16, 8, 8], [16., 8., 8.]
+    pos = _particles(4000, L, "f8")
+    full = po.paint(pos, None, N, L, "tsc")
+    p = torch.from_numpy(pos).cuda()
+    for x0, xn in [(0, 4), (4, 4), (12, 4), (5, 11)]:
+        mesh = torch.zeros((xn, 8, 8), dtype=torch.float64, device="cuda")
+        _lib.check(_lib.lib().nbk_paint(ctypes.c_void_p(p.data_ptr()), 8, len(pos), None, 8, 3, 0.0, _lib.darr(L),
+                                        _lib.iarr(N), x0, xn, ctypes.c_void_p(mesh.data_ptr()), 8, None))
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(mesh.cpu().numpy(), full[x0:x0 + xn], rtol=0, atol=1e-12 * full.max())
+
+
+def test_paint_empty(cuda):
+    pm = _pm(8, 1.0, "f4")
+    out = pm.paint(np.empty((0, 3), dtype="f4"), resampler="cic")
+    assert float(out.numpy().sum()) == 0.0
+
+
+def test_paint_interlaced_pair(cuda):
+    from nbodykit_b200.pmesh.pm import RealField
+    N, L = 16, 100.
+    pos = _particles(8000, [L] * 3, "f4")
+    pm = _pm(N, L, "f4")
+    r1, r2 = RealField(pm), RealField(pm)
+    r1[...] = 0; r2[...] = 0
+    pm.paint_interlaced(pos, None, "cic", r1, r2)
+    w1 = po.paint(pos, None, N, L, "cic", 0.0)
+    w2 = po.paint(pos, None, N, L, "cic", 0.5)
+    np.testing.assert_allclose(r1.numpy(), w1, rtol=0, atol=2e-5 * w1.max())
+    np.testing.assert_allclose(r2.numpy(), w2, rtol=0, atol=2e-5 * w2.max())
+
+
+@pytest.mark.parametrize("N", [[8, 8, 8], [16, 32, 64], [64, 16, 4], [128, 128, 128], [2, 4, 8]])
+@pytest.mark.parametrize("dtype,tol", [("f8", 1e-13), ("f4", 2e-6)])
+def test_r2c_c2r(cuda, N, dtype, tol):
+    from nbodykit_b200.pmesh.pm import RealField
+    rng = np.random.RandomState(5)
+    real = rng.standard_normal(N).astype(dtype)
+    pm = _pm(N, 1.0, dtype)
+    f = RealField(pm)
+    f[...] = real
+    c = f.r2c()
+    want = np.fft.rfftn(real.astype("f8")) / real.size
+    got = c.numpy()
+    assert got.shape == want.shape
+    # tolerance relative to the rms amplitude of the spectrum
+    assert np.abs(got - want).max() <= tol * np.sqrt((np.abs(want) ** 2).mean()) * np.log2(real.size)
+    back = c.c2r().numpy()
+    assert np.abs(back - real).max() <= tol * 10 * np.log2(real.size)
+    # the complex input of c2r is preserved
+    np.testing.assert_array_equal(c.numpy(), got)
+
+
+@pytest.mark.parametrize("name", sorted(["CompensateCIC", "CompensateTSC", "CompensatePCS", "CompensateCICShotnoise",
+                                         "CompensateTSCShotnoise", "CompensatePCSShotnoise"]))
+@pytest.mark.parametrize("dtype,tol", [("f8", 5e-7), ("f4", 2e-6)])
+def test_compensate(cuda, name, dtype, tol):
+    """oracle forms the factors in float32 (reference dtype flow); the kernel in f8 -> 1e-7-level agreement"""
+    from nbodykit_b200.pmesh.pm import ComplexField
+    N, L = [16, 8, 32], [10., 20., 30.]
+    rng = np.random.RandomState(2)
+    shape = (N[0], N[1], N[2] // 2 + 1)
+    c = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype("c8" if dtype == "f4" else "c16")
+    pm = _pm(N, L, dtype)
+    f = ComplexField(pm)
+    f[...] = c
+    f.compensate(name)
+    want = po.compensate(name, po.k_coords(N, L, "f4", kind="circular"), c)
+    np.testing.assert_allclose(f.numpy(), want, rtol=tol, atol=0)
+    # and against exact f8 factors: tight
+    want8 = po.compensate(name, po.k_coords(N, L, "f8", kind="circular"), c.astype("c16"))
+    np.testing.assert_allclose(f.numpy(), want8, rtol=1e-13 if dtype == "f8" else 2e-7, atol=0)
+
+
+@pytest.mark.parametrize("dtype,tol", [("f8", 1e-13), ("f4", 3e-7)])
+def test_interlace_combine(cuda, dtype, tol):
+    from nbodykit_b200.pmesh.pm import ComplexField
+    N, L = [8, 16, 32], [10., 20., 30.]
+    rng = np.random.RandomState(4)
+    shape = (N[0], N[1], N[2] // 2 + 1)
+    cd = "c8" if dtype == "f4" else "c16"
+    c1 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cd)
+    c2 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cd)
+    pm = _pm(N, L, dtype)
+    f1, f2 = ComplexField(pm), ComplexField(pm)
+    f1[...] = c1; f2[...] = c2
+    f1.interlace_combine(f2)
+    want = po.interlace_combine(c1.astype("c16"), c2.astype("c16"), N, L, "f8")
+    assert np.abs(f1.numpy() - want).max() <= tol * 4
+
+
+def _bin(pm, c, edges, los, poles, coord="f4", is_p3d=True, c2=None, volume=1.0):
+    from nbodykit_b200.algorithms.fftpower import project_to_basis_device
+    from nbodykit_b200.pmesh.pm import ComplexField
+    f = ComplexField(pm)
+    f[...] = c
+    g = None
+    if c2 is not None:
+        g = ComplexField(pm)
+        g[...] = c2
+    return project_to_basis_device(f, edges, los=los, poles=poles, coord_dtype=coord, is_p3d=is_p3d, second=g,
+                                   volume=volume)
+
+
+@pytest.mark.parametrize("N,L", [([16, 16, 16], 64.), ([8, 16, 32], [10., 20., 30.]), ([32, 32, 32], 1024.)])
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+@pytest.mark.parametrize("Nmu,poles,los", [(1, [], [0, 0, 1]), (5, [0, 2, 4], [0, 0, 1]), (4, [1, 2], [0, 1, 0]),
+                                           (3, [2], [0.6, 0, 0.8])])
+@pytest.mark.parametrize("coord", ["f4", "f8"])
+def test_power_bin_vs_oracle(cuda, N, L, dtype, Nmu, poles, los, coord):
+    rng = np.random.RandomState(11)
+    shape = (N[0], N[1], N[2] // 2 + 1)
+    c = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype("c8" if dtype == "f4" else "c16")
+    Lv = np.ones(3) * L
+    dk = 2 * np.pi / Lv.min()
+    kedges = np.arange(0., np.pi * min(N) / Lv.max() + dk / 2, dk)
+    muedges = np.linspace(-1, 1, Nmu + 1)
+    pm = _pm(N, L, dtype)
+    res, pres = _bin(pm, c, [kedges, muedges], los, poles, coord)
+    ores, opres = po.project_to_basis(c, po.k_coords(N, L, coord), [kedges, muedges], los=los, poles=poles)
+    # mode counts: bit-exact
+    assert np.array_equal(res[3], ores[3])
+    tol = 1e-12 if dtype == "f8" else 2e-6
+    for a, b in zip(res[:3], ores[:3]):
+        assert np.array_equal(np.isnan(a), np.isnan(b))
+        np.testing.assert_allclose(np.nan_to_num(a), np.nan_to_num(b), rtol=tol, atol=tol * np.nanmax(np.abs(b)))
+    if poles:
+        assert np.array_equal(pres[2], opres[2])
+        np.testing.assert_allclose(np.nan_to_num(pres[0]), np.nan_to_num(opres[0]), rtol=tol)
+        np.testing.assert_allclose(np.nan_to_num(pres[1]), np.nan_to_num(opres[1]), rtol=tol,
+                                   atol=tol * np.nanmax(np.abs(opres[1])))
+
+
+def test_power_bin_cross_and_zero_mode(cuda):
+    """c1*conj(c2)*V with the k=0 mode cleared (fftpower.py:115-128) fused into the binning pass"""
+    N, L = [16, 16, 16], 100.
+    rng = np.random.RandomState(12)
+    shape = (16, 16, 9)
+    c1 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+    c2 = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape))
+    V = L ** 3
+    p3d = c1 * np.conj(c2)
+    p3d[0, 0, 0] = 0
+    p3d *= V
+    dk = 2 * np.pi / L
+    kedges = np.arange(0., np.pi * 16 / L + dk / 2, dk)
+    muedges = np.linspace(-1, 1, 6)
+    pm = _pm(N, L, "f8")
+    res, pres = _bin(pm, c1, [kedges, muedges], [0, 0, 1], [0, 2], "f4", is_p3d=False, c2=c2, volume=V)
+    ores, opres = po.project_to_basis(p3d, po.k_coords(N, L, "f4"), [kedges, muedges], poles=[0, 2])
+    assert np.array_equal(res[3], ores[3])
+    np.testing.assert_allclose(np.nan_to_num(res[2]), np.nan_to_num(ores[2]), rtol=1e-12, atol=1e-12 * V)
+    np.testing.assert_allclose(np.nan_to_num(pres[1]), np.nan_to_num(opres[1]), rtol=1e-12, atol=1e-12 * V)
+
+
+def test_shell_counts_match_reference_fixture(cuda):
+    """known-answer: k-marginal mode counts of nbodykit/tests/data/dataset_2d.json (128^3, L=512, dk=k_f)"""
+    gold = json.load(open(os.path.join(GOLD, "dataset_2d_modes.json")))
+    N, L = gold["Nmesh"], gold["BoxSize"]
+    dk = 2 * np.pi / L
+    kedges = np.arange(0., np.pi * N / L + dk / 2, dk)
+    pm = _pm(N, L, "f4")
+    c = np.ones((N, N, N // 2 + 1), dtype="c8")
+    res, _ = _bin(pm, c, [kedges, np.linspace(-1, 1, 2)], [0, 0, 1], [], "f4")
+    assert res[3][:, 0].tolist() == gold["modes_k"]
+    # and through 5 mu bins the k-marginal is unchanged
+    res5, _ = _bin(pm, c, [kedges, np.linspace(-1, 1, 6)], [0, 0, 1], [], "f4")
+    assert res5[3].sum(axis=1).tolist() == gold["modes_k"]
+
+
+def test_elementwise_and_sums(cuda):
+    from nbodykit_b200.pmesh.pm import RealField
+    pm = _pm([8, 4, 6], 1.0, "f4")   # 192 elements: exercises vector body; odd sizes below the tail
+    f = RealField(pm)
+    f[...] = 2.0
+    f *= 1.5
+    g = f.copy()
+    g /= 3.0
+    f += g
+    assert np.allclose(f.numpy(), 4.0)
+    assert abs(f.csum() - 4.0 * 192) < 1e-9
+    assert abs(f.cmean() - 4.0) < 1e-12
