@@ -75,6 +75,19 @@ int nbk_paint_interlaced(const void *pos, int pos_dtype, int64_t n, const void *
                          const int64_t *nmesh_host, int64_t x_start, int64_t x_n, void *mesh1,
                          void *mesh2, int mesh_dtype, void *stream);
 
+/* The same scatter through the tile-sorted path: particles are bucketed by 16^3-cell tile, each tile is
+ * accumulated in shared memory in 64-bit fixed point (order-independent, resolution 2^-31 of the largest
+ * |mass|) and flushed once.  mesh2 != NULL paints the +0.5-cell shifted mesh of the interlaced branch from
+ * the same buckets (then shift must be 0).  `work`: device scratch of nbk_paint_tiled_workspace() bytes.
+ * nbk_paint_tiled_supported() says whether the mesh admits the tiling (sides multiples of 16, >= 32). */
+int nbk_paint_tiled_supported(const int64_t *nmesh_host, int64_t x_n, int window);
+int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_dtype, const int64_t *nmesh_host,
+                                  int64_t x_n);
+int nbk_paint_tiled(const void *pos, int pos_dtype, int64_t n, const void *mass, int mass_dtype, int window,
+                    double shift, const double *boxsize_host, const int64_t *nmesh_host, int64_t x_start,
+                    int64_t x_n, void *mesh, void *mesh2, int mesh_dtype, void *work, int64_t work_bytes,
+                    void *stream);
+
 /* leftmost stencil cell (wrapped) of every particle, [n][3] int32 -- the bit-exact part of the
  * paint contract, exported for parity tests and for pm.decompose (catalog.py:271-273) */
 int nbk_cell_index(const void *pos, int pos_dtype, int64_t n, int window, double shift,

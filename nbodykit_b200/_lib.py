@@ -33,6 +33,9 @@ SIGNATURES = {
     "nbk_launch_count": ([], _i64),
     "nbk_paint": ([_vp, _i, _i64, _vp, _i, _i, _d, _pd, _pi64, _i64, _i64, _vp, _i, _vp], _i),
     "nbk_paint_interlaced": ([_vp, _i, _i64, _vp, _i, _i, _pd, _pi64, _i64, _i64, _vp, _vp, _i, _vp], _i),
+    "nbk_paint_tiled_supported": ([_pi64, _i64, _i], _i),
+    "nbk_paint_tiled_workspace": ([_i64, _i, _i, _pi64, _i64], _i64),
+    "nbk_paint_tiled": ([_vp, _i, _i64, _vp, _i, _i, _d, _pd, _pi64, _i64, _i64, _vp, _vp, _i, _vp, _i64, _vp], _i),
     "nbk_cell_index": ([_vp, _i, _i64, _i, _d, _pd, _pi64, _vp, _vp], _i),
     "nbk_sum_w_w2": ([_vp, _i, _i64, _vp, _vp], _i),
     "nbk_r2c": ([_vp, _vp, _i, _pi64, _vp], _i),
@@ -92,3 +95,52 @@ def i32arr(x):
 
 def launch_count():
     return int(lib().nbk_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------
+# optional per-stage device timing (CUDA events on the launching stream); used by bench.py to
+# attribute time inside the timed region to individual kernels.  Off by default: zero overhead.
+# ---------------------------------------------------------------------------------------------
+class _Profiler(object):
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def start(self):
+        self.enabled = True
+        self.records = []
+
+    def stop(self):
+        """synchronise and return {name: [ms, ...]}"""
+        import torch
+        self.enabled = False
+        torch.cuda.synchronize()
+        out = {}
+        for name, a, b in self.records:
+            out.setdefault(name, []).append(a.elapsed_time(b))
+        self.records = []
+        return out
+
+
+profiler = _Profiler()
+
+
+class stage(object):
+    """with stage('paint'): ...  -- records a CUDA event pair when profiling is on"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if profiler.enabled:
+            import torch
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if profiler.enabled:
+            self.b.record()
+            profiler.records.append((self.name, self.a, self.b))
+        return False

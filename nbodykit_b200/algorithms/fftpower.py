@@ -18,7 +18,7 @@ import numpy
 import torch
 
 from .. import CurrentMPIComm, _lib
-from .._lib import check, lib
+from .._lib import check, lib, stage
 from ..binned_statistic import BinnedStatistic
 from ..base.catalog import CatalogSourceBase
 from ..base.mesh import MeshSource
@@ -242,11 +242,12 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     ysum = facc[2 * nb:]
     tr, start, count = y3d._slab()
     los_f = [float(v) for v in los]
-    check(lib().nbk_power_bin(
-        _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
-        1 if is_p3d else 0, float(volume), 1, pm._nmesh_c, pm._box_c, tr, start, count,
-        _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
-        _lib.i32arr(_poles), Nell, 1, _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
+    with stage("power_bin"):
+        check(lib().nbk_power_bin(
+            _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
+            1 if is_p3d else 0, float(volume), 1, pm._nmesh_c, pm._box_c, tr, start, count,
+            _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
+            _lib.i32arr(_poles), Nell, 1, _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
     if comm.size > 1:
         comm.allreduce_tensor(nsum)
         comm.allreduce_tensor(facc)

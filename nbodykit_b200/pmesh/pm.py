@@ -19,7 +19,7 @@ import numpy
 import torch
 
 from .. import _lib
-from .._lib import F4, F8, check, darr, iarr, lib
+from .._lib import F4, F8, check, darr, iarr, lib, stage
 from . import window as _window
 
 _TORCH_REAL = {"f4": torch.float32, "f8": torch.float64}
@@ -237,7 +237,8 @@ class ParticleMesh(object):
         return Layout(self.comm, src[order], counts, recv)
 
     # ---- paint (source/mesh/catalog.py:287,295-296)
-    def paint(self, pos, mass=1.0, resampler=None, transform=None, hold=False, gradient=None, layout=None, out=None):
+    def paint(self, pos, mass=1.0, resampler=None, transform=None, hold=False, gradient=None, layout=None, out=None,
+              method=None):
         if gradient is not None:
             raise NotImplementedError("gradient painting is not part of the FFTPower path")
         if out is None:
@@ -278,15 +279,12 @@ class ParticleMesh(object):
         if scale_after is not None:
             target = RealField(self)
             target[...] = 0
-        check(lib().nbk_paint(_ptr(p), F4 if p.dtype == torch.float32 else F8, p.shape[0],
-                              _ptr(m), (F4 if m.dtype == torch.float32 else F8) if m is not None else F8,
-                              res.code, shift, self._box_c, self._nmesh_c, self.x_start, self.x_n,
-                              _ptr(target.value), _CODE[self.typestr], _stream()), "nbk_paint")
+        self._scatter(p, m, res, shift, target, None, method)
         if scale_after is not None:
             out.axpy(target, scale_after)
         return out
 
-    def paint_interlaced(self, pos, mass, resampler, out1, out2):
+    def paint_interlaced(self, pos, mass, resampler, out1, out2, method=None):
         """both meshes of the interlaced branch (catalog.py:289-296) in one pass over the particles"""
         res = _window.FindResampler(resampler)
         if res.code is None:
@@ -300,11 +298,42 @@ class ParticleMesh(object):
             m = as_device_tensor(mass, device=dev)
             if m.dtype not in (torch.float32, torch.float64):
                 m = m.to(torch.float64)
-        check(lib().nbk_paint_interlaced(_ptr(p), F4 if p.dtype == torch.float32 else F8, p.shape[0],
-                                         _ptr(m), (F4 if m.dtype == torch.float32 else F8) if m is not None else F8,
-                                         res.code, self._box_c, self._nmesh_c, self.x_start, self.x_n,
-                                         _ptr(out1.value), _ptr(out2.value), _CODE[self.typestr], _stream()),
-              "nbk_paint_interlaced")
+        self._scatter(p, m, res, 0.0, out1, out2, method)
+
+    # below this many particles per mesh cell the per-tile overhead of the tiled path outweighs its gain
+    TILED_MIN_OCCUPANCY = 0.02
+
+    def _scatter(self, p, m, res, shift, out1, out2, method=None):
+        """dispatch to the tile-sorted shared-memory path or to the direct REDG path.
+        method: None (choose), 'tiled', 'direct'"""
+        L = lib()
+        n = int(p.shape[0])
+        pcode = F4 if p.dtype == torch.float32 else F8
+        mcode = (F4 if m.dtype == torch.float32 else F8) if m is not None else F8
+        code = _CODE[self.typestr]
+        ok = bool(L.nbk_paint_tiled_supported(self._nmesh_c, self.x_n, res.code)) and shift in (0.0, 0.5)
+        if method == 'tiled' and not ok:
+            raise ValueError("the tiled paint path needs mesh sides that are multiples of 16 (>= 32)")
+        if method is None:
+            cells = float(self.x_n) * float(self.Nmesh[1]) * float(self.Nmesh[2])
+            method = 'tiled' if (ok and n >= self.TILED_MIN_OCCUPANCY * cells and n >= 100000) else 'direct'
+        if method == 'tiled':
+            nbytes = int(L.nbk_paint_tiled_workspace(n, pcode, mcode if m is not None else 0, self._nmesh_c, self.x_n))
+            work = torch.empty(nbytes, dtype=torch.uint8, device=p.device)
+            with stage("paint"):
+                check(L.nbk_paint_tiled(_ptr(p), pcode, n, _ptr(m), mcode, res.code, float(shift), self._box_c,
+                                        self._nmesh_c, self.x_start, self.x_n, _ptr(out1.value),
+                                        _ptr(out2.value) if out2 is not None else None, code, _ptr(work), nbytes,
+                                        _stream()), "nbk_paint_tiled")
+            return
+        with stage("paint"):
+            if out2 is None:
+                check(L.nbk_paint(_ptr(p), pcode, n, _ptr(m), mcode, res.code, float(shift), self._box_c, self._nmesh_c,
+                                  self.x_start, self.x_n, _ptr(out1.value), code, _stream()), "nbk_paint")
+            else:
+                check(L.nbk_paint_interlaced(_ptr(p), pcode, n, _ptr(m), mcode, res.code, self._box_c, self._nmesh_c,
+                                             self.x_start, self.x_n, _ptr(out1.value), _ptr(out2.value), code,
+                                             _stream()), "nbk_paint_interlaced")
 
     def cell_index(self, pos, resampler="cic", shift=0.0):
         """wrapped leftmost stencil cell of every particle, (n,3) int32 device tensor"""
@@ -562,7 +591,8 @@ class RealField(Field):
         P = pm.comm.size
         Nx, Ny, Nz = [int(v) for v in pm.Nmesh]
         if P == 1:
-            check(lib().nbk_r2c(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, _stream()), "nbk_r2c")
+            with stage("r2c"):
+                check(lib().nbk_r2c(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, _stream()), "nbk_r2c")
         else:
             Nzc = pm.Nzc
             work = torch.empty((pm.x_n, Ny, Nzc), dtype=out.value.dtype, device=out.value.device)
@@ -630,8 +660,9 @@ class ComplexField(BaseComplexField):
         """v /= window transfer function (source/mesh/catalog.py:449-594), in place"""
         pm = self.pm
         tr, start, count = self._slab()
-        check(lib().nbk_compensate(_ptr(self.value), _CODE[pm.typestr], _lib.COMP[name], pm._nmesh_c, tr, start, count,
-                                   _stream()), "nbk_compensate")
+        with stage("compensate"):
+            check(lib().nbk_compensate(_ptr(self.value), _CODE[pm.typestr], _lib.COMP[name], pm._nmesh_c, tr, start, count,
+                                       _stream()), "nbk_compensate")
         return self
 
     def interlace_combine(self, other):

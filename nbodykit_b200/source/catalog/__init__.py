@@ -1,4 +1,5 @@
 from .array import ArrayCatalog
 from .uniform import UniformCatalog, RandomCatalog
+from .lognormal import LogNormalCatalog
 
-__all__ = ['ArrayCatalog', 'UniformCatalog', 'RandomCatalog']
+__all__ = ["ArrayCatalog", "UniformCatalog", "RandomCatalog", "LogNormalCatalog"]

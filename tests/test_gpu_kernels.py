@@ -260,3 +260,104 @@ def test_elementwise_and_sums(cuda):
     assert np.allclose(f.numpy(), 4.0)
     assert abs(f.csum() - 4.0 * 192) < 1e-9
     assert abs(f.cmean() - 4.0) < 1e-12
+
+
+# ---------------------------------------------------------------------------------------------
+# tile-sorted shared-memory paint path (nbk_paint_tiled)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("resampler", ["nnb", "cic", "tsc", "pcs"])
+@pytest.mark.parametrize("mesh_dtype,pos_dtype", [("f8", "f4"), ("f4", "f4"), ("f8", "f8")])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_paint_tiled_vs_oracle(cuda, resampler, mesh_dtype, pos_dtype, weighted):
+    N, L = [32, 48, 64], [64., 100., 10.]
+    pos = _particles(200000, L, pos_dtype)
+    mass = None
+    if weighted:   # includes negative and widely different masses
+        mass = np.random.RandomState(3).uniform(-2.0, 3.0, size=len(pos))
+    pm = _pm(N, L, mesh_dtype)
+    got = pm.paint(pos, mass=mass if weighted else 1.0, resampler=resampler, method='tiled').numpy()
+    want = po.paint(pos, mass, N, L, resampler, dtype="f8")
+    amax = np.abs(want).max()
+    # fixed point: 2^-31 of max|mass| per deposit; f4 meshes add the final cast
+    tol = 1e-7 if mesh_dtype == "f8" else 3e-6
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol * amax)
+    # agrees with the direct (REDG) path as well
+    direct = pm.paint(pos, mass=mass if weighted else 1.0, resampler=resampler, method='direct').numpy()
+    np.testing.assert_allclose(got, direct, rtol=0, atol=max(tol, 2e-5 if mesh_dtype == "f4" else 0) * amax)
+
+
+def test_paint_tiled_is_order_independent(cuda):
+    """fixed-point accumulation: any particle order gives the same bits (the REDG path cannot promise that)"""
+    N, L = 64, 200.
+    pos = _particles(300000, [L] * 3, "f4", outside=False)
+    pm = _pm(N, L, "f8")
+    a = pm.paint(pos, resampler="tsc", method='tiled').numpy()
+    perm = np.random.RandomState(1).permutation(len(pos))
+    b = pm.paint(pos[perm], resampler="tsc", method='tiled').numpy()
+    order = np.lexsort((pos[:, 2], pos[:, 1], pos[:, 0]))
+    c = pm.paint(pos[order], resampler="tsc", method='tiled').numpy()
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_paint_tiled_interlaced_hold_and_shift(cuda):
+    from nbodykit_b200.pmesh.pm import RealField
+    N, L = [32, 32, 64], 100.
+    pos = _particles(150000, [L] * 3, "f4")
+    mass = np.random.RandomState(5).uniform(0.1, 1.0, size=len(pos)).astype("f4")
+    pm = _pm(N, L, "f8")
+    r1, r2 = RealField(pm), RealField(pm)
+    r1[...] = 1.0; r2[...] = 2.0          # hold semantics: accumulate into what is there
+    pm.paint_interlaced(pos, mass, "tsc", r1, r2, method='tiled')
+    w1 = 1.0 + po.paint(pos, mass, N, L, "tsc", 0.0)
+    w2 = 2.0 + po.paint(pos, mass, N, L, "tsc", 0.5)
+    np.testing.assert_allclose(r1.numpy(), w1, rtol=0, atol=1e-7 * w1.max())
+    np.testing.assert_allclose(r2.numpy(), w2, rtol=0, atol=1e-7 * w2.max())
+    out = pm.paint(pos, mass=mass, resampler="cic", transform=pm.affine.shift(0.5), method='tiled')
+    w = po.paint(pos, mass, N, L, "cic", 0.5)
+    np.testing.assert_allclose(out.numpy(), w, rtol=0, atol=1e-7 * w.max())
+
+
+def test_paint_tiled_slab_ghosts(cuda):
+    """x slabs: ghost particles (leftmost cell below the slab) contribute only their in-slab planes"""
+    import ctypes
+    import torch
+    from nbodykit_b200 import _lib
+    N, L = [64, 32, 32], [64., 32., 32.]
+    pos = _particles(120000, L, "f4")
+    full = po.paint(pos, None, N, L, "tsc")
+    p = torch.from_numpy(pos).cuda()
+    Lb = _lib.lib()
+    for x0, xn in [(0, 16), (16, 16), (48, 16), (8, 40)]:
+        for shift in (0.0, 0.5):
+            want = full if shift == 0.0 else po.paint(pos, None, N, L, "tsc", 0.5)
+            mesh = torch.zeros((xn, 32, 32), dtype=torch.float64, device="cuda")
+            nb = Lb.nbk_paint_tiled_workspace(len(pos), 4, 0, _lib.iarr(N), xn)
+            work = torch.empty(nb, dtype=torch.uint8, device="cuda")
+            _lib.check(Lb.nbk_paint_tiled(ctypes.c_void_p(p.data_ptr()), 4, len(pos), None, 8, 3, shift, _lib.darr(L),
+                                          _lib.iarr(N), x0, xn, ctypes.c_void_p(mesh.data_ptr()), None, 8,
+                                          ctypes.c_void_p(work.data_ptr()), nb, None))
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(mesh.cpu().numpy(), want[x0:x0 + xn], rtol=0, atol=1e-7 * want.max())
+
+
+def test_paint_tiled_clustered_and_empty_tiles(cuda):
+    """all particles inside two cells (one hot tile, thousands of empty ones) + a tile on the periodic seam"""
+    N, L = 64, 64.
+    rng = np.random.RandomState(8)
+    pos = np.concatenate([rng.uniform(10.0, 11.0, size=(100000, 3)), rng.uniform(63.0, 64.0, size=(100000, 3))]).astype("f4")
+    pm = _pm(N, L, "f4")
+    got = pm.paint(pos, resampler="cic", method='tiled').numpy()
+    want = po.paint(pos, None, N, L, "cic")
+    np.testing.assert_allclose(got, want, rtol=0, atol=3e-7 * want.max())
+    assert abs(got.sum(dtype="f8") - len(pos)) < 1e-2
+
+
+def test_paint_auto_dispatch_matches(cuda):
+    """the default dispatch (tiled for dense catalogues, direct otherwise) is transparent"""
+    N, L = 32, 50.
+    pm = _pm(N, L, "f8")
+    for n in (5000, 200000):
+        pos = _particles(n, [L] * 3, "f4")
+        a = pm.paint(pos, resampler="cic").numpy()
+        w = po.paint(pos, None, N, L, "cic")
+        np.testing.assert_allclose(a, w, rtol=0, atol=1e-7 * w.max())
