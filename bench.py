@@ -56,7 +56,7 @@ class ClockSampler(object):
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "50"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
@@ -138,11 +138,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
+    # the clock sampler needs ~1 s to come up: start it before the warm-up; "under load" samples are picked by
+    # power draw when the numbers are reduced
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_w = time.time()
+    nw = 0
+    while nw < args.warmup or (time.time() - t_w < 1.5 and nw < 200):
         r = step(cat)
+        nw += 1
     barrier()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
     _lib.profiler.start()
     barrier()
@@ -293,7 +298,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

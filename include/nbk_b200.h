@@ -101,7 +101,8 @@ int nbk_sum_w_w2(const void *w, int dtype, int64_t n, double *out2, void *stream
 /* RealField.r2c / ComplexField.c2r (base/mesh.py:228,237; source/mesh/catalog.py:341-351).
  * Forward is normalised by 1/(Nx*Ny*Nz), backward unnormalised (source/mesh/array.py:36-37).
  * Single-GPU whole-mesh transforms; real [Nx][Ny][Nz], cplx [Nx][Ny][Nzc].  Out of place. */
-int nbk_r2c(const void *real, void *cplx, int dtype, const int64_t *nmesh_host, void *stream);
+int nbk_r2c(const void *real, void *cplx, int dtype, const int64_t *nmesh_host, double extra_scale,
+            void *stream); /* cplx = extra_scale * FFT(real) / prod(N): folds e.g. the 1/nbar of catalog.py:394-398 */
 int nbk_c2r(const void *cplx, void *real, int dtype, const int64_t *nmesh_host, void *work,
             void *stream);
 
@@ -142,14 +143,16 @@ int nbk_interlace_combine(void *c1, const void *c2, int dtype, const int64_t *nm
  * y3d (project_to_basis semantics only; c2, volume, clear_zero ignored).
  * k2edges: host double[Nx+1] = kedges**2; muedges: host double[Nmu+1]; ells: host int[Nell]
  * (ells[0] must be 0).  coord_dtype NBK_F4 (fixture-faithful) | NBK_F8.
+ * comp1 / comp2 (NBK_COMP_*): window compensation applied on the fly to c1 / c2 (the fused equivalent of
+ * running nbk_compensate on each field first); NBK_COMP_NONE when the fields are already compensated.
  * Outputs (device, ACCUMULATED into; zero first), nb = (Nx+2)*(Nmu+2):
  *   nsum int64[nb]; xsum, musum double[nb]; ysum double[Nell][nb][2] (re, im). */
 int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume,
                   int clear_zero, const int64_t *nmesh_host, const double *boxsize_host,
                   int transposed, int64_t start, int64_t count, int coord_dtype,
                   const double *k2edges_host, int Nx, const double *muedges_host, int Nmu,
-                  const double *los_host, const int *ells_host, int Nell, int hermitian,
-                  int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
+                  const double *los_host, const int *ells_host, int Nell, int hermitian, int comp1,
+                  int comp2, int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
 
 /* elementwise helpers behind RealField/ComplexField `[...] = v`, `*= a`, `+= other`
  * (source/mesh/catalog.py:203,354,396-398; fftpower.py:128).  n counts REAL scalars. */

@@ -38,7 +38,7 @@ SIGNATURES = {
     "nbk_paint_tiled": ([_vp, _i, _i64, _vp, _i, _i, _d, _pd, _pi64, _i64, _i64, _vp, _vp, _i, _vp, _i64, _vp], _i),
     "nbk_cell_index": ([_vp, _i, _i64, _i, _d, _pd, _pi64, _vp, _vp], _i),
     "nbk_sum_w_w2": ([_vp, _i, _i64, _vp, _vp], _i),
-    "nbk_r2c": ([_vp, _vp, _i, _pi64, _vp], _i),
+    "nbk_r2c": ([_vp, _vp, _i, _pi64, _d, _vp], _i),
     "nbk_c2r": ([_vp, _vp, _i, _pi64, _vp, _vp], _i),
     "nbk_fft_zy_forward": ([_vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
     "nbk_fft_zy_backward": ([_vp, _vp, _i, _i64, _i64, _i64, _vp], _i),
@@ -50,7 +50,7 @@ SIGNATURES = {
     "nbk_compensate": ([_vp, _i, _i, _pi64, _i, _i64, _i64, _vp], _i),
     "nbk_interlace_combine": ([_vp, _vp, _i, _pi64, _pd, _i, _i64, _i64, _vp], _i),
     "nbk_power_bin": ([_vp, _vp, _i, _i, _d, _i, _pi64, _pd, _i, _i64, _i64, _i, _pd, _i, _pd, _i, _pd, _pi,
-                       _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
+                       _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp], _i),
     "nbk_fill": ([_vp, _i, _i64, _d, _vp], _i),
     "nbk_scale": ([_vp, _i, _i64, _d, _vp], _i),
     "nbk_axpy": ([_vp, _vp, _i, _i64, _d, _vp], _i),

@@ -76,11 +76,19 @@ class FFTBase(object):
         The product c1*conj(c2)*V with the zero mode cleared is formed inside the binning kernel."""
         attrs = {}
         attrs.update(self.attrs)
-        c1 = first.compute(mode='complex', Nmesh=self.attrs['Nmesh'])
+
+        def field_of(src):
+            # a CatalogMesh whose only action is its window compensation hands over the uncompensated field
+            # and the name of the transfer function; the binning kernel applies it on the fly
+            if hasattr(src, 'compute_complex_deferred'):
+                return src.compute_complex_deferred()
+            return src.compute(mode='complex', Nmesh=self.attrs['Nmesh']), None
+        c1, comp1 = field_of(first)
         if first is second:
-            c2 = c1
+            c2, comp2 = c1, comp1
         else:
-            c2 = second.compute(mode='complex', Nmesh=self.attrs['Nmesh'])
+            c2, comp2 = field_of(second)
+        self._deferred_compensation = (comp1, comp2)
         N1 = c1.attrs.get('N', 0)
         N2 = c2.attrs.get('N', 0)
         attrs.update({'N1': N1, 'N2': N2})
@@ -142,7 +150,7 @@ class FFTPower(FFTBase):
         coords = [kcoords, None]
         result, pole_result = project_to_basis_device(
             c1, edges, poles=self.attrs['poles'], los=self.attrs['los'], second=None if c2 is c1 else c2,
-            is_p3d=False, volume=float(self.attrs['BoxSize'].prod()))
+            is_p3d=False, volume=float(self.attrs['BoxSize'].prod()), compensation=self._deferred_compensation)
 
         if self.attrs['mode'] == "1d":
             cols = ['k', 'power', 'modes']
@@ -203,13 +211,14 @@ def _los_coord_mode(los, coord_dtype):
 
 
 def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4", is_p3d=True, second=None,
-                            volume=1.0):
+                            volume=1.0, compensation=(None, None)):
     """
     project_to_basis (fftpower.py:507-701) for a device ComplexField.
 
     With ``is_p3d=True`` `y3d` is the 3-D statistic itself (reference semantics).  With
     ``is_p3d=False`` the statistic is `y3d * conj(second or y3d) * volume` with the k=0 mode
-    cleared, formed on the fly (fftpower.py:115-128) -- the FFTPower fast path.
+    cleared, formed on the fly (fftpower.py:115-128) -- the FFTPower fast path; `compensation` then names
+    the window transfer functions (`Compensate*`) still to be divided out of `y3d` / `second`, also on the fly.
 
     Returns exactly what the reference returns:
     ``(xmean_2d, mumean_2d, y2d, N_2d), (xmean_1d, poles, N_1d) | None``.
@@ -247,7 +256,8 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
             _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
             1 if is_p3d else 0, float(volume), 1, pm._nmesh_c, pm._box_c, tr, start, count,
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
-            _lib.i32arr(_poles), Nell, 1, _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
+            _lib.i32arr(_poles), Nell, 1, _lib.COMP.get(compensation[0], 0), _lib.COMP.get(compensation[1], 0),
+            _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
     if comm.size > 1:
         comm.allreduce_tensor(nsum)
         comm.allreduce_tensor(facc)

@@ -108,6 +108,35 @@ static int get_comp_table(int kind, int N, cudaStream_t s, double **out) {
     return NBK_OK;
 }
 
+// product of two kinds' reciprocal factors along one axis (for the compensation fused into nbk_power_bin)
+__global__ void k_comp_pair_table(double *tab, int kind1, int kind2, int N) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) {
+        const double TWO_PI = 6.28318530717958647692;
+        double w = TWO_PI * (double)nbk_freq(j, N) / (double)N;
+        double f1 = kind1 ? 1.0 / comp_factor(kind1, w) : 1.0;
+        double f2 = kind2 ? 1.0 / comp_factor(kind2, w) : 1.0;
+        tab[j] = f1 * f2;
+    }
+}
+
+static int get_comp_pair_table(int kind1, int kind2, int N, cudaStream_t s, double **out) {
+    int dev = 0;
+    NBK_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_ct_mutex);
+    auto key = std::make_tuple(dev, 1000 + kind1 * 16 + kind2, N);
+    auto it = g_ct.find(key);
+    if (it != g_ct.end()) { *out = it->second; return NBK_OK; }
+    double *p = nullptr;
+    NBK_CUDA(cudaMalloc(&p, sizeof(double) * N));
+    k_comp_pair_table<<<(N + 255) / 256, 256, 0, s>>>(p, kind1, kind2, N);
+    NBK_LAUNCHED();
+    NBK_CUDA(cudaStreamSynchronize(s));
+    g_ct[key] = p;
+    *out = p;
+    return NBK_OK;
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_compensate(T *__restrict__ c, SlabGeom g, const double *__restrict__ t0, const double *__restrict__ t1,
@@ -233,13 +262,21 @@ __device__ __forceinline__ void acc_add(double *p, double v) {
     if (v != 0.0) atomicAdd(p, v);
 }
 
-// One warp iteration handles 32 consecutive stored modes; equal-bin runs are combined with a segmented
-// shuffle reduction so each run costs one atomic per accumulated quantity.
+// Row sweep: one warp per (i0, i1) row of the slab, lanes strided along kz (coalesced 8/16-byte loads).
+// Everything that depends on (jx, jy) only is hoisted out of the kz loop; the k bin starts from a
+// uniform-spacing guess and is corrected against the exact f64 edges^2 (so it equals numpy.digitize for any
+// increasing edges).  Along a row |k| is monotone in kz, so equal bins form contiguous lane runs: a
+// segmented shuffle reduction leaves one shared-memory atomic per run and quantity (f64 shared atomics are
+// CAS loops on sm_100a -- same-address collisions inside a warp are what make them slow, and the run
+// reduction removes exactly those).  Mode counts come from the run length (no shuffle).
 template <typename T, int NELL, bool SMEM_ACC>
 __global__ void __launch_bounds__(256)
 k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, const double *__restrict__ k2edges,
             const double *__restrict__ muedges, unsigned long long *__restrict__ g_nsum, double *__restrict__ g_xsum,
-            double *__restrict__ g_musum, double *__restrict__ g_ysum) {
+            double *__restrict__ g_musum, double *__restrict__ g_ysum, double kmin, double inv_dk, int uniform,
+            const double *__restrict__ ct0, const double *__restrict__ ct1, const double *__restrict__ ctz) {
+    // ct0/ct1/ctz: per-axis products of the two fields' reciprocal window factors (first stored axis, second
+    // stored axis, z); null when no compensation is fused
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout: k2edges[Nx+1] | muedges[Nmu+1] | (if SMEM_ACC) xsum[nb] musum[nb] ysum[NELL][nb][2] nsum[nb](u32)
     double *s_k2 = reinterpret_cast<double *>(smem_raw);
@@ -263,84 +300,106 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
 
     const SlabGeom &g = P.g;
     const int lane = threadIdx.x & 31;
-    const int64_t total = (int64_t)g.count * g.D1 * g.Nzc;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t nit = (total + stride - 1) / stride;
-    for (int64_t it = 0; it < nit; it++) {
-        int64_t e = it * stride + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        int key = -1;
-        unsigned cnt = 0;
-        double xs = 0, ms = 0, yr[NELL], yi[NELL];
+    const int wpb = blockDim.x >> 5;
+    const int rows = g.count * g.D1;
+    const int nedge = P.Nx + 1;
+    const int kz_iters = (g.Nzc + 31) >> 5;
+    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
+        int i0 = row / g.D1, i1 = row - i0 * g.D1;
+        int jx, jy, jz0;
+        slab_freqs(g, i0, i1, 0, jx, jy, jz0);
+        // per-row constants, in the arithmetic the coordinate mode prescribes
+        float kx32 = (float)jx * P.kf32[0], ky32 = (float)jy * P.kf32[1];
+        float kp2_32 = kx32 * kx32 + ky32 * ky32;                       // (0 + kx^2) + ky^2
+        float lp_32 = kx32 * P.los32[0] + ky32 * P.los32[1];            // (0 + kx l0) + ky l1
+        double kx64 = (double)jx * P.kf64[0], ky64 = (double)jy * P.kf64[1];
+        double kp2_64 = kx64 * kx64 + ky64 * ky64;
+        double lp_64 = kx64 * P.los64[0] + ky64 * P.los64[1];
+        double lp_48 = (double)kx32 * P.los64[0] + (double)ky32 * P.los64[1];
+        const T *r1 = c1 + (int64_t)row * g.Nzc * 2;
+        const T *r2 = P.has_c2 ? c2 + (int64_t)row * g.Nzc * 2 : r1;
+        const double vol_row = ct0 ? P.volume * (ct0[g.start + i0] * ct1[i1]) : P.volume;
+        for (int it = 0; it < kz_iters; it++) {
+            const int kz = it * 32 + lane;
+            int key = -1;
+            double xs = 0, ms = 0, yr[NELL], yi[NELL];
+            unsigned wcnt = 0;
 #pragma unroll
-        for (int l = 0; l < NELL; l++) { yr[l] = 0; yi[l] = 0; }
-        if (e < total) {
-            int64_t row = e / g.Nzc;
-            int kz = (int)(e - row * g.Nzc);
-            int i0 = (int)(row / g.D1), i1 = (int)(row - (int64_t)i0 * g.D1);
-            int jx, jy, jz;
-            slab_freqs(g, i0, i1, kz, jx, jy, jz);
-            if (!P.hermitian) jz = nbk_freq(kz, g.N[2]);
-            double k2d, knorm, mu;
-            if (P.coord_mode == 8) {
-                double kx = (double)jx * P.kf64[0], ky = (double)jy * P.kf64[1], kzv = (double)jz * P.kf64[2];
-                k2d = (kx * kx + ky * ky) + kzv * kzv;
-                knorm = sqrt(k2d);
-                mu = ((kx * P.los64[0] + ky * P.los64[1]) + kzv * P.los64[2]) / knorm;
-                if (knorm == 0.0) mu = 0.0;
-            } else {
-                float kx = (float)jx * P.kf32[0], ky = (float)jy * P.kf32[1], kzv = (float)jz * P.kf32[2];
-                float k2 = (kx * kx + ky * ky) + kzv * kzv;
-                float kn = sqrtf(k2);  // IEEE sqrt (-prec-sqrt=true), numpy `** 0.5` on f4 -> sqrtf
-                k2d = (double)k2;
-                knorm = (double)kn;
-                if (P.coord_mode == 4) {
-                    float m = ((kx * P.los32[0] + ky * P.los32[1]) + kzv * P.los32[2]) / kn;
-                    mu = (kn == 0.0f) ? 0.0 : (double)m;
+            for (int l = 0; l < NELL; l++) { yr[l] = 0; yi[l] = 0; }
+            if (kz < g.Nzc) {
+                int jz = nbk_freq(kz, g.N[2]);
+                double k2d, knorm, mu;
+                if (P.coord_mode == 8) {
+                    double kzv = (double)jz * P.kf64[2];
+                    k2d = kp2_64 + kzv * kzv;
+                    knorm = sqrt(k2d);
+                    mu = (lp_64 + kzv * P.los64[2]) / knorm;
+                    if (knorm == 0.0) mu = 0.0;
                 } else {
-                    double m = (((double)kx * P.los64[0] + (double)ky * P.los64[1]) + (double)kzv * P.los64[2]) / knorm;
-                    mu = (kn == 0.0f) ? 0.0 : m;
+                    float kzv = (float)jz * P.kf32[2];
+                    float k2 = kp2_32 + kzv * kzv;
+                    float kn = sqrtf(k2);   // IEEE sqrt; numpy `** 0.5` on float32 is sqrtf
+                    k2d = (double)k2;
+                    knorm = (double)kn;
+                    if (P.coord_mode == 4) {
+                        float m = (lp_32 + kzv * P.los32[2]) / kn;
+                        mu = (kn == 0.0f) ? 0.0 : (double)m;
+                    } else {
+                        double m = (lp_48 + (double)kzv * P.los64[2]) / knorm;
+                        mu = (kn == 0.0f) ? 0.0 : m;
+                    }
                 }
-            }
-            int dig_x = digitize(s_k2, P.Nx + 1, k2d);
-            int dig_mu = digitize(s_mu, P.Nmu + 1, mu);
-            key = dig_x * (P.Nmu + 2) + dig_mu;
-            bool nonsing = P.hermitian && (jz > 0);
-            double wH = nonsing ? 2.0 : 1.0;
-            cnt = nonsing ? 2u : 1u;
-            xs = knorm * wH;
-            ms = mu * wH;
-            // the statistic y
-            double a = (double)c1[2 * e], b = (double)c1[2 * e + 1], yre, yim;
-            if (P.is_p3d) { yre = a; yim = b; }
-            else {
-                double c = a, d = b;
-                if (P.has_c2) { c = (double)c2[2 * e]; d = (double)c2[2 * e + 1]; }
-                yre = (a * c + b * d) * P.volume;   // c1 * conj(c2)
-                yim = (b * c - a * d) * P.volume;
-                if (P.clear_zero && jx == 0 && jy == 0 && jz == 0) { yre = 0; yim = 0; }
-            }
+                // numpy.digitize(k2, edges2): number of edges <= k2
+                int b;
+                if (uniform) {
+                    double t = (knorm - kmin) * inv_dk;
+                    b = t < 0.0 ? 0 : (t >= (double)nedge ? nedge : (int)t + 1);
+                    while (b > 0 && k2d < s_k2[b - 1]) b--;
+                    while (b < nedge && k2d >= s_k2[b]) b++;
+                } else {
+                    b = digitize(s_k2, nedge, k2d);
+                }
+                int dm = 0;
+                for (int i = 0; i <= P.Nmu; i++) dm += (s_mu[i] <= mu) ? 1 : 0;
+                key = b * (P.Nmu + 2) + dm;
+                bool nonsing = P.hermitian && (jz > 0);
+                double wH = nonsing ? 2.0 : 1.0;
+                wcnt = nonsing ? 2u : 1u;
+                xs = knorm * wH;
+                ms = mu * wH;
+                double a = (double)r1[2 * kz], bb = (double)r1[2 * kz + 1], yre, yim;
+                if (P.is_p3d) { yre = a; yim = bb; }
+                else {
+                    double c = (double)r2[2 * kz], d = (double)r2[2 * kz + 1];
+                    double vol = ct0 ? vol_row * ctz[kz] : vol_row;
+                    yre = (a * c + bb * d) * vol;   // c1 * conj(c2) * V [* window compensation of both fields]
+                    yim = (bb * c - a * d) * vol;
+                    if (P.clear_zero && jx == 0 && jy == 0 && jz == 0) { yre = 0; yim = 0; }
+                }
 #pragma unroll
-            for (int l = 0; l < NELL; l++) {
-                int ell = P.ells[l];
-                double f = legendre(ell, mu) * (2.0 * ell + 1.0);
-                double re = f * yre, im = f * yim;
-                if (nonsing) {
-                    if (ell & 1) { re = 0.0; im *= 2.0; }
-                    else { re *= 2.0; im = 0.0; }
+                for (int l = 0; l < NELL; l++) {
+                    int ell = P.ells[l];
+                    double f = legendre(ell, mu) * (2.0 * ell + 1.0);
+                    double re = f * yre, im = f * yim;
+                    if (nonsing) {
+                        if (ell & 1) { re = 0.0; im *= 2.0; }
+                        else { re *= 2.0; im = 0.0; }
+                    }
+                    yr[l] = re;
+                    yi[l] = im;
                 }
-                yr[l] = re;
-                yi[l] = im;
             }
-        }
-        // ---- segmented reduction over equal-key runs
-        int prev = __shfl_up_sync(0xffffffffu, key, 1);
-        bool head = (lane == 0) || (prev != key);
-        unsigned heads = __ballot_sync(0xffffffffu, head);
-        if (heads == 1u) {  // whole warp in one bin
-            if (key >= 0) {
+            // ---- equal-key runs of lanes -> one atomic per run
+            int prev = __shfl_up_sync(0xffffffffu, key, 1);
+            bool head = (lane == 0) || (prev != key);
+            unsigned heads = __ballot_sync(0xffffffffu, head);
+            // count: all members of a run share wcnt except the kz = 0 / Nyquist planes -> reduce it as an int
+            if (heads == 0xffffffffu) {
+                // every lane is its own run: nothing to combine
+            } else if (heads == 1u) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+                    wcnt += __shfl_xor_sync(0xffffffffu, wcnt, o);
                     xs += __shfl_xor_sync(0xffffffffu, xs, o);
                     ms += __shfl_xor_sync(0xffffffffu, ms, o);
 #pragma unroll
@@ -349,34 +408,45 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                         yi[l] += __shfl_xor_sync(0xffffffffu, yi[l], o);
                     }
                 }
-            }
-        } else {
-            int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
+            } else {
+                // longest run bounds the number of doubling steps needed
+                unsigned hm = heads;
+                int seg = __popc(hm & (0xffffffffu >> (31 - lane)));
+                int maxrun = 1;
+                {   // run length of my segment = distance between my head and the next head
+                    unsigned above = hm & ~((2u << lane) - 1u);          // heads strictly above me
+                    int next = above ? (__ffs(above) - 1) : 32;
+                    unsigned below = hm & ((2u << lane) - 1u);           // heads at or below me
+                    int mine = 31 - __clz(below);
+                    maxrun = next - mine;
+                }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int so = __shfl_down_sync(0xffffffffu, seg, o);
-                bool take = (lane + o < 32) && (so == seg);
-                unsigned c_o = __shfl_down_sync(0xffffffffu, cnt, o);
-                double x_o = __shfl_down_sync(0xffffffffu, xs, o);
-                double m_o = __shfl_down_sync(0xffffffffu, ms, o);
-                if (take) { cnt += c_o; xs += x_o; ms += m_o; }
+                for (int o = 16; o > 0; o >>= 1) maxrun = max(maxrun, __shfl_xor_sync(0xffffffffu, maxrun, o));
+                for (int o = 1; o < maxrun; o <<= 1) {
+                    int so = __shfl_down_sync(0xffffffffu, seg, o);
+                    bool take = (lane + o < 32) && (so == seg);
+                    unsigned c_o = __shfl_down_sync(0xffffffffu, wcnt, o);
+                    double x_o = __shfl_down_sync(0xffffffffu, xs, o);
+                    double m_o = __shfl_down_sync(0xffffffffu, ms, o);
+                    if (take) { wcnt += c_o; xs += x_o; ms += m_o; }
 #pragma unroll
-                for (int l = 0; l < NELL; l++) {
-                    double r_o = __shfl_down_sync(0xffffffffu, yr[l], o);
-                    double i_o = __shfl_down_sync(0xffffffffu, yi[l], o);
-                    if (take) { yr[l] += r_o; yi[l] += i_o; }
+                    for (int l = 0; l < NELL; l++) {
+                        double r_o = __shfl_down_sync(0xffffffffu, yr[l], o);
+                        double i_o = __shfl_down_sync(0xffffffffu, yi[l], o);
+                        if (take) { yr[l] += r_o; yi[l] += i_o; }
+                    }
                 }
             }
-        }
-        if (head && key >= 0) {
-            if (SMEM_ACC) atomicAdd(&s_n[key], cnt);
-            else atomicAdd(&g_nsum[key], (unsigned long long)cnt);
-            acc_add<SMEM_ACC>(&a_x[key], xs);
-            acc_add<SMEM_ACC>(&a_m[key], ms);
+            if (head && key >= 0) {
+                if (SMEM_ACC) atomicAdd(&s_n[key], wcnt);
+                else atomicAdd(&g_nsum[key], (unsigned long long)wcnt);
+                acc_add<SMEM_ACC>(&a_x[key], xs);
+                acc_add<SMEM_ACC>(&a_m[key], ms);
 #pragma unroll
-            for (int l = 0; l < NELL; l++) {
-                acc_add<SMEM_ACC>(&a_y[((size_t)l * P.nb + key) * 2], yr[l]);
-                acc_add<SMEM_ACC>(&a_y[((size_t)l * P.nb + key) * 2 + 1], yi[l]);
+                for (int l = 0; l < NELL; l++) {
+                    acc_add<SMEM_ACC>(&a_y[((size_t)l * P.nb + key) * 2], yr[l]);
+                    acc_add<SMEM_ACC>(&a_y[((size_t)l * P.nb + key) * 2 + 1], yi[l]);
+                }
             }
         }
     }
@@ -424,23 +494,30 @@ static int get_edges(const double *host, int n, cudaStream_t s, double **out) {
 
 template <typename T, int NELL>
 static int launch_bin(const void *c1, const void *c2, const BinParams &P, const double *d_k2, const double *d_mu,
-                      int64_t *nsum, double *xsum, double *musum, double *ysum, cudaStream_t s) {
+                      int64_t *nsum, double *xsum, double *musum, double *ysum, double kmin, double inv_dk, int uniform,
+                      const double *ct0, const double *ct1, const double *ctz, cudaStream_t s) {
     size_t edge_bytes = sizeof(double) * (P.Nx + 1 + P.Nmu + 1);
     size_t acc_bytes = (size_t)P.nb * (sizeof(double) * (2 + 2 * NELL) + sizeof(unsigned));
-    bool smem_acc = edge_bytes + acc_bytes <= 100 * 1024;
+    bool smem_acc = edge_bytes + acc_bytes <= 200 * 1024;
     size_t smem = edge_bytes + (smem_acc ? acc_bytes : 0);
     NBK_CHECK_ARG(smem <= 227 * 1024, "power_bin: too many bin edges for shared memory");
-    int64_t total = (int64_t)P.g.count * P.g.D1 * P.g.Nzc;
-    int per_sm = smem_acc ? 2 : 4;
-    int grid = nbk_grid_for(total, 256, per_sm);
+    int64_t rows = (int64_t)P.g.count * P.g.D1;
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    int64_t want = (rows + 7) / 8;
+    int grid = (int)(want < (int64_t)NBK_SM_COUNT * per_sm ? want : (int64_t)NBK_SM_COUNT * per_sm);
+    if (grid < 1) grid = 1;
     if (smem_acc) {
         NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_power_bin<T, NELL, true><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,
-                                                            (unsigned long long *)nsum, xsum, musum, ysum);
+                                                            (unsigned long long *)nsum, xsum, musum, ysum, kmin, inv_dk,
+                                                            uniform, ct0, ct1, ctz);
     } else {
         NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_power_bin<T, NELL, false><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,
-                                                             (unsigned long long *)nsum, xsum, musum, ysum);
+                                                             (unsigned long long *)nsum, xsum, musum, ysum, kmin, inv_dk,
+                                                             uniform, ct0, ct1, ctz);
     }
     NBK_LAUNCHED();
     return NBK_OK;
@@ -448,16 +525,17 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
 
 template <typename T>
 static int launch_bin_ell(const void *c1, const void *c2, const BinParams &P, const double *d_k2, const double *d_mu,
-                          int64_t *nsum, double *xsum, double *musum, double *ysum, cudaStream_t s) {
+                          int64_t *nsum, double *xsum, double *musum, double *ysum, double kmin, double inv_dk,
+                          int uniform, const double *ct0, const double *ct1, const double *ctz, cudaStream_t s) {
     switch (P.Nell) {
-        case 1: return launch_bin<T, 1>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 2: return launch_bin<T, 2>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 3: return launch_bin<T, 3>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 4: return launch_bin<T, 4>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 5: return launch_bin<T, 5>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 6: return launch_bin<T, 6>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 7: return launch_bin<T, 7>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-        case 8: return launch_bin<T, 8>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
+        case 1: return launch_bin<T, 1>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 2: return launch_bin<T, 2>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 3: return launch_bin<T, 3>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 4: return launch_bin<T, 4>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 5: return launch_bin<T, 5>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 6: return launch_bin<T, 6>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 7: return launch_bin<T, 7>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+        case 8: return launch_bin<T, 8>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
     }
     nbk_set_error("power_bin: Nell=%d unsupported (1..%d)", P.Nell, NBK_MAX_ELL);
     return NBK_ERR_UNSUPPORTED;
@@ -466,11 +544,12 @@ static int launch_bin_ell(const void *c1, const void *c2, const BinParams &P, co
 extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume, int clear_zero,
                              const int64_t *nmesh, const double *box, int transposed, int64_t start, int64_t count,
                              int coord_dtype, const double *k2edges, int Nx, const double *muedges, int Nmu,
-                             const double *los, const int *ells, int Nell, int hermitian, int64_t *nsum,
-                             double *xsum, double *musum, double *ysum, void *stream) {
+                             const double *los, const int *ells, int Nell, int hermitian, int comp1, int comp2,
+                             int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream) {
     NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "power_bin: bad dtype %d", dtype);
     NBK_CHECK_ARG(coord_dtype == 4 || coord_dtype == 8 || coord_dtype == 48, "power_bin: bad coord_dtype %d", coord_dtype);
     NBK_CHECK_ARG(Nx >= 0 && Nmu >= 1, "power_bin: need Nx >= 0 and Nmu >= 1");
+    NBK_CHECK_ARG((int64_t)nmesh[0] * nmesh[1] < (1ll << 31), "power_bin: too many rows");
     NBK_CHECK_ARG(Nell >= 1 && Nell <= NBK_MAX_ELL && ells[0] == 0, "power_bin: ells must start with 0, 1 <= Nell <= %d", NBK_MAX_ELL);
     BinParams P;
     int rc = make_slab(nmesh, transposed, start, count, hermitian, P.g);
@@ -498,6 +577,30 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
     double *d_k2, *d_mu;
     if ((rc = get_edges(k2edges, Nx + 1, s, &d_k2))) return rc;
     if ((rc = get_edges(muedges, Nmu + 1, s, &d_mu))) return rc;
-    if (dtype == NBK_F4) return launch_bin_ell<float>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
-    return launch_bin_ell<double>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, s);
+    // fused window compensation: per-axis products of the two fields' reciprocal factors
+    const double *ct0 = nullptr, *ct1 = nullptr, *ctz = nullptr;
+    if (!is_p3d && (comp1 != NBK_COMP_NONE || comp2 != NBK_COMP_NONE)) {
+        NBK_CHECK_ARG(comp1 >= 0 && comp1 <= NBK_COMP_PCS_SHOTNOISE && comp2 >= 0 && comp2 <= NBK_COMP_PCS_SHOTNOISE,
+                      "power_bin: unknown compensation kind");
+        if (c2 == nullptr || c2 == c1) comp2 = comp1;
+        double *t[3];
+        for (int d = 0; d < 3; d++)
+            if ((rc = get_comp_pair_table(comp1, comp2, P.g.N[d], s, &t[d]))) return rc;
+        ct0 = transposed ? t[1] : t[0];
+        ct1 = transposed ? t[0] : t[1];
+        ctz = t[2];
+    }
+    // are the k edges uniformly spaced (numpy.arange)?  then bins start from a closed-form guess
+    double kmin = 0.0, inv_dk = 0.0;
+    int uniform = 0;
+    if (Nx >= 1 && k2edges[0] >= 0.0) {
+        kmin = sqrt(k2edges[0]);
+        double dk = (sqrt(k2edges[Nx]) - kmin) / Nx;
+        uniform = dk > 0.0;
+        for (int i = 0; i <= Nx && uniform; i++)
+            if (fabs(sqrt(k2edges[i]) - (kmin + i * dk)) > 1e-3 * dk) uniform = 0;
+        if (uniform) inv_dk = 1.0 / dk;
+    }
+    if (dtype == NBK_F4) return launch_bin_ell<float>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+    return launch_bin_ell<double>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
 }

@@ -43,18 +43,20 @@ __device__ __forceinline__ int pos_of_freq(int k, int N, int log2n) {
 
 // In-place forward DIF FFT of B side-by-side lines of length N held in sm[n*pitch + b].
 // tw[k] = exp(-2 pi i k / N), k < N.  All threads of the CTA must call.
-template <typename C>
-__device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N, int log2n, int B, int pitch) {
+template <typename C, int B>
+__device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N, int log2n) {
+    constexpr int pitch = B + 1;
     const int T = blockDim.x;
     int Ns = N;
     for (int s = 0; s < (log2n >> 1); s++) {
         const int Q = Ns >> 2;
+        const int lq = log2n - 2 * (s + 1);     // log2(Q)
         const int tws = N / Ns;
         const int work = (N >> 2) * B;
         for (int w = threadIdx.x; w < work; w += T) {
             int b = w % B;
             int t = w / B;
-            int blk = t / Q, q = t - blk * Q;
+            int blk = t >> lq, q = t & (Q - 1);
             C *p = sm + (blk * Ns + q) * pitch + b;
             const int st = Q * pitch;
             C a0 = p[0], a1 = p[st], a2 = p[2 * st], a3 = p[3 * st];
@@ -89,15 +91,15 @@ __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N,
 // strided line pass (y and x passes), in place.  element(outer, n, inner) =
 //   data[outer*outer_stride + n*line_stride + inner],  inner < n_inner contiguous.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int B>
 __global__ void __launch_bounds__(256)
 k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type *__restrict__ tw, int N, int log2n,
-            int B, int64_t line_stride, int64_t n_inner, int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride,
+            int64_t line_stride, int64_t n_inner, int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride,
             int inverse, T scale) {
     typedef typename C2<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *sm = reinterpret_cast<C *>(smem_raw);
-    const int pitch = B + 1;
+    constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t outer = tile / tiles_inner;
@@ -112,7 +114,7 @@ k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type 
             sm[n * pitch + b] = v;
         }
         __syncthreads();
-        fft_tile<C>(sm, tw, N, log2n, B, pitch);
+        fft_tile<C, B>(sm, tw, N, log2n);
         for (int w = threadIdx.x; w < N * B; w += T_) {
             int b = w % B, k = w / B;
             if (b < bvalid) {
@@ -132,17 +134,17 @@ k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type 
 // packed trick: z[n] = x[2n] + i x[2n+1], Z = FFT_M(z), M = Nz/2,
 //   X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k]) ],  k = 0..M  (Z[M] := Z[0])
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int B>
 __global__ void __launch_bounds__(256)
 k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
             const typename C2<T>::type *__restrict__ twM, const typename C2<T>::type *__restrict__ twN, int Nz,
-            int log2m, int B, int64_t rows, T scale) {
+            int log2m, int64_t rows, T scale) {
     typedef typename C2<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *sm = reinterpret_cast<C *>(smem_raw);
     const int M = Nz >> 1;
     const int Nzc = M + 1;
-    const int pitch = B + 1;
+    constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
     const int64_t n_tiles = (rows + B - 1) / B;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -150,13 +152,13 @@ k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
         int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
         const C *src = reinterpret_cast<const C *>(real + row0 * Nz);  // rows of M packed pairs, 2*sizeof(T) aligned
         for (int w = threadIdx.x; w < M * B; w += T_) {
-            int n = w % M, b = w / M;  // lanes run along the contiguous row
+            int n = w & (M - 1), b = w >> log2m;  // lanes run along the contiguous row
             C v = C{0, 0};
             if (b < bvalid) v = src[(int64_t)b * M + n];
             sm[n * pitch + b] = v;
         }
         __syncthreads();
-        fft_tile<C>(sm, twM, M, log2m, B, pitch);
+        fft_tile<C, B>(sm, twM, M, log2m);
         C *dst = cplx + row0 * Nzc;
         for (int w = threadIdx.x; w < Nzc * B; w += T_) {
             int k = w % Nzc, b = w / Nzc;
@@ -177,17 +179,17 @@ k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
 // z pass backward: complex rows [rows][Nz/2+1] -> real rows [rows][Nz], unnormalised
 //   E = (X[k] + conj X[M-k])/2, O = conj(W_N^k) (X[k] - conj X[M-k])/2, Z[k] = E + i O, k < M
 //   x[2n] + i x[2n+1] = 2 * sum_k Z[k] e^{+2 pi i k n / M} = 2 * conj(FFT_M(conj Z))[n]
-template <typename T>
+template <typename T, int B>
 __global__ void __launch_bounds__(256)
 k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
             const typename C2<T>::type *__restrict__ twM, const typename C2<T>::type *__restrict__ twN, int Nz,
-            int log2m, int B, int64_t rows) {
+            int log2m, int64_t rows) {
     typedef typename C2<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C *sm = reinterpret_cast<C *>(smem_raw);
     const int M = Nz >> 1;
     const int Nzc = M + 1;
-    const int pitch = B + 1;
+    constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
     const int64_t n_tiles = (rows + B - 1) / B;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -195,7 +197,7 @@ k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
         int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
         const C *src = cplx + row0 * Nzc;
         for (int w = threadIdx.x; w < M * B; w += T_) {
-            int k = w % M, b = w / M;
+            int k = w & (M - 1), b = w >> log2m;
             C v = C{0, 0};
             if (b < bvalid) {
                 C xk = src[(int64_t)b * Nzc + k];
@@ -209,10 +211,10 @@ k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
             sm[k * pitch + b] = v;
         }
         __syncthreads();
-        fft_tile<C>(sm, twM, M, log2m, B, pitch);
+        fft_tile<C, B>(sm, twM, M, log2m);
         C *dst = reinterpret_cast<C *>(real + row0 * Nz);
         for (int w = threadIdx.x; w < M * B; w += T_) {
-            int n = w % M, b = w / M;
+            int n = w & (M - 1), b = w >> log2m;
             if (b < bvalid) {
                 C v = cconj(sm[pos_of_freq(n, M, log2m) * pitch + b]);
                 dst[(int64_t)b * M + n] = v;
@@ -294,15 +296,23 @@ static int launch_lines(void *data, int N, int64_t line_stride, int64_t n_inner,
     int B = pick_B(N, (int)sizeof(C), n_inner);
     size_t smem = (size_t)N * (B + 1) * sizeof(C);
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: N=%d does not fit in shared memory", N);
-    NBK_CUDA(cudaFuncSetAttribute(k_fft_lines<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t tiles_inner = (n_inner + B - 1) / B;
     int64_t n_tiles = tiles_inner * n_outer;
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
-    k_fft_lines<T><<<(int)g, 256, smem, s>>>((C *)data, (const C *)tw, N, ilog2(N), B, line_stride, n_inner,
-                                             tiles_inner, n_tiles, outer_stride, inverse, (T)scale);
+#define LAUNCH_LINES(BB)                                                                                          \
+    case BB:                                                                                                      \
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_lines<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_fft_lines<T, BB><<<(int)g, 256, smem, s>>>((C *)data, (const C *)tw, N, ilog2(N), line_stride, n_inner,   \
+                                                     tiles_inner, n_tiles, outer_stride, inverse, (T)scale);      \
+        break;
+    switch (B) {
+        LAUNCH_LINES(1) LAUNCH_LINES(2) LAUNCH_LINES(4) LAUNCH_LINES(8) LAUNCH_LINES(16)
+        default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
+    }
+#undef LAUNCH_LINES
     NBK_LAUNCHED();
     return NBK_OK;
 }
@@ -337,15 +347,23 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
-    if (forward) {
-        NBK_CUDA(cudaFuncSetAttribute(k_fft_z_r2c<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fft_z_r2c<T><<<(int)g, 256, smem, s>>>((const T *)in, (C *)out, (const C *)twM, (const C *)twN, Nz,
-                                                 ilog2(M), B, rows, (T)scale);
-    } else {
-        NBK_CUDA(cudaFuncSetAttribute(k_fft_z_c2r<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_fft_z_c2r<T><<<(int)g, 256, smem, s>>>((const C *)in, (T *)out, (const C *)twM, (const C *)twN, Nz,
-                                                 ilog2(M), B, rows);
+#define LAUNCH_Z(BB)                                                                                              \
+    case BB:                                                                                                      \
+        if (forward) {                                                                                            \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_z_r2c<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_z_r2c<T, BB><<<(int)g, 256, smem, s>>>((const T *)in, (C *)out, (const C *)twM, (const C *)twN, Nz, \
+                                                         ilog2(M), rows, (T)scale);                               \
+        } else {                                                                                                  \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_z_c2r<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_z_c2r<T, BB><<<(int)g, 256, smem, s>>>((const C *)in, (T *)out, (const C *)twM, (const C *)twN, Nz, \
+                                                         ilog2(M), rows);                                         \
+        }                                                                                                         \
+        break;
+    switch (B) {
+        LAUNCH_Z(1) LAUNCH_Z(2) LAUNCH_Z(4) LAUNCH_Z(8) LAUNCH_Z(16)
+        default: nbk_set_error("fft z pass: internal tile width %d", B); return NBK_ERR_ARG;
     }
+#undef LAUNCH_Z
     NBK_LAUNCHED();
     return NBK_OK;
 }
@@ -384,13 +402,13 @@ extern "C" int nbk_fft_zy_backward(void *cplx, void *real, int dtype, int64_t x_
                              : launch_z<double>(cplx, real, x_n * Ny, (int)Nz, false, 1.0, s);
 }
 
-extern "C" int nbk_r2c(const void *real, void *cplx, int dtype, const int64_t *nmesh, void *stream) {
+extern "C" int nbk_r2c(const void *real, void *cplx, int dtype, const int64_t *nmesh, double extra_scale, void *stream) {
     int rc = check_dims("r2c", dtype, nmesh[0], nmesh[1], nmesh[2]);
     if (rc) return rc;
     int64_t Nx = nmesh[0], Ny = nmesh[1], Nz = nmesh[2], Nzc = Nz / 2 + 1;
     rc = nbk_fft_zy_forward(real, cplx, dtype, Nx, Ny, Nz, stream);
     if (rc) return rc;
-    double scale = 1.0 / ((double)Nx * (double)Ny * (double)Nz);
+    double scale = extra_scale / ((double)Nx * (double)Ny * (double)Nz);
     if (Nx == 1) return nbk_scale(cplx, dtype, 2 * Ny * Nzc, scale, stream);
     return nbk_fft_lines(cplx, dtype, Nx, Ny * Nzc, Ny * Nzc, 1, 0, 0, scale, stream);
 }

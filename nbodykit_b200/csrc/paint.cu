@@ -68,6 +68,9 @@ struct PaintGeom {
 };
 
 __device__ __forceinline__ int wrap(long long i, int n) {
+    // in-box particles (the overwhelming majority) never pay for the 64-bit modulo
+    if ((unsigned long long)i < (unsigned long long)n) return (int)i;
+    if (i >= -(long long)n && i < 2ll * n) return (int)(i < 0 ? i + n : i - n);
     long long r = i % n;
     return (int)(r < 0 ? r + n : r);
 }
@@ -277,9 +280,16 @@ __device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, co
 
 // one atomic per distinct key per warp; returns this lane's rank within its key group and the group's base
 __device__ __forceinline__ unsigned warp_claim(unsigned *counter, int key, bool active) {
-    unsigned mask = __match_any_sync(__activemask(), active ? key : -1 - (int)(threadIdx.x & 31));
+    const int lane = threadIdx.x & 31;
+    // fast path: the whole warp is active and in one tile (spatially coherent catalogues)
+    int k0 = __shfl_sync(0xffffffffu, key, 0);
+    if (__all_sync(0xffffffffu, active && key == k0)) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&counter[key], 32u);
+        return __shfl_sync(0xffffffffu, base, 0) + lane;
+    }
+    unsigned mask = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
     if (!active) return 0;
-    int lane = threadIdx.x & 31;
     int leader = __ffs(mask) - 1;
     unsigned rank = __popc(mask & ((1u << lane) - 1));
     unsigned base = 0;
@@ -364,13 +374,13 @@ __device__ __forceinline__ void fixed_add(unsigned *lo, unsigned *hi, int cell, 
     if (h) atomicAdd(&hi[cell], h);
 }
 
-template <int SUP, typename PT, typename MT, typename FT>
+template <int SUP, typename PT, typename MT, typename FT, bool SHIFTED>
 __global__ void __launch_bounds__(256)
 k_tile_paint(const PT *__restrict__ spos, const MT *__restrict__ smass, TileGeom tg, double shift,
              const unsigned *__restrict__ offsets, unsigned *__restrict__ queue,
              const unsigned *__restrict__ absmax_bits, FT *__restrict__ mesh) {
     extern __shared__ unsigned s_acc[];
-    const int R = tg.R, R2 = R * R, R3 = R2 * R;
+    constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0), R2 = R * R, R3 = R2 * R;   // == tg.R
     unsigned *lo = s_acc, *hi = s_acc + R3;
     __shared__ int s_tile;
     // scale 2^31 / M, M = power of two >= max |mass|
@@ -518,17 +528,22 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass);
     NBK_LAUNCHED();
     size_t smem = (size_t)2 * tg.R * tg.R * tg.R * sizeof(unsigned);
-    NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = (int)((220 * 1024) / (smem + 2048));
     if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
     int grid = NBK_SM_COUNT * per_sm;
     if (grid > tg.ntiles) grid = tg.ntiles;
-    k_tile_paint<SUP, PT, MT, FT><<<grid, 256, smem, s>>>(spos, smass, tg, shift, offsets, queue, absmax, (FT *)mesh);
+    if (shifted) {
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_paint<SUP, PT, MT, FT, true><<<grid, 256, smem, s>>>(spos, smass, tg, shift, offsets, queue, absmax, (FT *)mesh);
+    } else {
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_tile_paint<SUP, PT, MT, FT, false><<<grid, 256, smem, s>>>(spos, smass, tg, shift, offsets, queue, absmax, (FT *)mesh);
+    }
     NBK_LAUNCHED();
     if (mesh2) {
         NBK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), s));
-        k_tile_paint<SUP, PT, MT, FT><<<grid, 256, smem, s>>>(spos, smass, tg, 0.5, offsets, queue, absmax, (FT *)mesh2);
+        k_tile_paint<SUP, PT, MT, FT, true><<<grid, 256, smem, s>>>(spos, smass, tg, 0.5, offsets, queue, absmax, (FT *)mesh2);
         NBK_LAUNCHED();
     }
     return NBK_OK;

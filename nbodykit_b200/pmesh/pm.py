@@ -581,9 +581,10 @@ class RealField(Field):
     def dtype(self):
         return self.pm.dtype
 
-    def r2c(self, out=None):
+    def r2c(self, out=None, scale=1.0):
         """forward FFT, normalised by 1/prod(N).  out=Ellipsis has no in-place meaning here (the
-        transform is out of place); the real buffer stays valid."""
+        transform is out of place); the real buffer stays valid.  `scale` (extension) multiplies the
+        result inside the last FFT pass -- e.g. the 1/nbar of the 1+delta normalisation."""
         pm = self.pm
         if out is None or out is Ellipsis:
             out = ComplexField(pm)
@@ -592,7 +593,7 @@ class RealField(Field):
         Nx, Ny, Nz = [int(v) for v in pm.Nmesh]
         if P == 1:
             with stage("r2c"):
-                check(lib().nbk_r2c(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, _stream()), "nbk_r2c")
+                check(lib().nbk_r2c(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, float(scale), _stream()), "nbk_r2c")
         else:
             Nzc = pm.Nzc
             work = torch.empty((pm.x_n, Ny, Nzc), dtype=out.value.dtype, device=out.value.device)
@@ -602,7 +603,7 @@ class RealField(Field):
             recv = work.view(-1)
             pm.comm.all_to_all_single(recv, send.view(-1))
             check(lib().nbk_transpose_unpack(_ptr(recv), _ptr(out.value), code, pm.y_n, Nx, Nzc, P, _stream()), "transpose_unpack")
-            scale = 1.0 / (float(Nx) * Ny * Nz)
+            scale = float(scale) / (float(Nx) * Ny * Nz)
             check(lib().nbk_fft_lines(_ptr(out.value), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 0, scale, _stream()), "fft_lines(x)")
         out.attrs = dict(self.attrs)
         return out

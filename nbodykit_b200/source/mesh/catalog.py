@@ -246,17 +246,26 @@ class CatalogMesh(MeshSource):
             c = real.r2c()
         elif self.interlaced:
             real1, real2 = painted
-            c = real1.r2c()
-            c2 = real2.r2c()
+            c = real1.r2c(scale=1.0 / nbar)          # normalisation folded into the FFT's last pass
+            c2 = real2.r2c(scale=1.0 / nbar)
             c.interlace_combine(c2)
-            c *= (1.0 / nbar)
         else:
-            c = painted.r2c()
-            c *= (1.0 / nbar)
+            c = painted.r2c(scale=1.0 / nbar)
         c.attrs = attrs
         if self.pm.comm.rank == 0:
             self.logger.info("painted %d out of %d objects to mesh" % (N, self.source.csize))
         return c
+
+    def compute_complex_deferred(self):
+        """FFTPower fast path: (complex field WITHOUT the window compensation, name of the compensation the
+        caller must still apply) when the compensation is the only action -- the power-binning kernel then
+        applies it on the fly.  Falls back to (compute('complex'), None)."""
+        own = self._get_compensation() if self.compensated else []
+        if list(MeshSource.actions.fget(self)) or not own:
+            return self.compute(mode='complex'), None
+        c = self.to_complex_field()
+        c.attrs.update(self.attrs)
+        return c, own[0][1].__name__
 
     @property
     def actions(self):

@@ -36,7 +36,7 @@ def test_version_and_error_calls_work_without_gpu():
     # argument validation happens before any CUDA call: a bad dtype is rejected with a message
     rc = L.nbk_fill(None, 3, 10, 0.0, None)
     assert rc == -1 and b"dtype" in L.nbk_last_error()
-    rc = L.nbk_r2c(None, None, 8, _lib.iarr([12, 12, 12]), None)
+    rc = L.nbk_r2c(None, None, 8, _lib.iarr([12, 12, 12]), 1.0, None)
     assert rc == -1 and b"power of two" in L.nbk_last_error()
 
 

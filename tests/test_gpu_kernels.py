@@ -361,3 +361,42 @@ def test_paint_auto_dispatch_matches(cuda):
         a = pm.paint(pos, resampler="cic").numpy()
         w = po.paint(pos, None, N, L, "cic")
         np.testing.assert_allclose(a, w, rtol=0, atol=1e-7 * w.max())
+
+
+def test_power_bin_fused_compensation_equals_two_pass(cuda):
+    """nbk_power_bin(comp1, comp2) == nbk_compensate on each field followed by nbk_power_bin"""
+    from nbodykit_b200.algorithms.fftpower import project_to_basis_device
+    from nbodykit_b200.pmesh.pm import ComplexField
+    N, L = [16, 32, 16], [100., 200., 100.]
+    rng = np.random.RandomState(21)
+    shape = (N[0], N[1], N[2] // 2 + 1)
+    a = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    b = rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+    pm = _pm(N, L, "f8")
+    dk = 2 * np.pi / 100.
+    edges = [np.arange(0., np.pi * 16 / 200. + dk / 2, dk), np.linspace(-1, 1, 4)]
+    for n1, n2 in [("CompensateCICShotnoise", "CompensateCICShotnoise"), ("CompensateTSC", "CompensatePCSShotnoise")]:
+        f1, f2 = ComplexField(pm), ComplexField(pm)
+        f1[...] = a; f2[...] = b
+        fused = project_to_basis_device(f1, edges, poles=[0, 2], is_p3d=False, second=f2, volume=3.0,
+                                        compensation=(n1, n2))
+        f1.compensate(n1); f2.compensate(n2)
+        two = project_to_basis_device(f1, edges, poles=[0, 2], is_p3d=False, second=f2, volume=3.0)
+        assert np.array_equal(fused[0][3], two[0][3])
+        np.testing.assert_allclose(np.nan_to_num(fused[0][2]), np.nan_to_num(two[0][2]), rtol=1e-12)
+        np.testing.assert_allclose(np.nan_to_num(fused[1][1]), np.nan_to_num(two[1][1]), rtol=1e-11, atol=1e-12)
+    # auto power: the same transfer function applies to both factors
+    f1 = ComplexField(pm); f1[...] = a
+    fused = project_to_basis_device(f1, edges, is_p3d=False, volume=1.0, compensation=("CompensateTSCShotnoise", None))
+    f1.compensate("CompensateTSCShotnoise")
+    two = project_to_basis_device(f1, edges, is_p3d=False, volume=1.0)
+    np.testing.assert_allclose(np.nan_to_num(fused[0][2]), np.nan_to_num(two[0][2]), rtol=1e-12)
+
+
+def test_r2c_extra_scale(cuda):
+    from nbodykit_b200.pmesh.pm import RealField
+    real = np.random.RandomState(6).standard_normal((16, 16, 16))
+    pm = _pm(16, 1.0, "f8")
+    f = RealField(pm)
+    f[...] = real
+    np.testing.assert_allclose(f.r2c(scale=2.5).numpy(), 2.5 * f.r2c().numpy(), rtol=1e-14)

@@ -40,24 +40,27 @@ def main():
     pos = torch.rand((n, 3), device=dev, dtype=torch.float32, generator=g) * L
     out = {"nmesh": N, "npart": n, "dtype": args.dtype}
     real = RealField(pm); real[...] = 0
-    for name, p in [("random", pos), ("xsorted", pos[torch.argsort(pos[:, 0])].contiguous())]:
+    for name, p in [("random", pos)]:
         for res in ["cic", "tsc"]:
-            t = timeit(lambda: pm.paint(p, resampler=res, hold=True, out=real))
-            out["paint_%s_%s_ms" % (res, name)] = t
-            print("paint %s %s: %.3f ms (median %.3f) -> %.3e particles/s" % (res, name, t[0], t[1], n / t[0] * 1e3), flush=True)
+            for method in ["direct", "tiled"]:
+                t = timeit(lambda: pm.paint(p, resampler=res, hold=True, out=real, method=method))
+                out["paint_%s_%s_%s_ms" % (res, name, method)] = t
+                print("paint %s %s %s: %.3f ms (median %.3f) -> %.3e particles/s" % (res, name, method, t[0], t[1], n / t[0] * 1e3), flush=True)
     # cell-sorted (morton-ish: sort by cell id)
     cell = (pos / (L / N)).floor().long()
     key = (cell[:, 0] * N + cell[:, 1]) * N + cell[:, 2]
     ps = pos[torch.argsort(key)].contiguous()
     del cell, key
     for res in ["cic", "tsc"]:
-        t = timeit(lambda: pm.paint(ps, resampler=res, hold=True, out=real))
-        out["paint_%s_cellsorted_ms" % res] = t
-        print("paint %s cellsorted: %.3f ms -> %.3e particles/s" % (res, t[0], n / t[0] * 1e3), flush=True)
+        for method in ["direct", "tiled"]:
+            t = timeit(lambda: pm.paint(ps, resampler=res, hold=True, out=real, method=method))
+            out["paint_%s_cellsorted_%s_ms" % (res, method)] = t
+            print("paint %s cellsorted %s: %.3f ms -> %.3e particles/s" % (res, method, t[0], n / t[0] * 1e3), flush=True)
     r2 = RealField(pm); r2[...] = 0
-    t = timeit(lambda: pm.paint_interlaced(ps, None, "tsc", real, r2))
-    print("paint tsc interlaced cellsorted: %.3f ms -> %.3e particles/s" % (t[0], n / t[0] * 1e3), flush=True)
-    out["paint_tsc_interlaced_cellsorted_ms"] = t
+    for method in ["direct", "tiled"]:
+        t = timeit(lambda: pm.paint_interlaced(ps, None, "tsc", real, r2, method=method))
+        print("paint tsc interlaced cellsorted %s: %.3f ms -> %.3e particles/s" % (method, t[0], n / t[0] * 1e3), flush=True)
+        out["paint_tsc_interlaced_cellsorted_%s_ms" % method] = t
     del r2
     c = ComplexField(pm)
     t = timeit(lambda: real.r2c(out=c))
