@@ -154,6 +154,16 @@ int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double 
                   const double *los_host, const int *ells_host, int Nell, int hermitian, int comp1,
                   int comp2, int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
 
+/* ConvolvedFFTPower's spherical-harmonic passes (algorithms/convpower/fkp.py:571-597), real Y_lm, l <= 8:
+ *   out(x) = in(x) * Y_lm(xhat), x = wrapped grid coordinate [-L/2, L/2) + offset[3] (BoxCenter + H/2, :457);
+ *   acc(k) += c(k) * Y_lm(khat), khat := 0 at k = 0 (:537). */
+int nbk_ylm_mul_real(const void *in, void *out, int dtype, int l, int m, const int64_t *nmesh_host,
+                     const double *boxsize_host, const double *offset_host, int64_t x_start, int64_t x_n,
+                     void *stream);
+int nbk_ylm_mul_complex_acc(void *acc, const void *c, int dtype, int l, int m, const int64_t *nmesh_host,
+                            const double *boxsize_host, int transposed, int64_t start, int64_t count,
+                            void *stream);
+
 /* elementwise helpers behind RealField/ComplexField `[...] = v`, `*= a`, `+= other`
  * (source/mesh/catalog.py:203,354,396-398; fftpower.py:128).  n counts REAL scalars. */
 int nbk_fill(void *x, int dtype, int64_t n, double value, void *stream);

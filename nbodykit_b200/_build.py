@@ -19,6 +19,7 @@ SOURCES = [
     ("paint.cu", ["--fmad=false"]),
     ("fft.cu", []),
     ("binning.cu", ["--fmad=false"]),
+    ("ylm.cu", []),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]
@@ -33,7 +34,7 @@ def _nvcc():
 
 def _stamp(path, flags):
     h = hashlib.sha1()
-    for dep in [path, os.path.join(CSRC, "common.cuh"),
+    for dep in [path, os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "ylm_table.inc"),
                 os.path.join(HERE, "..", "include", "nbk_b200.h")]:
         with open(dep, "rb") as f:
             h.update(f.read())

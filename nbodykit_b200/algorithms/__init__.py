@@ -1,3 +1,7 @@
 from .fftpower import FFTPower, FFTBase, project_to_basis
+from .convpower import ConvolvedFFTPower, FKPCatalog, FKPWeightFromNbar, FKPCatalogMesh
 
-__all__ = ['FFTPower', 'FFTBase', 'project_to_basis']
+FKPPower = ConvolvedFFTPower
+
+__all__ = ['FFTPower', 'FFTBase', 'project_to_basis', 'ConvolvedFFTPower', 'FKPPower', 'FKPCatalog',
+           'FKPWeightFromNbar', 'FKPCatalogMesh']

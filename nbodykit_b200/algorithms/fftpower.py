@@ -211,7 +211,7 @@ def _los_coord_mode(los, coord_dtype):
 
 
 def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4", is_p3d=True, second=None,
-                            volume=1.0, compensation=(None, None)):
+                            volume=1.0, compensation=(None, None), clear_zero=True):
     """
     project_to_basis (fftpower.py:507-701) for a device ComplexField.
 
@@ -254,7 +254,7 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     with stage("power_bin"):
         check(lib().nbk_power_bin(
             _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
-            1 if is_p3d else 0, float(volume), 1, pm._nmesh_c, pm._box_c, tr, start, count,
+            1 if is_p3d else 0, float(volume), 1 if clear_zero else 0, pm._nmesh_c, pm._box_c, tr, start, count,
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
             _lib.i32arr(_poles), Nell, 1, _lib.COMP.get(compensation[0], 0), _lib.COMP.get(compensation[1], 0),
             _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")

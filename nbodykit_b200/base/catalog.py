@@ -69,6 +69,13 @@ class Column(object):
             return Column(self.data.to(getattr(torch, numpy.dtype(dtype).name)))
         return Column(self.data.astype(dtype))
 
+    def sum(self, axis=None):
+        """sum of the column (a Python float / array for axis != None); device columns reduce on the device"""
+        if _is_torch(self.data):
+            r = self.data.double().sum() if axis is None else self.data.double().sum(dim=axis)
+            return float(r.item()) if axis is None else r.cpu().numpy()
+        return self.data.sum(axis=axis, dtype='f8' if self.data.dtype.kind == 'f' else None)
+
     def __repr__(self):
         where = ("torch:%s" % self.data.device) if _is_torch(self.data) else "numpy"
         return "Column(shape=%s, dtype=%s, %s)" % (self.shape, self.dtype, where)
@@ -130,6 +137,9 @@ class ConstantColumn(Column):
 
     def compute(self):
         return self.materialize()
+
+    def sum(self, axis=None):
+        return self.value * self.size
 
     def __array__(self, dtype=None, copy=None):
         a = self.materialize()
@@ -327,6 +337,14 @@ class CatalogSourceBase(object):
             else:
                 out.append(a.compute() if isinstance(a, Column) else a)
         return out[0] if len(out) == 1 else tuple(out)
+
+    def read(self, columns):
+        """list of columns by name (base/catalog.py `read`)"""
+        missing = set(columns) - set(self.columns)
+        if len(missing) > 0:
+            raise ValueError("source does not contain columns: %s; " % str(missing) +
+                             "try adding columns via `source[column] = data`")
+        return [self[col] for col in columns]
 
     def copy(self):
         return self._subset(slice(None))

@@ -7,10 +7,10 @@
 //   y pass  : lines strided by Nzc, tiles of B adjacent kz columns  (B*sizeof(cplx) >= 64 B runs)
 //   x pass  : lines strided by Ny*Nzc, tiles of B adjacent (y,kz) elements
 // Every pass stages a [N][B] tile (pitch B+1: conflict-free both for the butterfly access and for
-// the transposed fill of the z pass) in shared memory, runs an in-place radix-4 (+ one radix-2)
-// decimation-in-frequency FFT, and writes frequencies out through the digit-reversal map, so no
-// ping-pong buffer is needed.  Twiddles come from an f8-accurate table built on the device with
-// sincospi.  Sizes: powers of two.
+// the transposed fill of the z pass) in shared memory, runs an in-place decimation-in-frequency FFT
+// with register-resident radix-8 butterflies (+ one radix-4 / radix-2 stage for the remainder), and
+// writes frequencies out through the mixed-radix digit-reversal map, so no ping-pong buffer is needed.
+// Twiddles: f8-accurate table built on the device with sincospi, staged in shared memory.  Sizes: 2^k.
 #include "common.cuh"
 #include <map>
 #include <mutex>
@@ -28,52 +28,96 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
 template <typename C> __device__ __forceinline__ C cconj(C a) { return C{a.x, -a.y}; }
 template <typename C> __device__ __forceinline__ C cmuli_neg(C a) { return C{a.y, -a.x}; }  // a * (-i)
 
-// position (in the in-place DIF output) of frequency k
+// Stage plan: radix-8 stages, then one radix-4 or radix-2 stage for the remainder of log2(N).
+// position (in the in-place DIF output) of frequency k = mixed-radix digit reversal
 __device__ __forceinline__ int pos_of_freq(int k, int N, int log2n) {
     int rem = k, base = N, pos = 0;
-    for (int s = 0; s < (log2n >> 1); s++) {
-        int d = rem & 3;
-        rem >>= 2;
-        base >>= 2;
+    const int n8 = log2n / 3, r = log2n - 3 * n8;
+    for (int s = 0; s < n8; s++) {
+        int d = rem & 7;
+        rem >>= 3;
+        base >>= 3;
         pos += d * base;
     }
-    if (log2n & 1) pos += (rem & 1);
+    if (r == 2) pos += (rem & 3);        // base == 4 -> base/4 == 1
+    else if (r == 1) pos += (rem & 1);
     return pos;
 }
 
-// In-place forward DIF FFT of B side-by-side lines of length N held in sm[n*pitch + b].
-// tw[k] = exp(-2 pi i k / N), k < N.  All threads of the CTA must call.
+template <typename C> struct Sqrt1_2;
+template <> struct Sqrt1_2<float2> { static __device__ __forceinline__ float v() { return 0.70710678118654752440f; } };
+template <> struct Sqrt1_2<double2> { static __device__ __forceinline__ double v() { return 0.70710678118654752440; } };
+
+// 4-point DFT (forward): X0 = c0+c1, X1 = c2+c3, X2 = c0-c1, X3 = c2-c3
+template <typename C>
+__device__ __forceinline__ void dft4(C &a0, C &a1, C &a2, C &a3) {
+    C c0 = cadd(a0, a2), c1 = cadd(a1, a3), c2 = csub(a0, a2), c3 = cmuli_neg(csub(a1, a3));
+    a0 = cadd(c0, c1);
+    a1 = cadd(c2, c3);
+    a2 = csub(c0, c1);
+    a3 = csub(c2, c3);
+}
+
+// In-place forward DIF FFT of B side-by-side lines of length N held in sm[n*(B+1) + b].
+// tw[k] = exp(-2 pi i k / N), k < N (shared or global memory).  All threads of the CTA must call.
+// Each radix-8 butterfly lives in registers: 8 LDS + 8 STS per 8 points per stage (3 stages at N = 512).
 template <typename C, int B>
 __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N, int log2n) {
     constexpr int pitch = B + 1;
     const int T = blockDim.x;
+    const int n8 = log2n / 3, rrem = log2n - 3 * n8;
     int Ns = N;
-    for (int s = 0; s < (log2n >> 1); s++) {
-        const int Q = Ns >> 2;
-        const int lq = log2n - 2 * (s + 1);     // log2(Q)
+    int lq = log2n;
+    for (int s = 0; s < n8; s++) {
+        const int Q = Ns >> 3;
+        lq -= 3;                       // log2(Q)
         const int tws = N / Ns;
-        const int work = (N >> 2) * B;
+        const int work = (N >> 3) * B;
+        const int st = Q * pitch;
         for (int w = threadIdx.x; w < work; w += T) {
             int b = w % B;
             int t = w / B;
             int blk = t >> lq, q = t & (Q - 1);
             C *p = sm + (blk * Ns + q) * pitch + b;
-            const int st = Q * pitch;
             C a0 = p[0], a1 = p[st], a2 = p[2 * st], a3 = p[3 * st];
-            C t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = cmuli_neg(csub(a1, a3));
-            C y0 = cadd(t0, t2), y1 = cadd(t1, t3), y2 = csub(t0, t2), y3 = csub(t1, t3);
+            C a4 = p[4 * st], a5 = p[5 * st], a6 = p[6 * st], a7 = p[7 * st];
+            // level 1: b_m = a_m + a_{m+4}; b_{m+4} = (a_m - a_{m+4}) W8^m
+            C b0 = cadd(a0, a4), b1 = cadd(a1, a5), b2 = cadd(a2, a6), b3 = cadd(a3, a7);
+            C b4 = csub(a0, a4), d5 = csub(a1, a5), d6 = csub(a2, a6), d7 = csub(a3, a7);
+            const auto h = Sqrt1_2<C>::v();
+            C b5 = C{(d5.x + d5.y) * h, (d5.y - d5.x) * h};     // * (1 - i)/sqrt2
+            C b6 = cmuli_neg(d6);                                // * (-i)
+            C b7 = C{(d7.y - d7.x) * h, -(d7.x + d7.y) * h};    // * (-1 - i)/sqrt2
+            dft4(b0, b1, b2, b3);      // -> y0, y2, y4, y6
+            dft4(b4, b5, b6, b7);      // -> y1, y3, y5, y7
             if (Q > 1) {
                 int ti = q * tws;
-                y1 = cmul(y1, tw[ti]);
-                y2 = cmul(y2, tw[2 * ti]);
-                y3 = cmul(y3, tw[3 * ti]);
+                b4 = cmul(b4, tw[ti]);
+                b1 = cmul(b1, tw[2 * ti]);
+                b5 = cmul(b5, tw[3 * ti]);
+                b2 = cmul(b2, tw[4 * ti]);
+                b6 = cmul(b6, tw[5 * ti]);
+                b3 = cmul(b3, tw[6 * ti]);
+                b7 = cmul(b7, tw[7 * ti]);
             }
-            p[0] = y0; p[st] = y1; p[2 * st] = y2; p[3 * st] = y3;
+            p[0] = b0; p[st] = b4; p[2 * st] = b1; p[3 * st] = b5;
+            p[4 * st] = b2; p[5 * st] = b6; p[6 * st] = b3; p[7 * st] = b7;
         }
         __syncthreads();
         Ns = Q;
     }
-    if (log2n & 1) {  // Ns == 2
+    if (rrem == 2) {   // Ns == 4, Q == 1: no twiddles
+        const int work = (N >> 2) * B;
+        for (int w = threadIdx.x; w < work; w += T) {
+            int b = w % B;
+            int t = w / B;
+            C *p = sm + (4 * t) * pitch + b;
+            C a0 = p[0], a1 = p[pitch], a2 = p[2 * pitch], a3 = p[3 * pitch];
+            dft4(a0, a1, a2, a3);
+            p[0] = a0; p[pitch] = a1; p[2 * pitch] = a2; p[3 * pitch] = a3;
+        }
+        __syncthreads();
+    } else if (rrem == 1) {  // Ns == 2
         const int work = (N >> 1) * B;
         for (int w = threadIdx.x; w < work; w += T) {
             int b = w % B;
@@ -85,6 +129,14 @@ __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N,
         }
         __syncthreads();
     }
+}
+
+// copy the twiddle table into shared memory (after the tile); returns the shared pointer
+template <typename C>
+__device__ __forceinline__ const C *stage_twiddles(C *dst, const C *__restrict__ tw, int N) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) dst[i] = tw[i];
+    __syncthreads();
+    return dst;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -101,6 +153,7 @@ k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type 
     C *sm = reinterpret_cast<C *>(smem_raw);
     constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
+    tw = stage_twiddles<C>(sm + N * pitch, tw, N);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t outer = tile / tiles_inner;
         int64_t inner0 = (tile - outer * tiles_inner) * B;
@@ -147,6 +200,7 @@ k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
     constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
     const int64_t n_tiles = (rows + B - 1) / B;
+    twM = stage_twiddles<C>(sm + M * pitch, twM, M);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t row0 = tile * B;
         int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
@@ -192,6 +246,7 @@ k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
     constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
     const int64_t n_tiles = (rows + B - 1) / B;
+    twM = stage_twiddles<C>(sm + M * pitch, twM, M);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t row0 = tile * B;
         int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
@@ -273,7 +328,7 @@ static bool is_pow2(int64_t n) { return n > 0 && (n & (n - 1)) == 0; }
 // pick the number of side-by-side lines: >= 64 B contiguous runs, tile <= ~96 KB (2 CTAs / SM)
 static int pick_B(int N, int csize, int64_t n_inner) {
     int B = 128 / csize;  // 128-byte runs: 16 (c8) or 8 (c16)
-    while (B > 1 && (size_t)N * (B + 1) * csize > 98304) B >>= 1;
+    while (B > 1 && (size_t)N * (B + 2) * csize > 98304) B >>= 1;
     while (B > 1 && B / 2 >= n_inner) B >>= 1;
     return B;
 }
@@ -294,7 +349,7 @@ static int launch_lines(void *data, int N, int64_t line_stride, int64_t n_inner,
     int rc = get_twiddle(N, dtype, s, &tw);
     if (rc) return rc;
     int B = pick_B(N, (int)sizeof(C), n_inner);
-    size_t smem = (size_t)N * (B + 1) * sizeof(C);
+    size_t smem = (size_t)N * (B + 2) * sizeof(C);     // tile [N][B+1] + twiddle table [N]
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: N=%d does not fit in shared memory", N);
     int64_t tiles_inner = (n_inner + B - 1) / B;
     int64_t n_tiles = tiles_inner * n_outer;
@@ -340,7 +395,7 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
     rc = get_twiddle(Nz, dtype, s, &twN);
     if (rc) return rc;
     int B = pick_B(M, (int)sizeof(C), rows);
-    size_t smem = (size_t)M * (B + 1) * sizeof(C);
+    size_t smem = (size_t)M * (B + 2) * sizeof(C);     // tile [M][B+1] + twiddle table [M]
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);
     int64_t n_tiles = (rows + B - 1) / B;
     int per_sm = (int)((227 * 1024) / (smem + 1024));

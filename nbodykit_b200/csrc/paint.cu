@@ -9,6 +9,7 @@
 // loops), while REDG f32/f64 is native, so the mesh itself is the accumulator and the L2 (126 MB)
 // absorbs the read-modify-write of spatially coherent catalogues.
 #include "common.cuh"
+#include <stdlib.h>
 
 template <int SUP> struct Window;
 
@@ -244,6 +245,11 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 // =============================================================================================
 #define TILE 16
 
+// tile-ordered particle record: one aligned vector per particle (x, y, z, pad)
+template <typename PT> struct Rec;
+template <> struct Rec<float> { typedef float4 type; };
+template <> struct Rec<double> { typedef double4 type; };
+
 struct TileGeom {
     PaintGeom gm;
     int G;            // ghost reach below the slab in x (0 when the slab is the whole mesh)
@@ -260,8 +266,23 @@ __device__ __forceinline__ int slab_local(int ix, const TileGeom &tg) {
     return lx;
 }
 
+// leftmost-cell offsets of the windows: i0 = floor(g + OFF_A) + OFF_B
+template <int SUP> struct WinOff;
+template <> struct WinOff<1> { static constexpr float A = 0.5f; static constexpr int B = 0; };
+template <> struct WinOff<2> { static constexpr float A = 0.0f; static constexpr int B = 0; };
+template <> struct WinOff<3> { static constexpr float A = 0.5f; static constexpr int B = -1; };
+template <> struct WinOff<4> { static constexpr float A = 0.0f; static constexpr int B = -1; };
+
+__device__ __forceinline__ int tile_from_cells(const int *c, const TileGeom &tg) {
+    int lx = slab_local(c[0], tg);
+    if (lx < -tg.G || lx >= tg.gm.x_n) return -1;   // cannot touch my planes
+    int tx = (lx + tg.G) / TILE, ty = c[1] / TILE, tz = c[2] / TILE;
+    return (tx * tg.nt[1] + ty) * tg.nt[2] + tz;
+}
+
+// exact (f8) tile id: the arithmetic of the scatter itself
 template <int SUP, typename PT>
-__device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, const TileGeom &tg) {
+__device__ __noinline__ int tile_of_exact(const PT *__restrict__ pos, int64_t i, const TileGeom &tg) {
     double g[3];
     if (!load_grid(pos, i, tg.gm, 0.0, g)) return -1;
     int c[3];
@@ -272,10 +293,33 @@ __device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, co
         Window<SUP>::eval(g[d], i0, w);
         c[d] = wrap(i0, tg.gm.n[d]);
     }
-    int lx = slab_local(c[0], tg);
-    if (lx < -tg.G || lx >= tg.gm.x_n) return -1;   // cannot touch my planes
-    int tx = (lx + tg.G) / TILE, ty = c[1] / TILE, tz = c[2] / TILE;
-    return (tx * tg.nt[1] + ty) * tg.nt[2] + tz;
+    return tile_from_cells(c, tg);
+}
+
+// Tile id of particle i.  float32 positions take a float32 fast path: g32 = x*scale differs from the f8 grid
+// coordinate by < 2^-22 |g|, so unless the fraction of (g32 + A) lies within 3e-7|g| of a cell boundary (or the
+// particle is far outside the box) floor() agrees with the exact arithmetic; the rare rest is recomputed in f8.
+// The result is therefore ALWAYS the exact leftmost cell -- count, scatter and paint passes agree.
+template <int SUP, typename PT>
+__device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
+                                       const float *sc32) {
+    if (sizeof(PT) == 4) {
+        int c[3];
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float g = (float)pos[3 * i + d] * sc32[d] + WinOff<SUP>::A;
+            float f = floorf(g);
+            float fr = g - f;
+            float eps = 3e-7f * fabsf(g) + 1e-6f;      // > |g32 - g_exact| (two float32 roundings)
+            ok = ok && (fr > eps) && (fr < 1.0f - eps) && (fabsf(g) < 65536.0f);
+            int ci = (int)f + WinOff<SUP>::B;
+            c[d] = ci < 0 ? ci + tg.gm.n[d] : (ci >= tg.gm.n[d] ? ci - tg.gm.n[d] : ci);
+            ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
+        }
+        if (ok) return tile_from_cells(c, tg);
+    }
+    return tile_of_exact<SUP, PT>(pos, i, tg);
 }
 
 // one atomic per distinct key per warp; returns this lane's rank within its key group and the group's base
@@ -304,10 +348,11 @@ k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n,
              unsigned *__restrict__ counts, unsigned *__restrict__ absmax_bits) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float mx = 0.f;
+    const float sc32[3] = {(float)tg.gm.scale[0], (float)tg.gm.scale[1], (float)tg.gm.scale[2]};
     int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
-        int t = in ? tile_of<SUP, PT>(pos, i, tg) : -1;
+        int t = in ? tile_of<SUP, PT>(pos, i, tg, sc32) : -1;
         warp_claim(counts, t, t >= 0);
         if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);
     }
@@ -348,40 +393,61 @@ k_tile_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ offsets,
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(256)
 k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg,
-               const unsigned *__restrict__ offsets, unsigned *__restrict__ cursor, PT *__restrict__ spos,
-               MT *__restrict__ smass) {
+               const unsigned *__restrict__ offsets, unsigned *__restrict__ cursor,
+               typename Rec<PT>::type *__restrict__ spos, MT *__restrict__ smass) {
+    typedef typename Rec<PT>::type R4;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const float sc32[3] = {(float)tg.gm.scale[0], (float)tg.gm.scale[1], (float)tg.gm.scale[2]};
     int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
-        int t = in ? tile_of<SUP, PT>(pos, i, tg) : -1;
+        int t = in ? tile_of<SUP, PT>(pos, i, tg, sc32) : -1;
         unsigned slot = warp_claim(cursor, t, t >= 0);
         if (t >= 0) {
             int64_t dst = (int64_t)offsets[t] + slot;
-            spos[3 * dst] = pos[3 * i];
-            spos[3 * dst + 1] = pos[3 * i + 1];
-            spos[3 * dst + 2] = pos[3 * i + 2];
+            R4 r;
+            r.x = pos[3 * i]; r.y = pos[3 * i + 1]; r.z = pos[3 * i + 2]; r.w = 0;
+            spos[dst] = r;                       // one 16-byte (f4) / 32-byte (f8) store per particle
             if (mass) smass[dst] = mass[i];
         }
     }
 }
 
-__device__ __forceinline__ void fixed_add(unsigned *lo, unsigned *hi, int cell, long long q) {
+// 64-bit fixed-point cell = two adjacent 32-bit limbs {lo, hi}; deposits are native ATOMS.ADD on the low
+// limb, the carry (seen in the returned old value) goes to the high limb.
+__device__ __forceinline__ void fixed_add(unsigned *acc, int cell, long long q) {
     unsigned ql = (unsigned)q, qh = (unsigned)(q >> 32);
-    unsigned old = atomicAdd(&lo[cell], ql);           // ATOMS.ADD (native)
-    unsigned carry = (unsigned)(old + ql < old);
-    unsigned h = qh + carry;
-    if (h) atomicAdd(&hi[cell], h);
+    unsigned old = atomicAdd(&acc[2 * cell], ql);
+    unsigned h = qh + (unsigned)(old + ql < old);
+    if (h) atomicAdd(&acc[2 * cell + 1], h);
+}
+// non-negative deposit: 0 <= q <= 2^31 fits the low limb
+__device__ __forceinline__ void fixed_add_pos(unsigned *acc, int cell, unsigned ql) {
+    unsigned old = atomicAdd(&acc[2 * cell], ql);
+    if (old + ql < old) atomicAdd(&acc[2 * cell + 1], 1u);
 }
 
-template <int SUP, typename PT, typename MT, typename FT, bool SHIFTED>
+__device__ __forceinline__ void tma_reduce_add(double *gdst, const void *ssrc, unsigned bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add(float *gdst, const void *ssrc, unsigned bytes) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(sa), "r"(bytes) : "memory");
+}
+
+// FLUSH 0: per-cell read-add-store (exclusive cells) / REDG (halo)   1: TMA bulk reduce-add, one row per op
+template <int SUP, typename PT, typename MT, typename FT, bool SHIFTED, int FLUSH>
 __global__ void __launch_bounds__(256)
-k_tile_paint(const PT *__restrict__ spos, const MT *__restrict__ smass, TileGeom tg, double shift,
+k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restrict__ smass, TileGeom tg, double shift,
              const unsigned *__restrict__ offsets, unsigned *__restrict__ queue,
              const unsigned *__restrict__ absmax_bits, FT *__restrict__ mesh) {
-    extern __shared__ unsigned s_acc[];
-    constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0), R2 = R * R, R3 = R2 * R;   // == tg.R
-    unsigned *lo = s_acc, *hi = s_acc + R3;
+    extern __shared__ __align__(16) unsigned s_acc[];
+    constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0);   // == tg.R
+    constexpr int RP = (R + 3) & ~3;                         // row pitch in cells: rows start 16-byte aligned
+    constexpr int NC = R * R * RP;
     __shared__ int s_tile;
     // scale 2^31 / M, M = power of two >= max |mass|
     double M = 1.0;
@@ -392,7 +458,7 @@ k_tile_paint(const PT *__restrict__ spos, const MT *__restrict__ smass, TileGeom
         M = mx > 0.f ? ldexp(1.0, e) : 1.0;
     }
     const double S = 2147483648.0 / M, invS = M / 2147483648.0;
-    const int H = R - TILE;   // cells with a local coordinate < H may also be written by the preceding tile
+    constexpr int H = R - TILE;   // cells with a local coordinate < H may also be written by the preceding tile
     for (;;) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(queue, 1u);
         __syncthreads();
@@ -400,7 +466,7 @@ k_tile_paint(const PT *__restrict__ spos, const MT *__restrict__ smass, TileGeom
         if (t >= tg.ntiles) break;
         unsigned b = offsets[t], e = offsets[t + 1];
         if (b == e) { __syncthreads(); continue; }
-        for (int i = threadIdx.x; i < 2 * R3; i += blockDim.x) s_acc[i] = 0u;
+        for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
         int tz = t % tg.nt[2], ty = (t / tg.nt[2]) % tg.nt[1], tx = t / (tg.nt[2] * tg.nt[1]);
         int o[3] = {tx * TILE - tg.G, ty * TILE, tz * TILE};   // region origin (x: slab-local)
         int gox = o[0] + tg.gm.x_start;                         // ... and as a global plane index
@@ -408,7 +474,13 @@ k_tile_paint(const PT *__restrict__ spos, const MT *__restrict__ smass, TileGeom
         __syncthreads();
         for (unsigned p = b + threadIdx.x; p < e; p += blockDim.x) {
             double g[3];
-            if (!load_grid(spos, (int64_t)p, tg.gm, shift, g)) continue;
+            {
+                typename Rec<PT>::type r = spos[p];
+                g[0] = (double)r.x * tg.gm.scale[0] + shift;   // two roundings (--fmad=false)
+                g[1] = (double)r.y * tg.gm.scale[1] + shift;
+                g[2] = (double)r.z * tg.gm.scale[2] + shift;
+            }
+            if (!(isfinite(g[0]) && isfinite(g[1]) && isfinite(g[2]))) continue;
             double m = smass ? (double)smass[p] : 1.0;
             long long i0[3];
             double w[3][SUP];
@@ -425,39 +497,98 @@ k_tile_paint(const PT *__restrict__ spos, const MT *__restrict__ smass, TileGeom
             if (l2 < 0) l2 += tg.gm.n[2];
             if ((unsigned)l0 + SUP > (unsigned)R || (unsigned)l1 + SUP > (unsigned)R || (unsigned)l2 + SUP > (unsigned)R)
                 continue;   // cannot happen for a consistent sort; guards shared memory
+            const int base0 = (l0 * R + l1) * RP + l2;
+            if (m >= 0.0) {
+                // all window weights are >= 0: deposits fit the low limb (the common case; one ATOMS each)
 #pragma unroll
-            for (int rx = 0; rx < SUP; rx++)
+                for (int rx = 0; rx < SUP; rx++)
 #pragma unroll
-                for (int ry = 0; ry < SUP; ry++) {
-                    double wxy = w[0][rx] * w[1][ry];
-                    int base = ((l0 + rx) * R + (l1 + ry)) * R + l2;
+                    for (int ry = 0; ry < SUP; ry++) {
+                        double wxy = w[0][rx] * w[1][ry];
 #pragma unroll
-                    for (int rz = 0; rz < SUP; rz++) {
-                        double wt = wxy * w[2][rz] * m;
-                        fixed_add(lo, hi, base + rz, __double2ll_rn(wt * S));
+                        for (int rz = 0; rz < SUP; rz++) {
+                            double wt = wxy * w[2][rz] * m;
+                            fixed_add_pos(s_acc, base0 + (rx * R + ry) * RP + rz, __double2uint_rn(wt * S));
+                        }
                     }
-                }
+            } else {
+#pragma unroll
+                for (int rx = 0; rx < SUP; rx++)
+#pragma unroll
+                    for (int ry = 0; ry < SUP; ry++) {
+                        double wxy = w[0][rx] * w[1][ry];
+#pragma unroll
+                        for (int rz = 0; rz < SUP; rz++) {
+                            double wt = wxy * w[2][rz] * m;
+                            fixed_add(s_acc, base0 + (rx * R + ry) * RP + rz, __double2ll_rn(wt * S));
+                        }
+                    }
+            }
         }
         __syncthreads();
-        // flush: lanes run along z
-        for (int i = threadIdx.x; i < R3; i += blockDim.x) {
-            unsigned l = lo[i], h = hi[i];
-            if ((l | h) == 0u) continue;
-            int cz = i % R, cy = (i / R) % R, cx = i / R2;
-            int lx = o[0] + cx;
-            // slab-local -> drop cells that are not mine (ghost semantics); whole mesh: wrap
-            int gx = lx + tg.gm.x_start;
-            if (gx < 0) gx += tg.gm.n[0];
-            if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
-            int ix = gx - tg.gm.x_start;
-            if (ix < 0 || ix >= tg.gm.x_n) continue;
-            int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
-            int iz = o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
-            double v = (double)(long long)(((unsigned long long)h << 32) | l) * invS;
-            FT *dst = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
-            bool exclusive = cx >= H && cx < TILE && cy >= H && cy < TILE && cz >= H && cz < TILE;
-            if (exclusive) *dst = (FT)((double)*dst + v);
-            else atomicAdd(dst, (FT)v);
+        if (FLUSH == 1) {
+            // ---- convert the region to mesh dtype in place, then one TMA bulk reduce-add per z row
+            constexpr int PER = (NC + 255) / 256;
+            if (sizeof(FT) == 8) {
+                for (int i = threadIdx.x; i < NC; i += blockDim.x) {
+                    unsigned l = s_acc[2 * i], h = s_acc[2 * i + 1];
+                    reinterpret_cast<double *>(s_acc)[i] = (double)(long long)(((unsigned long long)h << 32) | l) * invS;
+                }
+            } else {
+                float v[PER];
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    int i = threadIdx.x + k * 256;
+                    v[k] = 0.f;
+                    if (i < NC) {
+                        unsigned l = s_acc[2 * i], h = s_acc[2 * i + 1];
+                        v[k] = (float)((double)(long long)(((unsigned long long)h << 32) | l) * invS);
+                    }
+                }
+                __syncthreads();
+#pragma unroll
+                for (int k = 0; k < PER; k++) {
+                    int i = threadIdx.x + k * 256;
+                    if (i < NC) reinterpret_cast<float *>(s_acc)[i] = v[k];
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            const int nz1 = min(RP, tg.gm.n[2] - o[2]);      // cells up to the end of the z row; the rest wraps to z = 0
+            for (int row = threadIdx.x; row < R * R; row += blockDim.x) {
+                int cx = row / R, cy = row - cx * R;
+                int gx = o[0] + cx + tg.gm.x_start;
+                if (gx < 0) gx += tg.gm.n[0];
+                if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
+                int ix = gx - tg.gm.x_start;
+                if (ix < 0 || ix >= tg.gm.x_n) continue;     // not my plane (ghost semantics)
+                int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
+                FT *grow = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2];
+                const FT *srow = reinterpret_cast<const FT *>(s_acc) + (size_t)row * RP;
+                tma_reduce_add(grow + o[2], srow, (unsigned)(nz1 * sizeof(FT)));
+                if (nz1 < RP) tma_reduce_add(grow, srow + nz1, (unsigned)((RP - nz1) * sizeof(FT)));
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused
+        } else {
+            // ---- per-cell flush: lanes run along z
+            for (int i = threadIdx.x; i < NC; i += blockDim.x) {
+                unsigned l = s_acc[2 * i], h = s_acc[2 * i + 1];
+                if ((l | h) == 0u) continue;
+                int cz = i % RP, cy = (i / RP) % R, cx = i / (RP * R);
+                int gx = o[0] + cx + tg.gm.x_start;
+                if (gx < 0) gx += tg.gm.n[0];
+                if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
+                int ix = gx - tg.gm.x_start;
+                if (ix < 0 || ix >= tg.gm.x_n) continue;
+                int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
+                int iz = o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
+                double v = (double)(long long)(((unsigned long long)h << 32) | l) * invS;
+                FT *dst = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
+                bool exclusive = cx >= H && cx < TILE && cy >= H && cy < TILE && cz >= H && cz < TILE;
+                if (exclusive) *dst = (FT)((double)*dst + v);
+                else atomicAdd(dst, (FT)v);
+            }
         }
         __syncthreads();
     }
@@ -497,7 +628,7 @@ extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_
     int64_t nt = ((x_n + G + TILE - 1) / TILE) * ((nmesh[1] + TILE - 1) / TILE) * ((nmesh[2] + TILE - 1) / TILE);
     size_t bytes = 256;                                  // header: queue, absmax
     bytes += 3 * align256(sizeof(unsigned) * (nt + 1));  // counts, offsets, cursor
-    bytes += align256((size_t)n * 3 * (pos_dtype == NBK_F4 ? 4 : 8));
+    bytes += align256((size_t)n * 4 * (pos_dtype == NBK_F4 ? 4 : 8));   // 16/32-byte records
     if (mass_dtype) bytes += align256((size_t)n * (mass_dtype == NBK_F4 ? 4 : 8));
     return (int64_t)bytes;
 }
@@ -517,7 +648,8 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     unsigned *counts = (unsigned *)w; w += tb;
     unsigned *offsets = (unsigned *)w; w += tb;
     unsigned *cursor = (unsigned *)w; w += tb;
-    PT *spos = (PT *)w; w += align256((size_t)n * 3 * sizeof(PT));
+    typedef typename Rec<PT>::type R4;
+    R4 *spos = (R4 *)w; w += align256((size_t)n * sizeof(R4));
     MT *smass = mass ? (MT *)w : nullptr;
     NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
     int g = nbk_grid_for(n, 256, 8);
@@ -527,25 +659,34 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     NBK_LAUNCHED();
     k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass);
     NBK_LAUNCHED();
-    size_t smem = (size_t)2 * tg.R * tg.R * tg.R * sizeof(unsigned);
+    const int RP = (tg.R + 3) & ~3;
+    size_t smem = (size_t)2 * tg.R * tg.R * RP * sizeof(unsigned);
     int per_sm = (int)((220 * 1024) / (smem + 2048));
     if (per_sm > 6) per_sm = 6;
     if (per_sm < 1) per_sm = 1;
     int grid = NBK_SM_COUNT * per_sm;
     if (grid > tg.ntiles) grid = tg.ntiles;
-    if (shifted) {
-        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_paint<SUP, PT, MT, FT, true><<<grid, 256, smem, s>>>(spos, smass, tg, shift, offsets, queue, absmax, (FT *)mesh);
-    } else {
-        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_tile_paint<SUP, PT, MT, FT, false><<<grid, 256, smem, s>>>(spos, smass, tg, shift, offsets, queue, absmax, (FT *)mesh);
+    // tile write-back: TMA bulk reduce-add rows (default) or per-cell stores/REDG (NBK_PAINT_FLUSH=st)
+    static int flush_mode = -1;
+    if (flush_mode < 0) {
+        const char *e = getenv("NBK_PAINT_FLUSH");
+        flush_mode = (e && e[0] == 's') ? 0 : 1;
     }
-    NBK_LAUNCHED();
+#define LAUNCH_TP(SH, FL, SHIFTV, MESHP)                                                                              \
+    do {                                                                                                              \
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)smem));                                                                    \
+        k_tile_paint<SUP, PT, MT, FT, SH, FL><<<grid, 256, smem, s>>>(spos, smass, tg, SHIFTV, offsets, queue, absmax,  \
+                                                                      (FT *)(MESHP));                                 \
+        NBK_LAUNCHED();                                                                                               \
+    } while (0)
+    if (shifted) { if (flush_mode) LAUNCH_TP(true, 1, shift, mesh); else LAUNCH_TP(true, 0, shift, mesh); }
+    else { if (flush_mode) LAUNCH_TP(false, 1, shift, mesh); else LAUNCH_TP(false, 0, shift, mesh); }
     if (mesh2) {
         NBK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), s));
-        k_tile_paint<SUP, PT, MT, FT, true><<<grid, 256, smem, s>>>(spos, smass, tg, 0.5, offsets, queue, absmax, (FT *)mesh2);
-        NBK_LAUNCHED();
+        if (flush_mode) LAUNCH_TP(true, 1, 0.5, mesh2); else LAUNCH_TP(true, 0, 0.5, mesh2);
     }
+#undef LAUNCH_TP
     return NBK_OK;
 }
 

@@ -144,3 +144,37 @@ if __name__ == "__main__":
     golden_dataset2d()
     golden_binned_statistic()
     print("golden vectors written to", HERE)
+
+
+def golden_ylm():
+    """values of the REFERENCE's get_real_Ylm (algorithms/convpower/fkp.py:12-73, executed from its source with
+    sympy.lambdify's 'numexpr' backend swapped for 'numpy') on seeded unit vectors and at the origin"""
+    import ast
+    import sympy
+    src = open(os.path.join(refload.REF, "nbodykit/algorithms/convpower/fkp.py")).read()
+    tree = ast.parse(src)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_real_Ylm"][0]
+    code = compile(ast.Module(body=[fn], type_ignores=[]), "fkp.py:get_real_Ylm", "exec")
+    ns_ = {"numpy": np}
+    exec(code, ns_)
+    orig = sympy.lambdify
+    sympy.lambdify = lambda args, expr, modules=None, **kw: orig(args, expr, "numpy", **kw)
+    try:
+        rng = np.random.RandomState(3)
+        v = rng.standard_normal((64, 3))
+        v /= np.sqrt((v ** 2).sum(axis=1))[:, None]
+        out = {"vec": v}
+        for l in range(0, 5):
+            for m in range(-l, l + 1):
+                f = ns_["get_real_Ylm"](l, m)
+                val = np.broadcast_to(np.asarray(f(v[:, 0], v[:, 1], v[:, 2]), dtype="f8"), (64,))
+                out["Y_%d_%d" % (l, m)] = val.copy()
+                out["Y0_%d_%d" % (l, m)] = np.array(float(f(0.0, 0.0, 0.0)))
+    finally:
+        sympy.lambdify = orig
+    np.savez_compressed(os.path.join(HERE, "ylm_reference.npz"), **out)
+
+
+if __name__ == "__main__":
+    golden_ylm()
+    print("ylm golden written")
