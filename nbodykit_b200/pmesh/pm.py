@@ -600,8 +600,8 @@ class RealField(Field):
             send = torch.empty_like(work)
             check(lib().nbk_fft_zy_forward(_ptr(self.value), _ptr(work), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_forward")
             check(lib().nbk_transpose_pack(_ptr(work), _ptr(send), code, pm.x_n, Ny, Nzc, P, _stream()), "transpose_pack")
-            recv = work.view(-1)
-            pm.comm.all_to_all_single(recv, send.view(-1))
+            recv = torch.view_as_real(work).view(-1)
+            pm.comm.all_to_all_single(recv, torch.view_as_real(send).view(-1))
             check(lib().nbk_transpose_unpack(_ptr(recv), _ptr(out.value), code, pm.y_n, Nx, Nzc, P, _stream()), "transpose_unpack")
             scale = float(scale) / (float(Nx) * Ny * Nz)
             check(lib().nbk_fft_lines(_ptr(out.value), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 0, scale, _stream()), "fft_lines(x)")
@@ -649,9 +649,9 @@ class ComplexField(BaseComplexField):
             check(lib().nbk_fft_lines(_ptr(work), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 1, 1.0, _stream()), "fft_lines(x)")
             send = torch.empty_like(work)
             check(lib().nbk_transpose_pack_back(_ptr(work), _ptr(send), code, pm.y_n, Nx, Nzc, P, _stream()), "pack_back")
-            recv = work.view(-1)
-            pm.comm.all_to_all_single(recv, send.view(-1))
-            slab = send.view(-1)
+            recv = torch.view_as_real(work).view(-1)
+            pm.comm.all_to_all_single(recv, torch.view_as_real(send).view(-1))
+            slab = torch.view_as_real(send).view(-1)
             check(lib().nbk_transpose_unpack_back(_ptr(recv), _ptr(slab), code, pm.x_n, Ny, Nzc, P, _stream()), "unpack_back")
             check(lib().nbk_fft_zy_backward(_ptr(slab), _ptr(out.value), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_backward")
         out.attrs = dict(self.attrs)
