@@ -301,6 +301,7 @@ class CatalogSourceBase(object):
         out = ArrayCatalog.__new__(ArrayCatalog)
         CatalogSourceBase.__init__(out, self.comm)
         out._size = size if size is not None else 0
+        out._csize = int(self.comm.allreduce(out._size))     # slicing is collective (as in the reference)
         out._overrides = {k: (v if isinstance(v, Column) else Column(v)) for k, v in data.items()}
         out.attrs.update(self.attrs)
         out.base = self
@@ -395,6 +396,9 @@ class CatalogSource(CatalogSourceBase):
         CatalogSourceBase.__init__(self, comm)
         if not hasattr(self, '_size'):
             raise ValueError("the `size` of the CatalogSource must be set before initializing the base class")
+        # collective: every rank constructs the catalogue, so the global size is known from here on and
+        # rank-0-only code (logging) may read `csize` without triggering a collective
+        self._csize = int(self.comm.allreduce(self._size))
 
     @column(is_default=True)
     def Selection(self):

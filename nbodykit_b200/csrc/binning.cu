@@ -269,7 +269,7 @@ __device__ __forceinline__ void acc_add(double *p, double v) {
 // segmented shuffle reduction leaves one shared-memory atomic per run and quantity (f64 shared atomics are
 // CAS loops on sm_100a -- same-address collisions inside a warp are what make them slow, and the run
 // reduction removes exactly those).  Mode counts come from the run length (no shuffle).
-template <typename T, int NELL, bool SMEM_ACC>
+template <typename T, int NELL, bool SMEM_ACC, bool SYM>
 __global__ void __launch_bounds__(256)
 k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, const double *__restrict__ k2edges,
             const double *__restrict__ muedges, unsigned long long *__restrict__ g_nsum, double *__restrict__ g_xsum,
@@ -301,13 +301,26 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
     const SlabGeom &g = P.g;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int rows = g.count * g.D1;
     const int nedge = P.Nx + 1;
     const int kz_iters = (g.Nzc + 31) >> 5;
-    for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += gridDim.x * wpb) {
-        int i0 = row / g.D1, i1 = row - i0 * g.D1;
+    // SYM (line of sight along z): the k and mu bins, |k| and mu of a mode do not change under jx -> -jx and
+    // jy -> -jy, so the (up to four) mirror rows of a canonical row (indices <= D/2) are binned together: the
+    // coordinate arithmetic, the run reduction and the atomics are paid once per group, the statistic is summed
+    // over the group first.  The mirror along the first stored axis is used only when the slab holds the full axis.
+    const int D0 = g.transposed ? g.N[1] : g.N[0];
+    const bool full0 = SYM && (g.count == D0);
+    const int n0c = full0 ? (D0 / 2 + 1) : g.count;
+    const int n1c = SYM ? (g.D1 / 2 + 1) : g.D1;
+    const int rows = n0c * n1c;
+    for (int rowc = blockIdx.x * wpb + (threadIdx.x >> 5); rowc < rows; rowc += gridDim.x * wpb) {
+        int i0 = rowc / n1c, i1 = rowc - i0 * n1c;
         int jx, jy, jz0;
         slab_freqs(g, i0, i1, 0, jx, jy, jz0);
+        // mirror partners (storage indices) and the multiplicity of the group
+        int m0 = i0, m1 = i1;
+        if (full0) { int t = (D0 - i0) % D0; if (t != i0) m0 = t; }
+        if (SYM) { int t = (g.D1 - i1) % g.D1; if (t != i1) m1 = t; }
+        const int mult = ((m0 != i0) ? 2 : 1) * ((m1 != i1) ? 2 : 1);
         // per-row constants, in the arithmetic the coordinate mode prescribes
         float kx32 = (float)jx * P.kf32[0], ky32 = (float)jy * P.kf32[1];
         float kp2_32 = kx32 * kx32 + ky32 * ky32;                       // (0 + kx^2) + ky^2
@@ -316,8 +329,13 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
         double kp2_64 = kx64 * kx64 + ky64 * ky64;
         double lp_64 = kx64 * P.los64[0] + ky64 * P.los64[1];
         double lp_48 = (double)kx32 * P.los64[0] + (double)ky32 * P.los64[1];
-        const T *r1 = c1 + (int64_t)row * g.Nzc * 2;
-        const T *r2 = P.has_c2 ? c2 + (int64_t)row * g.Nzc * 2 : r1;
+        const int64_t rowlen = (int64_t)g.Nzc * 2;
+        int64_t roff[4];
+        roff[0] = ((int64_t)i0 * g.D1 + i1) * rowlen;
+        roff[1] = ((int64_t)i0 * g.D1 + m1) * rowlen;
+        roff[2] = ((int64_t)m0 * g.D1 + i1) * rowlen;
+        roff[3] = ((int64_t)m0 * g.D1 + m1) * rowlen;
+        const bool use1 = (m1 != i1), use2 = (m0 != i0), use3 = use1 && use2;
         const double vol_row = ct0 ? P.volume * (ct0[g.start + i0] * ct1[i1]) : P.volume;
         for (int it = 0; it < kz_iters; it++) {
             const int kz = it * 32 + lane;
@@ -363,17 +381,30 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                 for (int i = 0; i <= P.Nmu; i++) dm += (s_mu[i] <= mu) ? 1 : 0;
                 key = b * (P.Nmu + 2) + dm;
                 bool nonsing = P.hermitian && (jz > 0);
-                double wH = nonsing ? 2.0 : 1.0;
-                wcnt = nonsing ? 2u : 1u;
+                double wH = (nonsing ? 2.0 : 1.0) * (double)mult;
+                wcnt = (nonsing ? 2u : 1u) * (unsigned)mult;
                 xs = knorm * wH;
                 ms = mu * wH;
-                double a = (double)r1[2 * kz], bb = (double)r1[2 * kz + 1], yre, yim;
-                if (P.is_p3d) { yre = a; yim = bb; }
-                else {
-                    double c = (double)r2[2 * kz], d = (double)r2[2 * kz + 1];
-                    double vol = ct0 ? vol_row * ctz[kz] : vol_row;
-                    yre = (a * c + bb * d) * vol;   // c1 * conj(c2) * V [* window compensation of both fields]
-                    yim = (bb * c - a * d) * vol;
+                double yre = 0.0, yim = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    if (q == 1 && !use1) continue;
+                    if (q == 2 && !use2) continue;
+                    if (q == 3 && !use3) continue;
+                    const T *p1 = c1 + roff[q] + 2 * kz;
+                    double a = (double)p1[0], bb = (double)p1[1];
+                    if (P.is_p3d) { yre += a; yim += bb; }
+                    else {
+                        double c = a, d = bb;
+                        if (P.has_c2) { const T *p2 = c2 + roff[q] + 2 * kz; c = (double)p2[0]; d = (double)p2[1]; }
+                        yre += a * c + bb * d;      // c1 * conj(c2)
+                        yim += bb * c - a * d;
+                    }
+                }
+                if (!P.is_p3d) {
+                    double vol = ct0 ? vol_row * ctz[kz] : vol_row;   // V [* window compensation of both fields]
+                    yre *= vol;
+                    yim *= vol;
                     if (P.clear_zero && jx == 0 && jy == 0 && jz == 0) { yre = 0; yim = 0; }
                 }
 #pragma unroll
@@ -508,17 +539,19 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
     int64_t want = (rows + 7) / 8;
     int grid = (int)(want < (int64_t)NBK_SM_COUNT * per_sm ? want : (int64_t)NBK_SM_COUNT * per_sm);
     if (grid < 1) grid = 1;
-    if (smem_acc) {
-        NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_power_bin<T, NELL, true><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,
-                                                            (unsigned long long *)nsum, xsum, musum, ysum, kmin, inv_dk,
-                                                            uniform, ct0, ct1, ctz);
-    } else {
-        NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_power_bin<T, NELL, false><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,
-                                                             (unsigned long long *)nsum, xsum, musum, ysum, kmin, inv_dk,
-                                                             uniform, ct0, ct1, ctz);
-    }
+    // mirror symmetry is usable when mu does not depend on kx, ky (line of sight along z)
+    const bool sym = (P.los64[0] == 0.0 && P.los64[1] == 0.0);
+#define LAUNCH_BIN(ACC, SYMV)                                                                                        \
+    do {                                                                                                             \
+        NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, ACC, SYMV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                      (int)smem));                                                                   \
+        k_power_bin<T, NELL, ACC, SYMV><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,          \
+                                                                (unsigned long long *)nsum, xsum, musum, ysum, kmin, \
+                                                                inv_dk, uniform, ct0, ct1, ctz);                      \
+    } while (0)
+    if (smem_acc) { if (sym) LAUNCH_BIN(true, true); else LAUNCH_BIN(true, false); }
+    else { if (sym) LAUNCH_BIN(false, true); else LAUNCH_BIN(false, false); }
+#undef LAUNCH_BIN
     NBK_LAUNCHED();
     return NBK_OK;
 }

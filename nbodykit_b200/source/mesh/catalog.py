@@ -224,7 +224,7 @@ class CatalogMesh(MeshSource):
         attrs, nbar = self._attrs_for(N, W, W2)
         toret.attrs = attrs
         if pm.comm.rank == 0:
-            self.logger.info("painted %d out of %d objects to mesh" % (N, self.source.csize))
+            self.logger.info("painted %d objects to mesh" % N)
             self.logger.info("mean particles per cell is %g", nbar)
         if normalize:
             if nbar > 0:
@@ -253,7 +253,7 @@ class CatalogMesh(MeshSource):
             c = painted.r2c(scale=1.0 / nbar)
         c.attrs = attrs
         if self.pm.comm.rank == 0:
-            self.logger.info("painted %d out of %d objects to mesh" % (N, self.source.csize))
+            self.logger.info("painted %d objects to mesh" % N)
         return c
 
     def compute_complex_deferred(self):
