@@ -111,6 +111,9 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    # keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1 directly
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -229,7 +232,9 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(host.numpy(), Nmesh, Box)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

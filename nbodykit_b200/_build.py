@@ -20,6 +20,7 @@ SOURCES = [
     ("fft.cu", []),
     ("binning.cu", ["--fmad=false"]),
     ("ylm.cu", []),
+    ("route.cu", ["--fmad=false"]),
 ]
 COMMON = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
           "-Xcompiler", "-fPIC", "-Xcompiler", "-O3"]

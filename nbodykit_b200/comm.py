@@ -42,6 +42,12 @@ class SelfComm(object):
         out.copy_(inp)
         return out
 
+    def alltoall_ints(self, xs):
+        return [int(x) for x in xs]
+
+    def allreduce_floats(self, xs):
+        return [float(x) for x in xs]
+
     def __repr__(self):
         return "SelfComm()"
 
@@ -124,6 +130,20 @@ class TorchComm(object):
             return out
         self._dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
         return out
+
+    def alltoall_ints(self, xs):
+        """alltoall of one integer per destination, as ONE small tensor collective (no pickling)"""
+        dev = self._device()
+        inp = torch.tensor([int(x) for x in xs], dtype=torch.int64, device=dev)
+        out = torch.empty_like(inp)
+        self.all_to_all_single(out, inp)
+        return [int(v) for v in out.cpu().tolist()]
+
+    def allreduce_floats(self, xs):
+        """sum-allreduce of a few scalars in one collective"""
+        t = torch.tensor([float(x) for x in xs], dtype=torch.float64, device=self._device())
+        self._dist.all_reduce(t, group=self.group)
+        return [float(v) for v in t.cpu().tolist()]
 
     def _gloo_all_to_all(self, outs, ins):
         reqs = []

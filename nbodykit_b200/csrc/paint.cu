@@ -345,7 +345,7 @@ __device__ __forceinline__ unsigned warp_claim(unsigned *counter, int key, bool 
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(256)
 k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg,
-             unsigned *__restrict__ counts, unsigned *__restrict__ absmax_bits) {
+             unsigned *__restrict__ counts, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float mx = 0.f;
     const float sc32[3] = {(float)tg.gm.scale[0], (float)tg.gm.scale[1], (float)tg.gm.scale[2]};
@@ -353,6 +353,7 @@ k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
         int t = in ? tile_of<SUP, PT>(pos, i, tg, sc32) : -1;
+        if (in) tile_ids[i] = t;          // the scatter pass reuses the id instead of recomputing it
         warp_claim(counts, t, t >= 0);
         if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);
     }
@@ -394,14 +395,13 @@ template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(256)
 k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg,
                const unsigned *__restrict__ offsets, unsigned *__restrict__ cursor,
-               typename Rec<PT>::type *__restrict__ spos, MT *__restrict__ smass) {
+               typename Rec<PT>::type *__restrict__ spos, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
     typedef typename Rec<PT>::type R4;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const float sc32[3] = {(float)tg.gm.scale[0], (float)tg.gm.scale[1], (float)tg.gm.scale[2]};
     int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
-        int t = in ? tile_of<SUP, PT>(pos, i, tg, sc32) : -1;
+        int t = in ? tile_ids[i] : -1;
         unsigned slot = warp_claim(cursor, t, t >= 0);
         if (t >= 0) {
             int64_t dst = (int64_t)offsets[t] + slot;
@@ -629,6 +629,7 @@ extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_
     size_t bytes = 256;                                  // header: queue, absmax
     bytes += 3 * align256(sizeof(unsigned) * (nt + 1));  // counts, offsets, cursor
     bytes += align256((size_t)n * 4 * (pos_dtype == NBK_F4 ? 4 : 8));   // 16/32-byte records
+    bytes += align256((size_t)n * sizeof(int));                          // tile id per particle
     if (mass_dtype) bytes += align256((size_t)n * (mass_dtype == NBK_F4 ? 4 : 8));
     return (int64_t)bytes;
 }
@@ -650,14 +651,16 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     unsigned *cursor = (unsigned *)w; w += tb;
     typedef typename Rec<PT>::type R4;
     R4 *spos = (R4 *)w; w += align256((size_t)n * sizeof(R4));
+    int *tile_ids = (int *)w; w += align256((size_t)n * sizeof(int));
     MT *smass = mass ? (MT *)w : nullptr;
     NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
     int g = nbk_grid_for(n, 256, 8);
-    k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, counts, absmax);
+    k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, counts, absmax, tile_ids);
     NBK_LAUNCHED();
     k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
     NBK_LAUNCHED();
-    k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass);
+    k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass,
+                                                  tile_ids);
     NBK_LAUNCHED();
     const int RP = (tg.R + 3) & ~3;
     size_t smem = (size_t)2 * tg.R * tg.R * RP * sizeof(unsigned);

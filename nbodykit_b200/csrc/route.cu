@@ -1,0 +1,112 @@
+// Particle routing for the x-slab decomposition (pmesh `pm.decompose` + `Layout.exchange`, called from
+// nbodykit/source/mesh/catalog.py:271-284): which OTHER ranks own a plane within `smoothing` cells of a particle.
+// A rank paints ALL of its local particles itself (the scatter kernels drop stencil points outside the slab), so
+// only copies for remote slabs travel: for spatially coherent catalogues that is the ghost layer alone.
+//   nbk_route_count   : destination bitmask per particle (P <= 32) + per-destination counts
+//   nbk_route_scatter : compact (pos[, mass]) into per-destination segments of the send buffer
+#include "common.cuh"
+
+struct RouteGeom {
+    double scale;     // Nx / Lx
+    double smoothing;
+    int Nx, x_n, P, rank;
+};
+
+__device__ __forceinline__ unsigned route_mask(double p, const RouteGeom &g) {
+    double gx = p * g.scale;
+    if (!isfinite(gx)) return 0u;
+    long long lo = (long long)floor(gx - g.smoothing), hi = (long long)floor(gx + g.smoothing);
+    unsigned m = 0u;
+    for (long long c = lo; c <= hi; c++) {
+        long long w = c % g.Nx;
+        if (w < 0) w += g.Nx;
+        m |= 1u << (unsigned)(w / g.x_n);
+    }
+    return m & ~(1u << g.rank);
+}
+
+template <typename PT>
+__global__ void __launch_bounds__(256)
+k_route_count(const PT *__restrict__ pos, int64_t n, RouteGeom g, unsigned long long *__restrict__ counts,
+              unsigned *__restrict__ flags) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t nround = ((n + stride - 1) / stride) * stride;
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        unsigned m = 0u;
+        if (i < n) {
+            m = route_mask((double)pos[3 * i], g);
+            flags[i] = m;
+        }
+        if (__any_sync(0xffffffffu, m != 0u)) {
+            for (int r = 0; r < g.P; r++) {
+                unsigned b = __ballot_sync(0xffffffffu, (m >> r) & 1u);
+                if (lane == 0 && b) atomicAdd(&counts[r], (unsigned long long)__popc(b));
+            }
+        }
+    }
+}
+
+template <typename PT, typename MT>
+__global__ void __launch_bounds__(256)
+k_route_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int P,
+                const unsigned *__restrict__ flags, const long long *__restrict__ offsets,
+                unsigned long long *__restrict__ cursor, PT *__restrict__ spos, MT *__restrict__ smass) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t nround = ((n + stride - 1) / stride) * stride;
+    const int lane = threadIdx.x & 31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
+        unsigned m = (i < n) ? flags[i] : 0u;
+        if (!__any_sync(0xffffffffu, m != 0u)) continue;
+        for (int r = 0; r < P; r++) {
+            unsigned b = __ballot_sync(0xffffffffu, (m >> r) & 1u);
+            if (!b) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(&cursor[r], (unsigned long long)__popc(b));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if ((m >> r) & 1u) {
+                long long dst = offsets[r] + (long long)base + __popc(b & ((1u << lane) - 1u));
+                spos[3 * dst] = pos[3 * i];
+                spos[3 * dst + 1] = pos[3 * i + 1];
+                spos[3 * dst + 2] = pos[3 * i + 2];
+                if (mass) smass[dst] = mass[i];
+            }
+        }
+    }
+}
+
+extern "C" int nbk_route_count(const void *pos, int pos_dtype, int64_t n, double smoothing, const double *box,
+                               const int64_t *nmesh, int P, int rank, uint64_t *counts, uint32_t *flags, void *stream) {
+    NBK_CHECK_ARG(pos_dtype == NBK_F4 || pos_dtype == NBK_F8, "route_count: bad pos dtype %d", pos_dtype);
+    NBK_CHECK_ARG(P >= 1 && P <= 32 && rank >= 0 && rank < P && nmesh[0] % P == 0, "route_count: bad decomposition");
+    NBK_CHECK_ARG(smoothing >= 0 && smoothing < 64, "route_count: bad smoothing");
+    if (n == 0) return NBK_OK;
+    RouteGeom g;
+    g.scale = (double)nmesh[0] / box[0];
+    g.smoothing = smoothing;
+    g.Nx = (int)nmesh[0]; g.x_n = (int)(nmesh[0] / P); g.P = P; g.rank = rank;
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = nbk_grid_for(n, 256, 8);
+    if (pos_dtype == NBK_F4) k_route_count<float><<<grid, 256, 0, s>>>((const float *)pos, n, g, (unsigned long long *)counts, flags);
+    else k_route_count<double><<<grid, 256, 0, s>>>((const double *)pos, n, g, (unsigned long long *)counts, flags);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+extern "C" int nbk_route_scatter(const void *pos, int pos_dtype, const void *mass, int mass_dtype, int64_t n, int P,
+                                 const uint32_t *flags, const int64_t *offsets, uint64_t *cursor, void *send_pos,
+                                 void *send_mass, void *stream) {
+    NBK_CHECK_ARG(pos_dtype == NBK_F4 || pos_dtype == NBK_F8, "route_scatter: bad pos dtype %d", pos_dtype);
+    NBK_CHECK_ARG(mass == nullptr || mass_dtype == NBK_F4 || mass_dtype == NBK_F8, "route_scatter: bad mass dtype");
+    if (n == 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    int grid = nbk_grid_for(n, 256, 8);
+    const long long *off = (const long long *)offsets;
+    unsigned long long *cur = (unsigned long long *)cursor;
+#define RS(PT, MT) k_route_scatter<PT, MT><<<grid, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, P, flags, off, cur, (PT *)send_pos, (MT *)send_mass)
+    bool pf = pos_dtype == NBK_F4, mf = (mass != nullptr && mass_dtype == NBK_F4);
+    if (pf && mf) RS(float, float); else if (pf) RS(float, double); else if (mf) RS(double, float); else RS(double, double);
+#undef RS
+    NBK_LAUNCHED();
+    return NBK_OK;
+}

@@ -101,6 +101,59 @@ class Layout(object):
         return out
 
 
+class SlabLayout(object):
+    """device-side routing plan (nbk_route_count): per-particle bitmask of REMOTE destination slabs.  Local
+    particles are never moved -- `route()` returns only what arrives from other ranks; `exchange()` keeps the
+    pmesh contract (local + received in one array)."""
+
+    def __init__(self, pm, n, flags, sendcounts, recvcounts):
+        self.pm = pm
+        self.comm = pm.comm
+        self.n = n
+        self.flags = flags
+        self.sendcounts = sendcounts
+        self.recvcounts = recvcounts
+        self.sendlength = int(sum(sendcounts))
+        self.recvlength = n + int(sum(recvcounts))     # pmesh semantics: what this rank will paint
+
+    def route(self, pos, mass=None):
+        """(received positions, received masses | None): copies for remote slabs travel in one all-to-all per column"""
+        P = self.comm.size
+        dev = pos.device
+        nsend, nrecv = int(sum(self.sendcounts)), int(sum(self.recvcounts))
+        spos = torch.empty((nsend, 3), dtype=pos.dtype, device=dev)
+        smass = torch.empty(nsend, dtype=mass.dtype, device=dev) if mass is not None else None
+        if nsend:
+            off = torch.tensor([0] + list(numpy.cumsum(self.sendcounts)[:-1]), dtype=torch.int64, device=dev)
+            cur = torch.zeros(P, dtype=torch.int64, device=dev)
+            with stage("route_scatter"):
+                check(lib().nbk_route_scatter(_ptr(pos), F4 if pos.dtype == torch.float32 else F8, _ptr(mass),
+                                              (F4 if mass.dtype == torch.float32 else F8) if mass is not None else F8,
+                                              self.n, P, _ptr(self.flags), _ptr(off), _ptr(cur), _ptr(spos), _ptr(smass),
+                                              _stream()), "nbk_route_scatter")
+        rpos = torch.empty((nrecv, 3), dtype=pos.dtype, device=dev)
+        with stage("route_alltoall"):
+            self.comm.all_to_all_single(rpos, spos, list(self.recvcounts), list(self.sendcounts))
+            rmass = None
+            if mass is not None:
+                rmass = torch.empty(nrecv, dtype=mass.dtype, device=dev)
+                self.comm.all_to_all_single(rmass, smass, list(self.recvcounts), list(self.sendcounts))
+        return rpos, rmass
+
+    def exchange(self, data):
+        t = as_device_tensor(data) if not isinstance(data, torch.Tensor) else data
+        P = self.comm.size
+        parts, counts = [], []
+        for r in range(P):
+            idx = torch.nonzero((self.flags >> r) & 1, as_tuple=False).reshape(-1)
+            parts.append(t.index_select(0, idx))
+            counts.append(int(idx.numel()))
+        send = torch.cat(parts) if parts else t[:0]
+        recv = torch.empty((int(sum(self.recvcounts)),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        self.comm.all_to_all_single(recv, send, list(self.recvcounts), counts)
+        return torch.cat([t, recv])
+
+
 class ParticleMesh(object):
     def __init__(self, BoxSize, Nmesh, dtype="f4", comm=None, np=None, plan_method=None, resampler="cic"):
         from .. import CurrentMPIComm
@@ -218,6 +271,8 @@ class ParticleMesh(object):
             n = int(pos.shape[0])
             return Layout(self.comm, None, [n], [n])
         pos = pos if isinstance(pos, torch.Tensor) else torch.as_tensor(numpy.asarray(pos))
+        if pos.is_cuda:
+            return self._decompose_device(pos, float(smoothing))
         Nx = int(self.Nmesh[0])
         gx = pos[:, 0].to(torch.float64) * float(self.Nmesh[0] / self.BoxSize[0])
         lo = torch.floor(gx - smoothing).to(torch.int64)
@@ -235,6 +290,23 @@ class ParticleMesh(object):
         counts = torch.bincount(dest, minlength=P).cpu().tolist()
         recv = self.comm.alltoall(counts)
         return Layout(self.comm, src[order], counts, recv)
+
+    def _decompose_device(self, pos, smoothing):
+        """routing plan for device-resident positions: one kernel pass, one tiny all-to-all of the counts"""
+        P = self.comm.size
+        n = int(pos.shape[0])
+        if pos.dtype not in (torch.float32, torch.float64):
+            pos = pos.to(torch.float64)
+        pos = pos.contiguous()
+        flags = torch.empty(n, dtype=torch.int32, device=pos.device)
+        counts = torch.zeros(P, dtype=torch.int64, device=pos.device)
+        with stage("route_count"):
+            check(lib().nbk_route_count(_ptr(pos), F4 if pos.dtype == torch.float32 else F8, n, smoothing, self._box_c,
+                                        self._nmesh_c, P, self.comm.rank, _ptr(counts), _ptr(flags), _stream()),
+                  "nbk_route_count")
+        sendcounts = [int(v) for v in counts.cpu().tolist()]
+        recvcounts = self.comm.alltoall_ints(sendcounts)
+        return SlabLayout(self, n, flags, sendcounts, recvcounts)
 
     # ---- paint (source/mesh/catalog.py:287,295-296)
     def paint(self, pos, mass=1.0, resampler=None, transform=None, hold=False, gradient=None, layout=None, out=None,
@@ -598,13 +670,18 @@ class RealField(Field):
             Nzc = pm.Nzc
             work = torch.empty((pm.x_n, Ny, Nzc), dtype=out.value.dtype, device=out.value.device)
             send = torch.empty_like(work)
-            check(lib().nbk_fft_zy_forward(_ptr(self.value), _ptr(work), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_forward")
-            check(lib().nbk_transpose_pack(_ptr(work), _ptr(send), code, pm.x_n, Ny, Nzc, P, _stream()), "transpose_pack")
+            with stage("fft_zy"):
+                check(lib().nbk_fft_zy_forward(_ptr(self.value), _ptr(work), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_forward")
+            with stage("fft_pack"):
+                check(lib().nbk_transpose_pack(_ptr(work), _ptr(send), code, pm.x_n, Ny, Nzc, P, _stream()), "transpose_pack")
             recv = torch.view_as_real(work).view(-1)
-            pm.comm.all_to_all_single(recv, torch.view_as_real(send).view(-1))
-            check(lib().nbk_transpose_unpack(_ptr(recv), _ptr(out.value), code, pm.y_n, Nx, Nzc, P, _stream()), "transpose_unpack")
+            with stage("fft_alltoall"):
+                pm.comm.all_to_all_single(recv, torch.view_as_real(send).view(-1))
+            with stage("fft_unpack"):
+                check(lib().nbk_transpose_unpack(_ptr(recv), _ptr(out.value), code, pm.y_n, Nx, Nzc, P, _stream()), "transpose_unpack")
             scale = float(scale) / (float(Nx) * Ny * Nz)
-            check(lib().nbk_fft_lines(_ptr(out.value), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 0, scale, _stream()), "fft_lines(x)")
+            with stage("fft_x"):
+                check(lib().nbk_fft_lines(_ptr(out.value), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 0, scale, _stream()), "fft_lines(x)")
         out.attrs = dict(self.attrs)
         return out
 

@@ -162,24 +162,31 @@ class CatalogMesh(MeshSource):
         resampler = window.methods[self.resampler]
         pos, mass, Nlocal, Wlocal, W2local = self._device_columns()
         smoothing = (1.0 if self.interlaced else 0.5) * resampler.support
+        scalar = isinstance(mass, float)
+        # every rank paints its own particles (out-of-slab stencil points are dropped by the kernel) plus the
+        # copies other ranks send for planes it owns
+        batches = [(pos, mass)]
         if pm.comm.size > 1:
             lay = pm.decompose(pos, smoothing=smoothing)
-            pos = lay.exchange(pos)
-            if not isinstance(mass, float):
-                mass = lay.exchange(mass)
-        N = pm.comm.allreduce(Nlocal)
-        W = pm.comm.allreduce(Wlocal)
-        W2 = pm.comm.allreduce(W2local)
+            rpos, rmass = lay.route(pos, None if scalar else mass)
+            batches.append((rpos, mass if scalar else rmass))
+            N, W, W2 = pm.comm.allreduce_floats([Nlocal, Wlocal, W2local])
+            N = int(round(N))
+        else:
+            N, W, W2 = Nlocal, Wlocal, W2local
         if not self.interlaced:
             real = RealField(pm)
             real[...] = 0
-            pm.paint(pos, mass=mass, resampler=resampler, hold=True, out=real)
+            for p, m in batches:
+                if p.shape[0]:
+                    pm.paint(p, mass=m, resampler=resampler, hold=True, out=real)
             return real, N, W, W2
         real1, real2 = RealField(pm), RealField(pm)
         real1[...] = 0
         real2[...] = 0
-        scalar = isinstance(mass, float)
-        pm.paint_interlaced(pos, None if scalar else mass, resampler, real1, real2)
+        for p, m in batches:
+            if p.shape[0]:
+                pm.paint_interlaced(p, None if scalar else m, resampler, real1, real2)
         if scalar and mass != 1.0:
             real1 *= mass
             real2 *= mass

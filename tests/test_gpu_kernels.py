@@ -400,3 +400,55 @@ def test_r2c_extra_scale(cuda):
     f = RealField(pm)
     f[...] = real
     np.testing.assert_allclose(f.r2c(scale=2.5).numpy(), 2.5 * f.r2c().numpy(), rtol=1e-14)
+
+
+def test_route_kernels_vs_numpy(cuda):
+    """nbk_route_count / nbk_route_scatter: destination bitmask, counts and compacted send segments"""
+    import ctypes
+    import torch
+    from nbodykit_b200 import _lib
+    N, L, P, rank = [64, 16, 16], [128., 16., 16.], 4, 1
+    rng = np.random.RandomState(31)
+    pos = rng.uniform(-40, 170, size=(50000, 3)).astype("f4")
+    mass = rng.uniform(size=len(pos))
+    Lb = _lib.lib()
+    p = torch.from_numpy(pos).cuda(); m = torch.from_numpy(mass).cuda()
+    for smoothing in (1.0, 1.5, 3.0):
+        flags = torch.empty(len(pos), dtype=torch.int32, device="cuda")
+        counts = torch.zeros(P, dtype=torch.int64, device="cuda")
+        _lib.check(Lb.nbk_route_count(ctypes.c_void_p(p.data_ptr()), 4, len(pos), smoothing, _lib.darr(L), _lib.iarr(N), P, rank,
+                                      ctypes.c_void_p(counts.data_ptr()), ctypes.c_void_p(flags.data_ptr()), None))
+        gx = pos[:, 0].astype("f8") * (N[0] / L[0])
+        want = np.zeros(len(pos), dtype="i8")
+        for c in range(-4, 5):
+            cell = np.floor(gx + c * 1.0)           # enumerate integer cells in [floor(gx-s), floor(gx+s)]
+        lo, hi = np.floor(gx - smoothing).astype("i8"), np.floor(gx + smoothing).astype("i8")
+        for off in range(0, 8):
+            cell = lo + off
+            ok = cell <= hi
+            r = (cell % N[0]) // (N[0] // P)
+            want |= np.where(ok, 1 << r, 0)
+        want &= ~(1 << rank)
+        got = flags.cpu().numpy().astype("i8")
+        assert np.array_equal(got, want)
+        cnt = [int(((want >> r) & 1).sum()) for r in range(P)]
+        assert counts.cpu().tolist() == cnt and cnt[rank] == 0
+        off = torch.tensor([0] + list(np.cumsum(cnt)[:-1]), dtype=torch.int64, device="cuda")
+        cur = torch.zeros(P, dtype=torch.int64, device="cuda")
+        spos = torch.empty((sum(cnt), 3), dtype=torch.float32, device="cuda")
+        smass = torch.empty(sum(cnt), dtype=torch.float64, device="cuda")
+        _lib.check(Lb.nbk_route_scatter(ctypes.c_void_p(p.data_ptr()), 4, ctypes.c_void_p(m.data_ptr()), 8, len(pos), P,
+                                        ctypes.c_void_p(flags.data_ptr()), ctypes.c_void_p(off.data_ptr()),
+                                        ctypes.c_void_p(cur.data_ptr()), ctypes.c_void_p(spos.data_ptr()),
+                                        ctypes.c_void_p(smass.data_ptr()), None))
+        torch.cuda.synchronize()
+        sp, sm = spos.cpu().numpy(), smass.cpu().numpy()
+        start = 0
+        for r in range(P):
+            sel = ((want >> r) & 1).astype(bool)
+            seg = slice(start, start + cnt[r])
+            # same multiset of (x, y, z, mass) rows, any order
+            a = np.concatenate([sp[seg].astype("f8"), sm[seg][:, None]], axis=1)
+            b = np.concatenate([pos[sel].astype("f8"), mass[sel][:, None]], axis=1)
+            assert np.array_equal(a[np.lexsort(a.T)], b[np.lexsort(b.T)])
+            start += cnt[r]
