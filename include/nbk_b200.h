@@ -130,6 +130,17 @@ int nbk_fft_zy_backward(void *cplx, void *real, int dtype, int64_t x_n, int64_t 
                         void *stream);
 int nbk_fft_lines(void *cplx, int dtype, int64_t n_line, int64_t line_stride, int64_t n_inner,
                   int64_t n_outer, int64_t outer_stride, int inverse, double scale, void *stream);
+int nbk_fft_lines_oop(const void *src, void *dst, int dtype, int64_t n_line, int64_t line_stride, int64_t n_inner,
+                      int64_t n_outer, int64_t outer_stride, int inverse, double scale, void *stream);
+int nbk_fft_z_forward(const void *real, void *cplx, int dtype, int64_t rows, int64_t Nz, void *stream);
+/* Fused line pass + slab transpose over NVLink peer memory: FFT along the second stored axis of the local slab
+ * src[n_outer][n_line][n_inner]; output frequency k is stored directly into rank (k / (n_line/P))'s buffer at
+ * peer[p][((k % (n_line/P)) * (n_outer*P) + outer_start + outer) * n_inner + kz].  peer_ptrs_host: host array of P
+ * device pointers valid on this GPU (CUDA IPC / symmetric memory; entry `rank` = the local buffer).  Replaces
+ * y-pass write + nbk_transpose_pack + all-to-all + nbk_transpose_unpack by one kernel; the caller provides the
+ * cross-rank barriers before and after. */
+int nbk_fft_lines_scatter(const void *src, void *const *peer_ptrs_host, int dtype, int64_t n_line, int64_t n_inner,
+                          int64_t n_outer, int64_t outer_start, int P, int inverse, double scale, void *stream);
 int nbk_transpose_pack(const void *src, void *dst, int dtype, int64_t x_n, int64_t Ny, int64_t Nzc,
                        int64_t P, void *stream);
 int nbk_transpose_unpack(const void *src, void *dst, int dtype, int64_t y_n, int64_t Nx,

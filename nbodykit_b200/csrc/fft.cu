@@ -145,8 +145,8 @@ __device__ __forceinline__ const C *stage_twiddles(C *dst, const C *__restrict__
 // ---------------------------------------------------------------------------------------------
 template <typename T, int B>
 __global__ void __launch_bounds__(256)
-k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type *__restrict__ tw, int N, int log2n,
-            int64_t line_stride, int64_t n_inner, int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride,
+k_fft_lines(const typename C2<T>::type *src, typename C2<T>::type *dst, const typename C2<T>::type *__restrict__ tw,
+            int N, int log2n, int64_t line_stride, int64_t n_inner, int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride,
             int inverse, T scale) {
     typedef typename C2<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,7 +157,8 @@ k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type 
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t outer = tile / tiles_inner;
         int64_t inner0 = (tile - outer * tiles_inner) * B;
-        C *base = data + outer * outer_stride + inner0;
+        const C *base = src + outer * outer_stride + inner0;
+        C *obase = dst + outer * outer_stride + inner0;      // dst == src: in place (a CTA owns its tile)
         int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
         for (int w = threadIdx.x; w < N * B; w += T_) {
             int b = w % B, n = w / B;
@@ -175,7 +176,59 @@ k_fft_lines(typename C2<T>::type *__restrict__ data, const typename C2<T>::type 
                 if (inverse) v.y = -v.y;
                 v.x *= scale;
                 v.y *= scale;
-                base[(int64_t)k * line_stride + b] = v;
+                obase[(int64_t)k * line_stride + b] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused line pass + slab transpose over peer memory (P > 1).  Lines of length N run along the SECOND stored axis
+// of the local slab src[n_outer][N][n_inner] (the y pass of r2c on [x_n][Ny][Nzc], or the inverse x pass of c2r on
+// [y_n][Nx][Nzc]).  Output frequency k belongs to rank p = k / (N/P); instead of writing the slab back, packing,
+// all-to-all and unpacking, the store phase writes each 64..128-byte kz run straight into rank p's transposed
+// field through its NVLink-mapped pointer:
+//     peer[p][ ((k % (N/P)) * (n_outer*P) + outer_start + outer) * n_inner + kz ]
+// (peer[rank] is the local buffer).  The caller brackets the launch with cross-rank barriers.
+// ---------------------------------------------------------------------------------------------
+#define NBK_MAX_PEERS 16
+template <typename C> struct PeerPtrs { C *p[NBK_MAX_PEERS]; };
+
+template <typename T, int B>
+__global__ void __launch_bounds__(256)
+k_fft_lines_scatter(const typename C2<T>::type *__restrict__ src, PeerPtrs<typename C2<T>::type> peers,
+                    const typename C2<T>::type *__restrict__ tw, int N, int log2n, int64_t n_inner, int64_t tiles_inner,
+                    int64_t n_tiles, int n_per, int64_t d_total, int64_t outer_start, int inverse, T scale) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    constexpr int pitch = B + 1;
+    const int T_ = blockDim.x;
+    tw = stage_twiddles<C>(sm + N * pitch, tw, N);
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t outer = tile / tiles_inner;
+        int64_t inner0 = (tile - outer * tiles_inner) * B;
+        const C *base = src + outer * (int64_t)N * n_inner + inner0;
+        int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+        for (int w = threadIdx.x; w < N * B; w += T_) {
+            int b = w % B, n = w / B;
+            C v = C{0, 0};
+            if (b < bvalid) v = base[(int64_t)n * n_inner + b];
+            if (inverse) v.y = -v.y;
+            sm[n * pitch + b] = v;
+        }
+        __syncthreads();
+        fft_tile<C, B>(sm, tw, N, log2n);
+        for (int w = threadIdx.x; w < N * B; w += T_) {
+            int b = w % B, k = w / B;
+            if (b < bvalid) {
+                C v = sm[pos_of_freq(k, N, log2n) * pitch + b];
+                if (inverse) v.y = -v.y;
+                v.x *= scale;
+                v.y *= scale;
+                int p = k / n_per, kl = k - p * n_per;
+                peers.p[p][((int64_t)kl * d_total + outer_start + outer) * n_inner + inner0 + b] = v;
             }
         }
         __syncthreads();
@@ -334,13 +387,13 @@ static int pick_B(int N, int csize, int64_t n_inner) {
 }
 
 template <typename T>
-static int launch_lines(void *data, int N, int64_t line_stride, int64_t n_inner, int64_t n_outer,
+static int launch_lines(const void *data, void *dst, int N, int64_t line_stride, int64_t n_inner, int64_t n_outer,
                         int64_t outer_stride, int inverse, double scale, cudaStream_t s) {
     typedef typename C2<T>::type C;
     int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
     if (N == 1) {
-        if (scale != 1.0) {
-            nbk_set_error("fft_lines: N == 1 with scale is not supported");
+        if (scale != 1.0 || dst != data) {
+            nbk_set_error("fft_lines: N == 1 with scale / out of place is not supported");
             return NBK_ERR_UNSUPPORTED;
         }
         return NBK_OK;
@@ -360,7 +413,7 @@ static int launch_lines(void *data, int N, int64_t line_stride, int64_t n_inner,
 #define LAUNCH_LINES(BB)                                                                                          \
     case BB:                                                                                                      \
         NBK_CUDA(cudaFuncSetAttribute(k_fft_lines<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_fft_lines<T, BB><<<(int)g, 256, smem, s>>>((C *)data, (const C *)tw, N, ilog2(N), line_stride, n_inner,   \
+        k_fft_lines<T, BB><<<(int)g, 256, smem, s>>>((const C *)data, (C *)dst, (const C *)tw, N, ilog2(N), line_stride, n_inner, \
                                                      tiles_inner, n_tiles, outer_stride, inverse, (T)scale);      \
         break;
     switch (B) {
@@ -380,8 +433,69 @@ extern "C" int nbk_fft_lines(void *cplx, int dtype, int64_t n_line, int64_t line
     if (n_inner <= 0 || n_outer <= 0) return NBK_OK;
     cudaStream_t s = (cudaStream_t)stream;
     if (dtype == NBK_F4)
-        return launch_lines<float>(cplx, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
-    return launch_lines<double>(cplx, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+        return launch_lines<float>(cplx, cplx, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+    return launch_lines<double>(cplx, cplx, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+}
+
+// out-of-place variant (same layout for src and dst)
+extern "C" int nbk_fft_lines_oop(const void *src, void *dst, int dtype, int64_t n_line, int64_t line_stride,
+                                 int64_t n_inner, int64_t n_outer, int64_t outer_stride, int inverse, double scale,
+                                 void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "fft_lines_oop: bad dtype %d", dtype);
+    NBK_CHECK_ARG(is_pow2(n_line) && n_line >= 2 && n_line <= 8192, "fft_lines_oop: line length %lld unsupported", (long long)n_line);
+    if (n_inner <= 0 || n_outer <= 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4)
+        return launch_lines<float>(src, dst, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+    return launch_lines<double>(src, dst, (int)n_line, line_stride, n_inner, n_outer, outer_stride, inverse, scale, s);
+}
+
+template <typename T>
+static int launch_lines_scatter(const void *src, void *const *peer_host, int N, int64_t n_inner, int64_t n_outer,
+                                int64_t outer_start, int P, int inverse, double scale, cudaStream_t s) {
+    typedef typename C2<T>::type C;
+    int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
+    void *tw;
+    int rc = get_twiddle(N, dtype, s, &tw);
+    if (rc) return rc;
+    int B = pick_B(N, (int)sizeof(C), n_inner);
+    size_t smem = (size_t)N * (B + 2) * sizeof(C);
+    NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines_scatter: N=%d does not fit in shared memory", N);
+    int64_t tiles_inner = (n_inner + B - 1) / B;
+    int64_t n_tiles = tiles_inner * n_outer;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+    PeerPtrs<C> peers;
+    for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = i < P ? (C *)peer_host[i] : nullptr;
+#define LAUNCH_LS(BB)                                                                                                \
+    case BB:                                                                                                         \
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_scatter<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_fft_lines_scatter<T, BB><<<(int)g, 256, smem, s>>>((const C *)src, peers, (const C *)tw, N, ilog2(N), n_inner, \
+                                                             tiles_inner, n_tiles, N / P, n_outer * P, outer_start,   \
+                                                             inverse, (T)scale);                                     \
+        break;
+    switch (B) {
+        LAUNCH_LS(1) LAUNCH_LS(2) LAUNCH_LS(4) LAUNCH_LS(8) LAUNCH_LS(16)
+        default: nbk_set_error("fft_lines_scatter: internal tile width %d", B); return NBK_ERR_ARG;
+    }
+#undef LAUNCH_LS
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+extern "C" int nbk_fft_lines_scatter(const void *src, void *const *peer_ptrs_host, int dtype, int64_t n_line,
+                                     int64_t n_inner, int64_t n_outer, int64_t outer_start, int P, int inverse,
+                                     double scale, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "fft_lines_scatter: bad dtype %d", dtype);
+    NBK_CHECK_ARG(is_pow2(n_line) && n_line >= 2 && n_line <= 8192, "fft_lines_scatter: line length %lld unsupported", (long long)n_line);
+    NBK_CHECK_ARG(P >= 1 && P <= NBK_MAX_PEERS && n_line % P == 0, "fft_lines_scatter: bad peer count %d", P);
+    if (n_inner <= 0 || n_outer <= 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4)
+        return launch_lines_scatter<float>(src, peer_ptrs_host, (int)n_line, n_inner, n_outer, outer_start, P, inverse, scale, s);
+    return launch_lines_scatter<double>(src, peer_ptrs_host, (int)n_line, n_inner, n_outer, outer_start, P, inverse, scale, s);
 }
 
 template <typename T>
@@ -429,6 +543,16 @@ static int check_dims(const char *who, int dtype, int64_t Nx, int64_t Ny, int64_
                   "%s: Nmesh (%lld,%lld,%lld) unsupported: each side must be a power of two (Nz >= 4)", who,
                   (long long)Nx, (long long)Ny, (long long)Nz);
     return NBK_OK;
+}
+
+// z pass alone: real rows [rows][Nz] -> complex rows [rows][Nz/2+1]
+extern "C" int nbk_fft_z_forward(const void *real, void *cplx, int dtype, int64_t rows, int64_t Nz, void *stream) {
+    int rc = check_dims("fft_z_forward", dtype, 1, 1, Nz);
+    if (rc) return rc;
+    if (rows <= 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    return (dtype == NBK_F4) ? launch_z<float>(real, cplx, rows, (int)Nz, true, 1.0, s)
+                             : launch_z<double>(real, cplx, rows, (int)Nz, true, 1.0, s);
 }
 
 extern "C" int nbk_fft_zy_forward(const void *real, void *cplx, int dtype, int64_t x_n, int64_t Ny, int64_t Nz,

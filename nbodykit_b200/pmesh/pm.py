@@ -291,6 +291,36 @@ class ParticleMesh(object):
         recv = self.comm.alltoall(counts)
         return Layout(self.comm, src[order], counts, recv)
 
+    # ---- NVLink peer-memory staging for the slab transpose (P > 1)
+    def _peer_stage(self):
+        """(local staging tensor viewed as this rank's transposed complex field, ctypes array of the P peer
+        pointers, symmetric-memory handle) -- allocated collectively at the first distributed transform.  None when
+        symmetric memory is unavailable: the transform then goes through pack + NCCL all-to-all + unpack."""
+        if hasattr(self, "_stage"):
+            return self._stage
+        self._stage = None
+        import os
+        if self.comm.size == 1 or os.environ.get("NBK_FFT_TRANSPOSE", "peer") != "peer":
+            return None
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+            dev = current_device()
+            nreal = 2 * int(numpy.prod(self.complex_shape))
+            buf = symm_mem.empty(nreal, dtype=_TORCH_REAL[self.typestr], device=dev)
+            group = getattr(self.comm, "group", None) or dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, group.group_name)
+            ptrs = (ctypes.c_void_p * self.comm.size)(*[int(p) for p in hdl.buffer_ptrs])
+            view = torch.view_as_complex(buf.view(-1, 2)).view(self.complex_shape)
+            ok = torch.ones(1, device=dev)
+            self.comm.allreduce_tensor(ok)                     # every rank got here
+            self._stage = (view, ptrs, hdl)
+        except Exception as e:   # noqa: BLE001  (any failure -> NCCL path, still on the GPU)
+            import logging
+            logging.getLogger("ParticleMesh").warning("peer-memory transpose unavailable (%s); using NCCL all-to-all", e)
+            self._stage = None
+        return self._stage
+
     def _decompose_device(self, pos, smoothing):
         """routing plan for device-resident positions: one kernel pass, one tiny all-to-all of the counts"""
         P = self.comm.size
@@ -669,6 +699,26 @@ class RealField(Field):
         else:
             Nzc = pm.Nzc
             work = torch.empty((pm.x_n, Ny, Nzc), dtype=out.value.dtype, device=out.value.device)
+            st = pm._peer_stage()
+            if st is not None:
+                # z pass locally; y pass writes every output row straight into its owner's staging buffer over
+                # NVLink (fused compute + transpose); barriers bracket the remote writes; x pass reads the staging
+                # buffer and writes the result field
+                view, ptrs, hdl = st
+                from .._lib import lib as _L
+                with stage("fft_z"):
+                    check(_L().nbk_fft_z_forward(_ptr(self.value), _ptr(work), code, pm.x_n * Ny, Nz, _stream()), "fft_z_forward")
+                hdl.barrier(channel=0)
+                with stage("fft_y_scatter"):
+                    check(_L().nbk_fft_lines_scatter(_ptr(work), ptrs, code, Ny, Nzc, pm.x_n, pm.x_start, P, 0, 1.0,
+                                                     _stream()), "fft_lines_scatter")
+                hdl.barrier(channel=1)
+                scale = float(scale) / (float(Nx) * Ny * Nz)
+                with stage("fft_x"):
+                    check(_L().nbk_fft_lines_oop(_ptr(view), _ptr(out.value), code, Nx, Nzc, Nzc, pm.y_n, Nx * Nzc, 0, scale,
+                                                 _stream()), "fft_lines_oop(x)")
+                out.attrs = dict(self.attrs)
+                return out
             send = torch.empty_like(work)
             with stage("fft_zy"):
                 check(lib().nbk_fft_zy_forward(_ptr(self.value), _ptr(work), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_forward")

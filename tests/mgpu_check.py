@@ -64,6 +64,9 @@ def main():
             print("case %s: %s (real field bit-identical to 1 GPU: %s)" % (c, "OK" if ok else "MISMATCH", bitexact), flush=True)
             if not ok:
                 failures.append(c)
+    if rank == 0:
+        st = getattr(mesh.pm, "_stage", "unused")
+        print("slab transpose path: %s" % ("NVLink peer-memory scatter" if st not in (None, "unused") else "NCCL all-to-all (%s)" % str(st)), flush=True)
     flag = torch.tensor([len(failures)], device="cuda")
     dist.broadcast(flag, 0)
     dist.barrier()

@@ -452,3 +452,38 @@ def test_route_kernels_vs_numpy(cuda):
             b = np.concatenate([pos[sel].astype("f8"), mass[sel][:, None]], axis=1)
             assert np.array_equal(a[np.lexsort(a.T)], b[np.lexsort(b.T)])
             start += cnt[r]
+
+
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+def test_fft_scatter_transpose_two_virtual_ranks(cuda, dtype):
+    """nbk_fft_z_forward + nbk_fft_lines_scatter + nbk_fft_lines_oop == r2c, with the slab transpose done by the y
+    pass writing into 'peer' buffers (two virtual ranks on one GPU: the peers are two buffers of this device)"""
+    import ctypes
+    import torch
+    from nbodykit_b200 import _lib
+    Nx, Ny, Nz, P = 16, 32, 8, 2
+    Nzc = Nz // 2 + 1
+    rng = np.random.RandomState(17)
+    real = rng.standard_normal((Nx, Ny, Nz)).astype(dtype)
+    want = np.fft.rfftn(real.astype("f8")) / real.size
+    cdt = torch.complex64 if dtype == "f4" else torch.complex128
+    code = 4 if dtype == "f4" else 8
+    Lb = _lib.lib()
+    x_n, y_n = Nx // P, Ny // P
+    stage = [torch.zeros((y_n, Nx, Nzc), dtype=cdt, device="cuda") for _ in range(P)]
+    ptrs = (ctypes.c_void_p * P)(*[t.data_ptr() for t in stage])
+    for r in range(P):      # each virtual rank transforms its x slab and scatters rows to the owners of y
+        slab = torch.from_numpy(real[r * x_n:(r + 1) * x_n].copy()).cuda()
+        work = torch.empty((x_n, Ny, Nzc), dtype=cdt, device="cuda")
+        _lib.check(Lb.nbk_fft_z_forward(ctypes.c_void_p(slab.data_ptr()), ctypes.c_void_p(work.data_ptr()), code, x_n * Ny, Nz, None))
+        _lib.check(Lb.nbk_fft_lines_scatter(ctypes.c_void_p(work.data_ptr()), ptrs, code, Ny, Nzc, x_n, r * x_n, P, 0, 1.0, None))
+    torch.cuda.synchronize()
+    tol = 1e-13 if dtype == "f8" else 2e-6
+    for r in range(P):      # x pass out of place on each rank's transposed field
+        out = torch.empty_like(stage[r])
+        _lib.check(Lb.nbk_fft_lines_oop(ctypes.c_void_p(stage[r].data_ptr()), ctypes.c_void_p(out.data_ptr()), code, Nx, Nzc, Nzc,
+                                        y_n, Nx * Nzc, 0, 1.0 / real.size, None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()                                  # [y_n][Nx][Nzc]
+        ref = np.transpose(want[:, r * y_n:(r + 1) * y_n, :], (1, 0, 2))
+        assert np.abs(got - ref).max() <= tol * np.sqrt((np.abs(want) ** 2).mean()) * 10
