@@ -162,6 +162,9 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     stages = _lib.profiler.stop()
+    if _lib.profiler.host and rank == 0:
+        for k, (t, c) in sorted(_lib.profiler.wall.items()):
+            sys.stderr.write("TRACE %-20s %8.3f ms/step (%d calls)\n" % (k, 1e3 * t / max(1, nw + args.steps), c))
     launches = _lib.launch_count() - l0
     clocks = sampler.stop() if sampler else None
     tms = torch.tensor([ms], dtype=torch.float64, device="cuda")

@@ -112,6 +112,10 @@ class _Profiler(object):
     def __init__(self):
         self.enabled = False
         self.records = []
+        # NBK_TRACE=1: additionally bracket every stage with a device synchronize and accumulate host wall time
+        # (diagnosis only -- it serialises the pipeline)
+        self.host = bool(os.environ.get("NBK_TRACE"))
+        self.wall = {}
 
     def start(self):
         self.enabled = True
@@ -139,6 +143,11 @@ class stage(object):
         self.name = name
 
     def __enter__(self):
+        if profiler.host:
+            import time
+            import torch
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
         if profiler.enabled:
             import torch
             self.a = torch.cuda.Event(enable_timing=True)
@@ -150,4 +159,11 @@ class stage(object):
         if profiler.enabled:
             self.b.record()
             profiler.records.append((self.name, self.a, self.b))
+        if profiler.host:
+            import time
+            import torch
+            torch.cuda.synchronize()
+            w = profiler.wall.setdefault(self.name, [0.0, 0])
+            w[0] += time.perf_counter() - self.t0
+            w[1] += 1
         return False

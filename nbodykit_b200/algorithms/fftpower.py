@@ -134,7 +134,8 @@ class FFTPower(FFTBase):
     def run(self):
         if self.attrs['mode'] == "1d":
             self.attrs['Nmu'] = 1
-        c1, c2, attrs = self._compute_3d_power(self.first, self.second)
+        with stage("H:compute_fields"):
+            c1, c2, attrs = self._compute_3d_power(self.first, self.second)
         dk = self.attrs['dk']
         kmin = self.attrs['kmin']
         kmax = self.attrs['kmax']
@@ -258,11 +259,12 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
             _lib.i32arr(_poles), Nell, 1, _lib.COMP.get(compensation[0], 0), _lib.COMP.get(compensation[1], 0),
             _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
-    if comm.size > 1:
-        comm.allreduce_tensor(nsum)
-        comm.allreduce_tensor(facc)
-    Nsum = nsum.cpu().numpy().reshape(Nx + 2, Nmu + 2)
-    f = facc.cpu().numpy()
+    with stage("H:bin_reduce"):
+        if comm.size > 1:
+            comm.allreduce_tensor(nsum)
+            comm.allreduce_tensor(facc)
+        Nsum = nsum.cpu().numpy().reshape(Nx + 2, Nmu + 2)
+        f = facc.cpu().numpy()
     xsum = f[:nb].reshape(Nx + 2, Nmu + 2)
     musum = f[nb:2 * nb].reshape(Nx + 2, Nmu + 2)
     ysum = f[2 * nb:].reshape(Nell, Nx + 2, Nmu + 2, 2)

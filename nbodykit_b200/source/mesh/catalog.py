@@ -19,7 +19,7 @@ import numpy
 import torch
 
 from ... import _global_options, _lib
-from ..._lib import check, lib
+from ..._lib import check, lib, stage
 from ...base.catalog import Column, ConstantColumn
 from ...base.mesh import MeshSource
 from ...pmesh import window
@@ -160,26 +160,31 @@ class CatalogMesh(MeshSource):
         """un-normalised paint: returns (real | (real1, real2) if interlaced, N, W, W2)"""
         pm = self.pm
         resampler = window.methods[self.resampler]
-        pos, mass, Nlocal, Wlocal, W2local = self._device_columns()
+        with stage("H:columns"):
+            pos, mass, Nlocal, Wlocal, W2local = self._device_columns()
         smoothing = (1.0 if self.interlaced else 0.5) * resampler.support
         scalar = isinstance(mass, float)
         # every rank paints its own particles (out-of-slab stencil points are dropped by the kernel) plus the
         # copies other ranks send for planes it owns
         batches = [(pos, mass)]
         if pm.comm.size > 1:
-            lay = pm.decompose(pos, smoothing=smoothing)
-            rpos, rmass = lay.route(pos, None if scalar else mass)
+            with stage("H:decompose"):
+                lay = pm.decompose(pos, smoothing=smoothing)
+            with stage("H:route"):
+                rpos, rmass = lay.route(pos, None if scalar else mass)
             batches.append((rpos, mass if scalar else rmass))
-            N, W, W2 = pm.comm.allreduce_floats([Nlocal, Wlocal, W2local])
+            with stage("H:allreduce3"):
+                N, W, W2 = pm.comm.allreduce_floats([Nlocal, Wlocal, W2local])
             N = int(round(N))
         else:
             N, W, W2 = Nlocal, Wlocal, W2local
         if not self.interlaced:
-            real = RealField(pm)
-            real[...] = 0
-            for p, m in batches:
-                if p.shape[0]:
-                    pm.paint(p, mass=m, resampler=resampler, hold=True, out=real)
+            with stage("H:paint_all"):
+                real = RealField(pm)
+                real[...] = 0
+                for p, m in batches:
+                    if p.shape[0]:
+                        pm.paint(p, mass=m, resampler=resampler, hold=True, out=real)
             return real, N, W, W2
         real1, real2 = RealField(pm), RealField(pm)
         real1[...] = 0
@@ -257,7 +262,8 @@ class CatalogMesh(MeshSource):
             c2 = real2.r2c(scale=1.0 / nbar)
             c.interlace_combine(c2)
         else:
-            c = painted.r2c(scale=1.0 / nbar)
+            with stage("H:r2c"):
+                c = painted.r2c(scale=1.0 / nbar)
         c.attrs = attrs
         if self.pm.comm.rank == 0:
             self.logger.info("painted %d objects to mesh" % N)
