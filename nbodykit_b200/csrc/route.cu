@@ -17,10 +17,18 @@ __device__ __forceinline__ unsigned route_mask(double p, const RouteGeom &g) {
     if (!isfinite(gx)) return 0u;
     long long lo = (long long)floor(gx - g.smoothing), hi = (long long)floor(gx + g.smoothing);
     unsigned m = 0u;
-    for (long long c = lo; c <= hi; c++) {
-        long long w = c % g.Nx;
-        if (w < 0) w += g.Nx;
-        m |= 1u << (unsigned)(w / g.x_n);
+    if (hi - lo < g.x_n && lo >= -(long long)g.Nx && hi < 2ll * g.Nx) {
+        // the reach is narrower than a slab: only the slabs of the two end cells can be touched
+        int wl = (int)lo, wh = (int)hi;
+        wl = wl < 0 ? wl + g.Nx : (wl >= g.Nx ? wl - g.Nx : wl);
+        wh = wh < 0 ? wh + g.Nx : (wh >= g.Nx ? wh - g.Nx : wh);
+        m = (1u << (unsigned)(wl / g.x_n)) | (1u << (unsigned)(wh / g.x_n));
+    } else {
+        for (long long c = lo; c <= hi; c++) {
+            long long w = c % g.Nx;
+            if (w < 0) w += g.Nx;
+            m |= 1u << (unsigned)(w / g.x_n);
+        }
     }
     return m & ~(1u << g.rank);
 }
