@@ -58,13 +58,19 @@ __device__ __forceinline__ void dft4(C &a0, C &a1, C &a2, C &a3) {
     a3 = csub(c2, c3);
 }
 
-// In-place forward DIF FFT of B side-by-side lines of length N held in sm[n*(B+1) + b].
+// Shared-memory address (in elements) of line element e, column b.  Rows are padded to B+1 elements; with SKEW an
+// extra element is inserted every N/8 rows, so that the digit-reversed rows 0, N/8, 2N/8, ... which consecutive
+// output frequencies live in fall into different banks (the z passes read the tile with lanes along frequency).
+template <int B, bool SKEW>
+__device__ __forceinline__ int saddr(int e, int sk) { return e * (B + 1) + (SKEW ? (e >> sk) : 0); }
+
+// In-place forward DIF FFT of B side-by-side lines of length N held at sm[saddr(n) + b].
 // tw[k] = exp(-2 pi i k / N), k < N (shared or global memory).  All threads of the CTA must call.
 // Each radix-8 butterfly lives in registers: 8 LDS + 8 STS per 8 points per stage (3 stages at N = 512).
-template <typename C, int B>
+template <typename C, int B, bool SKEW = false>
 __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N, int log2n) {
-    constexpr int pitch = B + 1;
     const int T = blockDim.x;
+    const int sk = log2n >= 3 ? log2n - 3 : 31;
     const int n8 = log2n / 3, rrem = log2n - 3 * n8;
     int Ns = N;
     int lq = log2n;
@@ -73,14 +79,16 @@ __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N,
         lq -= 3;                       // log2(Q)
         const int tws = N / Ns;
         const int work = (N >> 3) * B;
-        const int st = Q * pitch;
         for (int w = threadIdx.x; w < work; w += T) {
             int b = w % B;
             int t = w / B;
             int blk = t >> lq, q = t & (Q - 1);
-            C *p = sm + (blk * Ns + q) * pitch + b;
-            C a0 = p[0], a1 = p[st], a2 = p[2 * st], a3 = p[3 * st];
-            C a4 = p[4 * st], a5 = p[5 * st], a6 = p[6 * st], a7 = p[7 * st];
+            const int e0 = blk * Ns + q;
+            C *p0 = sm + saddr<B, SKEW>(e0, sk) + b, *p1 = sm + saddr<B, SKEW>(e0 + Q, sk) + b;
+            C *p2 = sm + saddr<B, SKEW>(e0 + 2 * Q, sk) + b, *p3 = sm + saddr<B, SKEW>(e0 + 3 * Q, sk) + b;
+            C *p4 = sm + saddr<B, SKEW>(e0 + 4 * Q, sk) + b, *p5 = sm + saddr<B, SKEW>(e0 + 5 * Q, sk) + b;
+            C *p6 = sm + saddr<B, SKEW>(e0 + 6 * Q, sk) + b, *p7 = sm + saddr<B, SKEW>(e0 + 7 * Q, sk) + b;
+            C a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3, a4 = *p4, a5 = *p5, a6 = *p6, a7 = *p7;
             // level 1: b_m = a_m + a_{m+4}; b_{m+4} = (a_m - a_{m+4}) W8^m
             C b0 = cadd(a0, a4), b1 = cadd(a1, a5), b2 = cadd(a2, a6), b3 = cadd(a3, a7);
             C b4 = csub(a0, a4), d5 = csub(a1, a5), d6 = csub(a2, a6), d7 = csub(a3, a7);
@@ -100,8 +108,7 @@ __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N,
                 b3 = cmul(b3, tw[6 * ti]);
                 b7 = cmul(b7, tw[7 * ti]);
             }
-            p[0] = b0; p[st] = b4; p[2 * st] = b1; p[3 * st] = b5;
-            p[4 * st] = b2; p[5 * st] = b6; p[6 * st] = b3; p[7 * st] = b7;
+            *p0 = b0; *p1 = b4; *p2 = b1; *p3 = b5; *p4 = b2; *p5 = b6; *p6 = b3; *p7 = b7;
         }
         __syncthreads();
         Ns = Q;
@@ -111,10 +118,11 @@ __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N,
         for (int w = threadIdx.x; w < work; w += T) {
             int b = w % B;
             int t = w / B;
-            C *p = sm + (4 * t) * pitch + b;
-            C a0 = p[0], a1 = p[pitch], a2 = p[2 * pitch], a3 = p[3 * pitch];
+            C *p0 = sm + saddr<B, SKEW>(4 * t, sk) + b, *p1 = sm + saddr<B, SKEW>(4 * t + 1, sk) + b;
+            C *p2 = sm + saddr<B, SKEW>(4 * t + 2, sk) + b, *p3 = sm + saddr<B, SKEW>(4 * t + 3, sk) + b;
+            C a0 = *p0, a1 = *p1, a2 = *p2, a3 = *p3;
             dft4(a0, a1, a2, a3);
-            p[0] = a0; p[pitch] = a1; p[2 * pitch] = a2; p[3 * pitch] = a3;
+            *p0 = a0; *p1 = a1; *p2 = a2; *p3 = a3;
         }
         __syncthreads();
     } else if (rrem == 1) {  // Ns == 2
@@ -122,10 +130,10 @@ __device__ __forceinline__ void fft_tile(C *sm, const C *__restrict__ tw, int N,
         for (int w = threadIdx.x; w < work; w += T) {
             int b = w % B;
             int t = w / B;
-            C *p = sm + (2 * t) * pitch + b;
-            C a0 = p[0], a1 = p[pitch];
-            p[0] = cadd(a0, a1);
-            p[pitch] = csub(a0, a1);
+            C *p0 = sm + saddr<B, SKEW>(2 * t, sk) + b, *p1 = sm + saddr<B, SKEW>(2 * t + 1, sk) + b;
+            C a0 = *p0, a1 = *p1;
+            *p0 = cadd(a0, a1);
+            *p1 = csub(a0, a1);
         }
         __syncthreads();
     }
@@ -143,31 +151,72 @@ __device__ __forceinline__ const C *stage_twiddles(C *dst, const C *__restrict__
 // strided line pass (y and x passes), in place.  element(outer, n, inner) =
 //   data[outer*outer_stride + n*line_stride + inner],  inner < n_inner contiguous.
 // ---------------------------------------------------------------------------------------------
+// 16- / 8-byte asynchronous global -> shared copies (LDGSTS): the next tile streams in while this one is transformed
+__device__ __forceinline__ void cp_async_elem(double2 *sdst, const double2 *gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(float2 *sdst, const float2 *gsrc) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N_> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N_) : "memory"); }
+
+// strided tile -> shared [N][B+1]; columns beyond the valid width are zero-filled with plain stores
+template <typename C, int B>
+__device__ __forceinline__ void prefetch_tile(C *sm, const C *base, int N, int64_t line_stride, int bvalid) {
+    constexpr int pitch = B + 1;
+    for (int w = threadIdx.x; w < N * B; w += blockDim.x) {
+        int b = w % B, n = w / B;
+        if (b < bvalid) cp_async_elem(&sm[n * pitch + b], base + (int64_t)n * line_stride + b);
+        else sm[n * pitch + b] = C{0, 0};
+    }
+}
+
 template <typename T, int B>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 k_fft_lines(const typename C2<T>::type *src, typename C2<T>::type *dst, const typename C2<T>::type *__restrict__ tw,
             int N, int log2n, int64_t line_stride, int64_t n_inner, int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride,
             int inverse, T scale) {
     typedef typename C2<T>::type C;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    C *sm = reinterpret_cast<C *>(smem_raw);
+    // shared: buf[2][N][B+1] | twiddles[N]  -- two tile buffers: tile i+1 is prefetched with cp.async while tile i is
+    // transformed and written back
+    C *buf0 = reinterpret_cast<C *>(smem_raw);
     constexpr int pitch = B + 1;
+    C *buf1 = buf0 + (size_t)N * pitch;
     const int T_ = blockDim.x;
-    tw = stage_twiddles<C>(sm + N * pitch, tw, N);
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    tw = stage_twiddles<C>(buf1 + (size_t)N * pitch, tw, N);
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) {
         int64_t outer = tile / tiles_inner;
         int64_t inner0 = (tile - outer * tiles_inner) * B;
-        const C *base = src + outer * outer_stride + inner0;
+        int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+        prefetch_tile<C, B>(buf0, src + outer * outer_stride + inner0, N, line_stride, bvalid);
+    }
+    cp_async_commit();
+    int cur = 0;
+    for (; tile < n_tiles; tile += gridDim.x, cur ^= 1) {
+        C *sm = cur ? buf1 : buf0;
+        int64_t outer = tile / tiles_inner;
+        int64_t inner0 = (tile - outer * tiles_inner) * B;
         C *obase = dst + outer * outer_stride + inner0;      // dst == src: in place (a CTA owns its tile)
         int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
-        for (int w = threadIdx.x; w < N * B; w += T_) {
-            int b = w % B, n = w / B;
-            C v = C{0, 0};
-            if (b < bvalid) v = base[(int64_t)n * line_stride + b];
-            if (inverse) v.y = -v.y;
-            sm[n * pitch + b] = v;
+        int64_t nxt = tile + gridDim.x;
+        if (nxt < n_tiles) {
+            int64_t o2 = nxt / tiles_inner;
+            int64_t i2 = (nxt - o2 * tiles_inner) * B;
+            int bv2 = (int)((n_inner - i2) < B ? (n_inner - i2) : B);
+            prefetch_tile<C, B>(cur ? buf0 : buf1, src + o2 * outer_stride + i2, N, line_stride, bv2);
         }
+        cp_async_commit();
+        cp_async_wait<1>();          // this tile's copies have landed (the prefetch may still be in flight)
         __syncthreads();
+        if (inverse) {
+            for (int w = threadIdx.x; w < N * B; w += T_) { int b = w % B, n = w / B; sm[n * pitch + b].y = -sm[n * pitch + b].y; }
+            __syncthreads();
+        }
         fft_tile<C, B>(sm, tw, N, log2n);
         for (int w = threadIdx.x; w < N * B; w += T_) {
             int b = w % B, k = w / B;
@@ -179,10 +228,10 @@ k_fft_lines(const typename C2<T>::type *src, typename C2<T>::type *dst, const ty
                 obase[(int64_t)k * line_stride + b] = v;
             }
         }
-        __syncthreads();
+        __syncthreads();             // everyone is done with `sm` before the next prefetch overwrites it
     }
+    cp_async_wait<0>();
 }
-
 // ---------------------------------------------------------------------------------------------
 // Fused line pass + slab transpose over peer memory (P > 1).  Lines of length N run along the SECOND stored axis
 // of the local slab src[n_outer][N][n_inner] (the y pass of r2c on [x_n][Ny][Nzc], or the inverse x pass of c2r on
@@ -252,8 +301,9 @@ k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
     const int Nzc = M + 1;
     constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
+    const int sk = log2m >= 3 ? log2m - 3 : 31;
     const int64_t n_tiles = (rows + B - 1) / B;
-    twM = stage_twiddles<C>(sm + M * pitch, twM, M);
+    twM = stage_twiddles<C>(sm + M * pitch + 8, twM, M);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t row0 = tile * B;
         int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
@@ -262,16 +312,16 @@ k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
             int n = w & (M - 1), b = w >> log2m;  // lanes run along the contiguous row
             C v = C{0, 0};
             if (b < bvalid) v = src[(int64_t)b * M + n];
-            sm[n * pitch + b] = v;
+            sm[saddr<B, true>(n, sk) + b] = v;
         }
         __syncthreads();
-        fft_tile<C, B>(sm, twM, M, log2m);
+        fft_tile<C, B, true>(sm, twM, M, log2m);
         C *dst = cplx + row0 * Nzc;
         for (int w = threadIdx.x; w < Nzc * B; w += T_) {
             int k = w % Nzc, b = w / Nzc;
             if (b < bvalid) {
-                C zk = sm[pos_of_freq(k & (M - 1), M, log2m) * pitch + b];
-                C zm = cconj(sm[pos_of_freq((M - k) & (M - 1), M, log2m) * pitch + b]);
+                C zk = sm[saddr<B, true>(pos_of_freq(k & (M - 1), M, log2m), sk) + b];
+                C zm = cconj(sm[saddr<B, true>(pos_of_freq((M - k) & (M - 1), M, log2m), sk) + b]);
                 C e = cadd(zk, zm), o = csub(zk, zm);
                 C wo = cmul(twN[k], o);          // W_N^k (Z[k] - conj Z[M-k])
                 C x = C{e.x + wo.y, e.y - wo.x};  // e - i*wo
@@ -298,8 +348,9 @@ k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
     const int Nzc = M + 1;
     constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
+    const int sk = log2m >= 3 ? log2m - 3 : 31;
     const int64_t n_tiles = (rows + B - 1) / B;
-    twM = stage_twiddles<C>(sm + M * pitch, twM, M);
+    twM = stage_twiddles<C>(sm + M * pitch + 8, twM, M);
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         int64_t row0 = tile * B;
         int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
@@ -316,15 +367,15 @@ k_fft_z_c2r(const typename C2<T>::type *__restrict__ cplx, T *__restrict__ real,
                 C z = C{e.x - o.y, e.y + o.x};
                 v = cconj(z);
             }
-            sm[k * pitch + b] = v;
+            sm[saddr<B, true>(k, sk) + b] = v;
         }
         __syncthreads();
-        fft_tile<C, B>(sm, twM, M, log2m);
+        fft_tile<C, B, true>(sm, twM, M, log2m);
         C *dst = reinterpret_cast<C *>(real + row0 * Nz);
         for (int w = threadIdx.x; w < M * B; w += T_) {
             int n = w & (M - 1), b = w >> log2m;
             if (b < bvalid) {
-                C v = cconj(sm[pos_of_freq(n, M, log2m) * pitch + b]);
+                C v = cconj(sm[saddr<B, true>(pos_of_freq(n, M, log2m), sk) + b]);
                 dst[(int64_t)b * M + n] = v;
             }
         }
@@ -401,8 +452,12 @@ static int launch_lines(const void *data, void *dst, int N, int64_t line_stride,
     void *tw;
     int rc = get_twiddle(N, dtype, s, &tw);
     if (rc) return rc;
-    int B = pick_B(N, (int)sizeof(C), n_inner);
-    size_t smem = (size_t)N * (B + 2) * sizeof(C);     // tile [N][B+1] + twiddle table [N]
+    // two tile buffers [N][B+1] + twiddle table [N].  B * sizeof(C) = 128 bytes makes every quarter-warp shared
+    // access one full padded row (bank-conflict free for any row), so keep that width as long as it fits and run
+    // one 512-thread CTA per SM; narrower tiles only for very long lines.
+    int B = 128 / (int)sizeof(C);
+    while (B > 1 && ((size_t)N * (2 * (B + 1) + 1) * sizeof(C) > 220 * 1024 || B / 2 >= n_inner)) B >>= 1;
+    size_t smem = (size_t)N * (2 * (B + 1) + 1) * sizeof(C);
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: N=%d does not fit in shared memory", N);
     int64_t tiles_inner = (n_inner + B - 1) / B;
     int64_t n_tiles = tiles_inner * n_outer;
@@ -410,10 +465,11 @@ static int launch_lines(const void *data, void *dst, int N, int64_t line_stride,
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;
     int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+    const int nthreads = (per_sm == 1 && (int64_t)N * B >= 4096) ? 512 : 256;
 #define LAUNCH_LINES(BB)                                                                                          \
     case BB:                                                                                                      \
         NBK_CUDA(cudaFuncSetAttribute(k_fft_lines<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_fft_lines<T, BB><<<(int)g, 256, smem, s>>>((const C *)data, (C *)dst, (const C *)tw, N, ilog2(N), line_stride, n_inner, \
+        k_fft_lines<T, BB><<<(int)g, nthreads, smem, s>>>((const C *)data, (C *)dst, (const C *)tw, N, ilog2(N), line_stride, n_inner, \
                                                      tiles_inner, n_tiles, outer_stride, inverse, (T)scale);      \
         break;
     switch (B) {
@@ -509,7 +565,7 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
     rc = get_twiddle(Nz, dtype, s, &twN);
     if (rc) return rc;
     int B = pick_B(M, (int)sizeof(C), rows);
-    size_t smem = (size_t)M * (B + 2) * sizeof(C);     // tile [M][B+1] + twiddle table [M]
+    size_t smem = ((size_t)M * (B + 2) + 8) * sizeof(C);     // tile [M][B+1] (+8 skew) + twiddle table [M]
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);
     int64_t n_tiles = (rows + B - 1) / B;
     int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -300,21 +300,38 @@ __device__ __noinline__ int tile_of_exact(const PT *__restrict__ pos, int64_t i,
 // coordinate by < 2^-22 |g|, so unless the fraction of (g32 + A) lies within 3e-7|g| of a cell boundary (or the
 // particle is far outside the box) floor() agrees with the exact arithmetic; the rare rest is recomputed in f8.
 // The result is therefore ALWAYS the exact leftmost cell -- count, scatter and paint passes agree.
+// per-launch constants of the float32 fast path
+struct FastTile {
+    float sc[3];    // float32 scale N/L
+    float lim[3];   // accept when |frac(g) - 0.5| < lim  (frac at least eps away from both cell boundaries)
+};
+
+__device__ __forceinline__ FastTile make_fast_tile(const TileGeom &tg) {
+    FastTile f;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        f.sc[d] = (float)tg.gm.scale[d];
+        // |g32 - g_exact| <= 2 float32 roundings of a value below n+2 -> 3e-7 (n+2) + 1e-6 is a safe margin
+        f.lim[d] = 0.5f - (3e-7f * (float)(tg.gm.n[d] + 2) + 1e-6f);
+    }
+    return f;
+}
+
+// Tile id of particle i.  float32 in-box positions take a float32 fast path: unless the fraction of
+// (x*scale + A) lies within the rounding margin of a cell boundary, floor() agrees with the exact f8 arithmetic;
+// everything else (near-boundary, outside the box, f8 positions) is recomputed in f8.  The id is therefore
+// ALWAYS the exact leftmost cell's tile -- count, scatter and paint passes agree.
 template <int SUP, typename PT>
-__device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
-                                       const float *sc32) {
+__device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, const FastTile &ft) {
     if (sizeof(PT) == 4) {
         int c[3];
         bool ok = true;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            float g = (float)pos[3 * i + d] * sc32[d] + WinOff<SUP>::A;
+            float g = (float)pos[3 * i + d] * ft.sc[d] + WinOff<SUP>::A;
             float f = floorf(g);
-            float fr = g - f;
-            float eps = 3e-7f * fabsf(g) + 1e-6f;      // > |g32 - g_exact| (two float32 roundings)
-            ok = ok && (fr > eps) && (fr < 1.0f - eps) && (fabsf(g) < 65536.0f);
-            int ci = (int)f + WinOff<SUP>::B;
-            c[d] = ci < 0 ? ci + tg.gm.n[d] : (ci >= tg.gm.n[d] ? ci - tg.gm.n[d] : ci);
+            ok = ok && (fabsf((g - f) - 0.5f) < ft.lim[d]);
+            c[d] = (int)f + WinOff<SUP>::B;
             ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
         }
         if (ok) return tile_from_cells(c, tg);
@@ -348,11 +365,11 @@ k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n,
              unsigned *__restrict__ counts, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float mx = 0.f;
-    const float sc32[3] = {(float)tg.gm.scale[0], (float)tg.gm.scale[1], (float)tg.gm.scale[2]};
+    const FastTile ft = make_fast_tile(tg);
     int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
-        int t = in ? tile_of<SUP, PT>(pos, i, tg, sc32) : -1;
+        int t = in ? tile_of<SUP, PT>(pos, i, tg, ft) : -1;
         if (in) tile_ids[i] = t;          // the scatter pass reuses the id instead of recomputing it
         warp_claim(counts, t, t >= 0);
         if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);

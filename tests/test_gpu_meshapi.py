@@ -1,0 +1,109 @@
+"""MeshSource API on the GPU: FieldMesh / ArrayMesh sources, user callbacks through `.apply`, preview, actions."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import pmesh_oracle as po
+
+
+def test_fieldmesh_and_arraymesh_sources(cuda):
+    from nbodykit_b200.lab import ArrayMesh, FieldMesh, FFTPower
+    rng = np.random.RandomState(3)
+    N, L = 16, 100.
+    arr = rng.standard_normal((N, N, N)) + 1.0
+    am = ArrayMesh(arr, BoxSize=L)
+    real = am.compute(mode='real')
+    np.testing.assert_allclose(real.numpy(), arr, rtol=1e-14)
+    r1 = FFTPower(am, mode='1d')
+    # the same through a FieldMesh wrapping the real field, and through a raw Field (fftpower.py:708-713)
+    r2 = FFTPower(FieldMesh(real), mode='1d')
+    r3 = FFTPower(real, mode='1d')
+    o = po.power_from_complex(po.r2c(arr), None, N, L, mode='1d')
+    for r in (r1, r2, r3):
+        assert np.array_equal(r.power['modes'], np.squeeze(o['modes']))
+        np.testing.assert_allclose(r.power['power'].real, np.squeeze(o['power']).real, rtol=1e-10)
+    # complex input to ArrayMesh: irfftn(c) * N^3 (source/mesh/array.py:36-37)
+    c = np.fft.rfftn(arr) / arr.size
+    am2 = ArrayMesh(c, BoxSize=L)
+    np.testing.assert_allclose(am2.compute(mode='real').numpy(), arr, rtol=1e-10, atol=1e-12)
+    # the wrapped field is never modified
+    before = real.numpy().copy()
+    FieldMesh(real).compute(mode='complex')
+    np.testing.assert_array_equal(real.numpy(), before)
+
+
+def test_apply_user_callbacks_and_filters(cuda):
+    """base/mesh.py:118-176 contract: func(x, v) with x the coordinate list for `kind`"""
+    from nbodykit_b200.lab import ArrayMesh
+    from nbodykit_b200.base.mesh import MeshFilter
+    rng = np.random.RandomState(4)
+    N, L = [8, 16, 8], [10., 40., 20.]
+    arr = rng.standard_normal(N)
+    mesh = ArrayMesh(arr, BoxSize=L)
+    R = 3.0
+
+    def gauss(k, v):
+        k2 = sum(ki ** 2 for ki in k)
+        return v * np.exp(-0.5 * k2 * R ** 2)
+    out = mesh.apply(gauss, kind='wavenumber', mode='complex').compute(mode='complex').numpy()
+    k = po.k_coords(N, L, 'f4')
+    want = po.r2c(arr) * np.exp(-0.5 * (k[0] ** 2 + k[1] ** 2 + k[2] ** 2) * R ** 2)
+    np.testing.assert_allclose(out, want, rtol=1e-6, atol=1e-12)
+
+    class Circ(MeshFilter):
+        kind = 'circular'
+        mode = 'complex'
+
+        def filter(self, w, v):
+            return v * np.cos(w[0]) * np.cos(w[2])
+    out = mesh.apply(Circ).compute(mode='complex').numpy()
+    w = po.k_coords(N, L, 'f4', kind='circular')
+    np.testing.assert_allclose(out, po.r2c(arr) * np.cos(w[0]) * np.cos(w[2]), rtol=1e-5, atol=1e-10)
+    # a real-space action on index coordinates, then back to real
+    out = mesh.apply(lambda i, v: v * (i[1] % 2), kind='index', mode='real').compute(mode='real').numpy()
+    np.testing.assert_allclose(out, arr * (np.arange(16)[None, :, None] % 2), rtol=1e-14)
+
+
+def test_compensation_action_runs_as_kernel_and_matches_host_formula(cuda):
+    """mesh.compute(mode='complex') with compensated=True == r2c then the reference formula"""
+    from nbodykit_b200.lab import UniformCatalog
+    cat = UniformCatalog(nbar=1e-3, BoxSize=100., seed=7)
+    for resampler, interlaced in [("cic", False), ("tsc", True)]:
+        plain = cat.to_mesh(Nmesh=16, resampler=resampler, interlaced=interlaced, compensated=False, dtype='f8')
+        comp = cat.to_mesh(Nmesh=16, resampler=resampler, interlaced=interlaced, compensated=True, dtype='f8')
+        c0 = plain.compute(mode='complex').numpy()
+        c1 = comp.compute(mode='complex').numpy()
+        name = po.COMPENSATION[(interlaced, resampler)]
+        want = po.compensate(name, po.k_coords(16, 100., 'f8', kind='circular'), c0)
+        np.testing.assert_allclose(c1, want, rtol=1e-12, atol=1e-14)
+
+
+def test_preview_and_attrs(cuda):
+    from nbodykit_b200.lab import UniformCatalog
+    cat = UniformCatalog(nbar=1e-3, BoxSize=100., seed=7)
+    mesh = cat.to_mesh(Nmesh=16, dtype='f8')
+    full = mesh.preview()
+    real = mesh.compute(mode='real')
+    np.testing.assert_allclose(full, real.numpy())
+    np.testing.assert_allclose(mesh.preview(axes=(0, 1)), real.numpy().sum(axis=2))
+    np.testing.assert_allclose(full.sum(), real.csum(), rtol=1e-12)             # base/tests/test_mesh.py:117-135
+    for key in ['N', 'W', 'W2', 'shotnoise', 'num_per_cell', 'BoxSize', 'Nmesh', 'interlaced', 'compensated', 'resampler']:
+        assert key in real.attrs
+    np.testing.assert_allclose(real.cmean(), 1.0, rtol=1e-12)
+    with pytest.raises(ValueError):
+        mesh.compute(mode='nope')
+    with pytest.raises(NotImplementedError):
+        mesh.save("x")
+    with pytest.raises(NotImplementedError):
+        cat.to_mesh(Nmesh=16, dtype='c16')
+
+
+def test_dk0_unique_bins(cuda):
+    """algorithms/tests/test_fftpower.py:65-71: dk=0 -> one bin per distinct |k|, bin centres equal the mean k"""
+    from nbodykit_b200.lab import UniformCatalog, FFTPower
+    cat = UniformCatalog(nbar=3e-3, BoxSize=64., seed=42)
+    r = FFTPower(cat, mode='1d', Nmesh=8, dk=0)
+    p = r.power
+    np.testing.assert_allclose(p.coords['k'], p['k'], rtol=1e-6)
+    assert np.all(p['modes'] > 0)
