@@ -168,6 +168,9 @@ int nbk_interlace_combine(void *c1, const void *c2, int dtype, const int64_t *nm
  * (ells[0] must be 0).  coord_dtype NBK_F4 (fixture-faithful) | NBK_F8.
  * comp1 / comp2 (NBK_COMP_*): window compensation applied on the fly to c1 / c2 (the fused equivalent of
  * running nbk_compensate on each field first); NBK_COMP_NONE when the fields are already compensated.
+ * real_input != 0: c1 is a REAL [count][D1][Nz] statistic (FFTCorr, algorithms/fftcorr.py:148-176; needs is_p3d,
+ * hermitian == 0).  coord_unit_host: per-axis coordinate of index 1 (NULL -> 2 pi / L, the wavenumbers; FFTCorr
+ * passes the cell size L/N so that coordinates are the wrapped separations).
  * Outputs (device, ACCUMULATED into; zero first), nb = (Nx+2)*(Nmu+2):
  *   nsum int64[nb]; xsum, musum double[nb]; ysum double[Nell][nb][2] (re, im). */
 int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume,
@@ -175,7 +178,13 @@ int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double 
                   int transposed, int64_t start, int64_t count, int coord_dtype,
                   const double *k2edges_host, int Nx, const double *muedges_host, int Nmu,
                   const double *los_host, const int *ells_host, int Nell, int hermitian, int comp1,
-                  int comp2, int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
+                  int comp2, int real_input, const double *coord_unit_host, int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
+
+/* out = c1 * conj(c2) * scale with element 0 cleared when clear_first != 0 (the k = 0 mode on the rank that owns
+ * it): FFTBase._compute_3d_power (algorithms/fftpower.py:115-128), materialised only where the 3-D power itself
+ * is needed (FFTCorr, algorithms/fftcorr.py:148-150).  c2 == NULL -> auto power.  out may alias c1. */
+int nbk_cross_power(const void *c1, const void *c2, void *out, int dtype, int64_t n_complex, double scale,
+                    int clear_first, void *stream);
 
 /* ConvolvedFFTPower's spherical-harmonic passes (algorithms/convpower/fkp.py:571-597), real Y_lm, l <= 8:
  *   out(x) = in(x) * Y_lm(xhat), x = wrapped grid coordinate [-L/2, L/2) + offset[3] (BoxCenter + H/2, :457);

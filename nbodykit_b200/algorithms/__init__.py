@@ -1,7 +1,8 @@
 from .fftpower import FFTPower, FFTBase, project_to_basis
+from .fftcorr import FFTCorr
 from .convpower import ConvolvedFFTPower, FKPCatalog, FKPWeightFromNbar, FKPCatalogMesh
 
 FKPPower = ConvolvedFFTPower
 
-__all__ = ['FFTPower', 'FFTBase', 'project_to_basis', 'ConvolvedFFTPower', 'FKPPower', 'FKPCatalog',
+__all__ = ['FFTCorr', 'FFTPower', 'FFTBase', 'project_to_basis', 'ConvolvedFFTPower', 'FKPPower', 'FKPCatalog',
            'FKPWeightFromNbar', 'FKPCatalogMesh']

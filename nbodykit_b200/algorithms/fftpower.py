@@ -224,9 +224,14 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     Returns exactly what the reference returns:
     ``(xmean_2d, mumean_2d, y2d, N_2d), (xmean_1d, poles, N_1d) | None``.
     """
-    if not isinstance(y3d, ComplexField):
-        raise TypeError("project_to_basis_device needs a ComplexField (RealField statistics: FFTCorr, not on this path)")
+    is_real = isinstance(y3d, RealField)
+    if not isinstance(y3d, (ComplexField, RealField)):
+        raise TypeError("project_to_basis_device needs a RealField or ComplexField")
+    if is_real and not is_p3d:
+        raise ValueError("a RealField is binned as a 3-D statistic (is_p3d=True)")
     pm = y3d.pm
+    # real-space statistics (FFTCorr) are binned in the wrapped separation x = index * L/N
+    coord_unit = _lib.darr(pm.BoxSize / pm.Nmesh) if is_real else None
     comm = pm.comm
     xedges, muedges = edges
     xedges = numpy.asarray(xedges, dtype='f8')
@@ -250,14 +255,15 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     xsum = facc[:nb]
     musum = facc[nb:2 * nb]
     ysum = facc[2 * nb:]
-    tr, start, count = y3d._slab()
+    tr, start, count = (0, pm.x_start, pm.x_n) if is_real else y3d._slab()
     los_f = [float(v) for v in los]
     with stage("power_bin"):
         check(lib().nbk_power_bin(
             _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
             1 if is_p3d else 0, float(volume), 1 if clear_zero else 0, pm._nmesh_c, pm._box_c, tr, start, count,
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
-            _lib.i32arr(_poles), Nell, 1, _lib.COMP.get(compensation[0], 0), _lib.COMP.get(compensation[1], 0),
+            _lib.i32arr(_poles), Nell, 0 if is_real else 1, _lib.COMP.get(compensation[0], 0),
+            _lib.COMP.get(compensation[1], 0), 1 if is_real else 0, coord_unit,
             _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
     with stage("H:bin_reduce"):
         if comm.size > 1:

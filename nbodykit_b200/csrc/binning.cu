@@ -233,6 +233,7 @@ struct BinParams {
     int Nell;
     int ells[NBK_MAX_ELL];
     int hermitian, is_p3d, clear_zero, has_c2;
+    int estride;     // 2: complex input (re, im interleaved)   1: real input (a RealField statistic, FFTCorr)
     double volume;
 };
 
@@ -329,7 +330,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
         double kp2_64 = kx64 * kx64 + ky64 * ky64;
         double lp_64 = kx64 * P.los64[0] + ky64 * P.los64[1];
         double lp_48 = (double)kx32 * P.los64[0] + (double)ky32 * P.los64[1];
-        const int64_t rowlen = (int64_t)g.Nzc * 2;
+        const int64_t rowlen = (int64_t)g.Nzc * P.estride;
         int64_t roff[4];
         roff[0] = ((int64_t)i0 * g.D1 + i1) * rowlen;
         roff[1] = ((int64_t)i0 * g.D1 + m1) * rowlen;
@@ -391,8 +392,8 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     if (q == 1 && !use1) continue;
                     if (q == 2 && !use2) continue;
                     if (q == 3 && !use3) continue;
-                    const T *p1 = c1 + roff[q] + 2 * kz;
-                    double a = (double)p1[0], bb = (double)p1[1];
+                    const T *p1 = c1 + roff[q] + P.estride * kz;
+                    double a = (double)p1[0], bb = (P.estride == 2) ? (double)p1[1] : 0.0;
                     if (P.is_p3d) { yre += a; yim += bb; }
                     else {
                         double c = a, d = bb;
@@ -578,7 +579,8 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
                              const int64_t *nmesh, const double *box, int transposed, int64_t start, int64_t count,
                              int coord_dtype, const double *k2edges, int Nx, const double *muedges, int Nmu,
                              const double *los, const int *ells, int Nell, int hermitian, int comp1, int comp2,
-                             int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream) {
+                             int real_input, const double *coord_unit, int64_t *nsum, double *xsum, double *musum,
+                             double *ysum, void *stream) {
     NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "power_bin: bad dtype %d", dtype);
     NBK_CHECK_ARG(coord_dtype == 4 || coord_dtype == 8 || coord_dtype == 48, "power_bin: bad coord_dtype %d", coord_dtype);
     NBK_CHECK_ARG(Nx >= 0 && Nmu >= 1, "power_bin: need Nx >= 0 and Nmu >= 1");
@@ -592,7 +594,7 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
     const double TWO_PI = 6.283185307179586476925286766559;
     for (int d = 0; d < 3; d++) {
         NBK_CHECK_ARG(box[d] > 0, "power_bin: bad BoxSize");
-        P.kf64[d] = TWO_PI / box[d];
+        P.kf64[d] = coord_unit ? coord_unit[d] : TWO_PI / box[d];
         P.kf32[d] = (float)P.kf64[d];
         P.los64[d] = los[d];
         P.los32[d] = (float)los[d];
@@ -603,6 +605,8 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
     for (int l = 0; l < Nell; l++) NBK_CHECK_ARG(ells[l] >= 0 && ells[l] <= 64, "power_bin: bad multipole %d", ells[l]);
     P.hermitian = hermitian ? 1 : 0;
     P.is_p3d = is_p3d ? 1 : 0;
+    P.estride = real_input ? 1 : 2;
+    NBK_CHECK_ARG(!real_input || (is_p3d && !hermitian), "power_bin: a real input must be a full (non-Hermitian) 3-D statistic");
     P.clear_zero = clear_zero ? 1 : 0;
     P.has_c2 = (c2 != nullptr && c2 != c1) ? 1 : 0;
     P.volume = volume;

@@ -104,6 +104,34 @@ __global__ void __launch_bounds__(256) k_sum(const T *__restrict__ x, int64_t n,
     }
 }
 
+// out = c1 * conj(c2) * scale, element 0 optionally cleared (FFTBase._compute_3d_power, fftpower.py:115-128;
+// materialised only for FFTCorr, which transforms the 3-D power back to configuration space)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_cross_power(const T *__restrict__ c1, const T *__restrict__ c2, T *__restrict__ out, int64_t n, T scale, int clear_first) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        T a = c1[2 * i], b = c1[2 * i + 1], c = c2[2 * i], d = c2[2 * i + 1];
+        T re = (a * c + b * d) * scale, im = (b * c - a * d) * scale;
+        if (clear_first && i == 0) { re = 0; im = 0; }
+        out[2 * i] = re;
+        out[2 * i + 1] = im;
+    }
+}
+
+extern "C" int nbk_cross_power(const void *c1, const void *c2, void *out, int dtype, int64_t n_complex, double scale,
+                               int clear_first, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "nbk_cross_power: bad dtype %d", dtype);
+    if (n_complex <= 0) return NBK_OK;
+    if (c2 == nullptr) c2 = c1;
+    cudaStream_t s = (cudaStream_t)stream;
+    int g = nbk_grid_for(n_complex, 256, 8);
+    if (dtype == NBK_F4) k_cross_power<float><<<g, 256, 0, s>>>((const float *)c1, (const float *)c2, (float *)out, n_complex, (float)scale, clear_first);
+    else k_cross_power<double><<<g, 256, 0, s>>>((const double *)c1, (const double *)c2, (double *)out, n_complex, scale, clear_first);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 extern "C" int nbk_fill(void *x, int dtype, int64_t n, double value, void *stream) {

@@ -107,3 +107,34 @@ def test_dk0_unique_bins(cuda):
     p = r.power
     np.testing.assert_allclose(p.coords['k'], p['k'], rtol=1e-6)
     assert np.all(p['modes'] > 0)
+
+
+@pytest.mark.parametrize("mode,poles", [("1d", []), ("2d", [0, 2])])
+def test_fftcorr_vs_oracle(cuda, mode, poles):
+    """FFTCorr (algorithms/fftcorr.py:148-176): xi = c2r(c1 c2* V, zero mode cleared) / V, binned in wrapped separation"""
+    from nbodykit_b200.lab import UniformCatalog, FFTCorr
+    from oracle import convpower_oracle as co
+    N, L = 32, 256.
+    cat = UniformCatalog(nbar=1e-3, BoxSize=L, seed=11)
+    r = FFTCorr(cat, mode=mode, Nmesh=N, Nmu=4, poles=poles)
+    pos, _ = po.uniform_catalog(1e-3, L, 11)
+    real, _ = po.paint_field(pos, N, L, 'cic', dtype='f8')
+    c = po.compensate('CompensateCICShotnoise', po.k_coords(N, L, 'f4', kind='circular'), po.r2c(real))
+    p3d = c * np.conj(c)
+    p3d[0, 0, 0] = 0
+    p3d = p3d * L ** 3
+    xi = po.c2r(p3d, N) / L ** 3
+    dr = L / N
+    redges = np.arange(0., 0.5 * L + dr / 2, dr)
+    Nmu = 1 if mode == "1d" else 4
+    res, pres = po.project_to_basis(xi, co.x_coords(N, L, 'f4'), [redges, np.linspace(0, 1, Nmu + 1)], poles=poles,
+                                    hermitian_symmetric=False)
+    assert np.array_equal(r.corr['modes'], np.squeeze(res[3]))
+    scale = np.nanmax(np.abs(res[2]))
+    np.testing.assert_allclose(np.nan_to_num(r.corr['corr'].real), np.nan_to_num(np.squeeze(res[2]).real), rtol=1e-6,
+                               atol=1e-9 * scale)
+    np.testing.assert_allclose(r.corr['r'], np.squeeze(res[0]), rtol=1e-6, equal_nan=True)
+    if poles:
+        np.testing.assert_allclose(np.nan_to_num(r.poles['corr_2'].real), np.nan_to_num(pres[1][1].real), rtol=1e-6,
+                                   atol=1e-9 * scale)
+    assert r.attrs['N1'] == len(pos)
