@@ -156,10 +156,66 @@ class CatalogMesh(MeshSource):
             mass = w.to(torch.float64) * v.to(torch.float64) if w.dtype != v.dtype else w * v
         return pos, mass, n, W, W2
 
+    def _host_streamed_paint(self):
+        """Host-resident positions with unit weights on one GPU: copy in `paint_chunk_size`-sized pieces on a side
+        stream and scatter each piece (direct REDG path) while the next one is in flight, so the paint hides behind
+        the PCIe transfer instead of following it.  Returns None when the catalogue does not qualify."""
+        pm = self.pm
+        if pm.comm.size != 1:
+            return None
+        pos = self.Position.compute() if isinstance(self.Position, Column) and not isinstance(self.Position, ConstantColumn) else None
+        if pos is None or (isinstance(pos, torch.Tensor) and pos.is_cuda):
+            return None
+        for c in (self.Weight, self.Value):
+            if c is not None and not (isinstance(c, ConstantColumn)):
+                return None
+        if self.Selection is not None and not (isinstance(self.Selection, ConstantColumn) and bool(self.Selection.value)):
+            return None
+        t = pos if isinstance(pos, torch.Tensor) else torch.from_numpy(numpy.ascontiguousarray(pos))
+        if t.dtype not in (torch.float32, torch.float64) or t.ndim != 2 or t.shape[1] != 3 or not t.is_contiguous():
+            return None
+        n = int(t.shape[0])
+        chunk = 4 * int(_global_options['paint_chunk_size'])
+        if n < 2 * chunk:
+            return None
+        resampler = window.methods[self.resampler]
+        w = float(self.Weight.value) if self.Weight is not None else 1.0
+        v = float(self.Value.value) if self.Value is not None else 1.0
+        dev = current_device()
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=dev)
+        reals = [RealField(pm)] + ([RealField(pm)] if self.interlaced else [])
+        for r in reals:
+            r[...] = 0
+        bufs = [torch.empty((chunk, 3), dtype=t.dtype, device=dev) for _ in range(2)]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        for k, lo in enumerate(range(0, n, chunk)):
+            hi = min(n, lo + chunk)
+            b = bufs[k % 2]
+            with torch.cuda.stream(side):
+                side.wait_event(free[k % 2])                 # the scatter that last used this buffer is done
+                b[:hi - lo].copy_(t[lo:hi], non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            main.wait_event(ready)
+            if self.interlaced:
+                pm.paint_interlaced(b[:hi - lo], None, resampler, reals[0], reals[1], method='direct')
+            else:
+                pm.paint(b[:hi - lo], mass=1.0, resampler=resampler, hold=True, out=reals[0], method='direct')
+            free[k % 2].record(main)
+        if w * v != 1.0:
+            for r in reals:
+                r *= (w * v)
+        painted = tuple(reals) if self.interlaced else reals[0]
+        return painted, n, w * n, w * w * n
+
     def _paint_raw(self):
         """un-normalised paint: returns (real | (real1, real2) if interlaced, N, W, W2)"""
         pm = self.pm
         resampler = window.methods[self.resampler]
+        streamed = self._host_streamed_paint()
+        if streamed is not None:
+            return streamed
         with stage("H:columns"):
             pos, mass, Nlocal, Wlocal, W2local = self._device_columns()
         smoothing = (1.0 if self.interlaced else 0.5) * resampler.support

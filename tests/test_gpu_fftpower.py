@@ -165,3 +165,26 @@ def test_reference_assertion_tsc_interlacing(cuda):
     mesh = source.to_mesh(resampler='tsc', Nmesh=64, interlaced=True, compensated=True)
     r = FFTPower(mesh, mode='1d', kmin=0.02)
     np.testing.assert_allclose(r.power['power'][5:].real, 1. / 3e-2, rtol=1e-1)
+
+
+def test_host_resident_streamed_paint_equals_device_resident(cuda):
+    """host columns are staged in paint_chunk_size pieces overlapped with the scatter (source/mesh/tests/
+    test_catalogmesh.py:47-60: the result must not depend on the chunk size)"""
+    import torch
+    from nbodykit_b200 import set_options
+    from nbodykit_b200.lab import ArrayCatalog
+    rng = np.random.RandomState(2)
+    pos = rng.uniform(0, 100., size=(500000, 3)).astype('f4')
+    dev = ArrayCatalog({'Position': torch.from_numpy(pos).cuda()}, BoxSize=100.)
+    want = dev.to_mesh(Nmesh=32, resampler='tsc', dtype='f8').compute(mode='real').numpy()
+    for chunk in (50000, 33333):
+        with set_options(paint_chunk_size=chunk):
+            host = ArrayCatalog({'Position': pos}, BoxSize=100.)
+            got = host.to_mesh(Nmesh=32, resampler='tsc', dtype='f8').compute(mode='real')
+            assert got.attrs['N'] == len(pos)
+            np.testing.assert_allclose(got.numpy(), want, rtol=0, atol=1e-7 * want.max())
+            pinned = torch.from_numpy(pos).pin_memory()
+            got2 = ArrayCatalog({'Position': pinned}, BoxSize=100.).to_mesh(Nmesh=32, resampler='tsc', interlaced=True,
+                                                                            dtype='f8').compute(mode='real')
+    want_i = dev.to_mesh(Nmesh=32, resampler='tsc', interlaced=True, dtype='f8').compute(mode='real').numpy()
+    np.testing.assert_allclose(got2.numpy(), want_i, rtol=0, atol=1e-7 * want_i.max())
