@@ -15,6 +15,8 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <stdlib.h>
+#include <string.h>
 
 template <typename T> struct C2;
 template <> struct C2<float> { typedef float2 type; };
@@ -285,6 +287,140 @@ k_fft_lines_scatter(const typename C2<T>::type *__restrict__ src, PeerPtrs<typen
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-I/O line pass (N >= 64).  The first radix-8 stage loads its 8 inputs per butterfly straight from global
+// memory (rows q + k*N/8, B adjacent columns per row = one 128-byte run per quarter warp), and the last stage
+// writes its outputs straight to their digit-reversed frequency rows; shared memory only carries the exchanges
+// between stages (4 instead of 8 shared accesses per element at N = 512, and no copy loops).  One tile buffer per
+// CTA, so 2-3 CTAs share an SM and one CTA's global phase overlaps another's butterflies.
+// PEER: the store goes to the NVLink-mapped transposed field of rank k / n_per (see k_fft_lines_scatter).
+// ---------------------------------------------------------------------------------------------
+template <typename C>
+__device__ __forceinline__ void radix8(C (&a)[8]) {   // in: a[j] = x_j ; out: a[m] = X_m (8-point forward DFT)
+    C b0 = cadd(a[0], a[4]), b1 = cadd(a[1], a[5]), b2 = cadd(a[2], a[6]), b3 = cadd(a[3], a[7]);
+    C b4 = csub(a[0], a[4]), d5 = csub(a[1], a[5]), d6 = csub(a[2], a[6]), d7 = csub(a[3], a[7]);
+    const auto h = Sqrt1_2<C>::v();
+    C b5 = C{(d5.x + d5.y) * h, (d5.y - d5.x) * h};
+    C b6 = cmuli_neg(d6);
+    C b7 = C{(d7.y - d7.x) * h, -(d7.x + d7.y) * h};
+    dft4(b0, b1, b2, b3);      // -> X0, X2, X4, X6
+    dft4(b4, b5, b6, b7);      // -> X1, X3, X5, X7
+    a[0] = b0; a[1] = b4; a[2] = b1; a[3] = b5; a[4] = b2; a[5] = b6; a[6] = b3; a[7] = b7;
+}
+
+__device__ __forceinline__ int rev8(int t, int ndig) {   // reverse the ndig base-8 digits of t
+    int r = 0;
+    for (int i = 0; i < ndig; i++) { r = (r << 3) | (t & 7); t >>= 3; }
+    return r;
+}
+
+template <typename T, int B, bool PEER>
+__global__ void __launch_bounds__(256, 2)
+k_fft_lines_rg(const typename C2<T>::type *src, typename C2<T>::type *dst, PeerPtrs<typename C2<T>::type> peers,
+               const typename C2<T>::type *__restrict__ tw, int N, int log2n, int64_t line_stride, int64_t n_inner,
+               int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride, int n_per, int64_t d_total,
+               int64_t outer_start, int inverse, T scale) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    constexpr int pitch = B + 1;
+    const int T_ = blockDim.x;
+    tw = stage_twiddles<C>(sm + (size_t)N * pitch, tw, N);
+    const int n8 = log2n / 3, rrem = log2n - 3 * n8;
+    const int Q1 = N >> 3;
+    const T sgn = inverse ? (T)-1 : (T)1;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t outer = tile / tiles_inner;
+        int64_t inner0 = (tile - outer * tiles_inner) * B;
+        const C *ibase = src + outer * outer_stride + inner0;
+        int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+        // ---- first stage: global -> registers -> shared
+        for (int w = threadIdx.x; w < Q1 * B; w += T_) {
+            int b = w % B, q = w / B;
+            C a[8];
+            if (b < bvalid) {
+                const C *g = ibase + (int64_t)q * line_stride + b;
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = g[(int64_t)j * Q1 * line_stride];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = C{0, 0};
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) a[j].y *= sgn;
+            radix8(a);
+            C *o = sm + q * pitch + b;
+            o[0] = a[0];
+#pragma unroll
+            for (int m = 1; m < 8; m++) o[m * Q1 * pitch] = cmul(a[m], tw[m * q]);
+        }
+        __syncthreads();
+        // ---- middle stages, in place in shared memory
+        {
+            const int last8 = rrem ? n8 : n8 - 1;    // radix-8 stages [1, last8) are exchanged through shared memory
+            int Ns = Q1, lq = log2n - 3;
+            for (int s = 1; s < last8; s++) {
+                const int Q = Ns >> 3;
+                lq -= 3;
+                const int tws = N / Ns;
+                for (int w = threadIdx.x; w < Q1 * B; w += T_) {
+                    int b = w % B, t = w / B;
+                    int blk = t >> lq, q = t & (Q - 1);
+                    C *p = sm + (blk * Ns + q) * pitch + b;
+                    C a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) a[j] = p[j * Q * pitch];
+                    radix8(a);
+                    int ti = q * tws;
+                    p[0] = a[0];
+#pragma unroll
+                    for (int m = 1; m < 8; m++) p[m * Q * pitch] = cmul(a[m], tw[m * ti]);
+                }
+                __syncthreads();
+                Ns = Q;
+            }
+        }
+        // ---- last stage: shared -> registers -> global (frequency rows)
+        const int R = rrem == 0 ? 8 : (rrem == 2 ? 4 : 2);
+        const int NR = N / R;                 // butterflies per line, and the frequency step between its outputs
+        const int ndig = rrem == 0 ? n8 - 1 : n8;
+        for (int w = threadIdx.x; w < NR * B; w += T_) {
+            int b = w % B, t = w / B;
+            const C *p = sm + (t * R) * pitch + b;
+            C a[8];
+            if (R == 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = p[j * pitch];
+                radix8(a);
+            } else if (R == 4) {
+                a[0] = p[0]; a[1] = p[pitch]; a[2] = p[2 * pitch]; a[3] = p[3 * pitch];
+                dft4(a[0], a[1], a[2], a[3]);
+            } else {
+                C x0 = p[0], x1 = p[pitch];
+                a[0] = cadd(x0, x1);
+                a[1] = csub(x0, x1);
+            }
+            if (b < bvalid) {
+                int k0 = rev8(t, ndig);
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    if (m < R) {
+                        int k = k0 + m * NR;
+                        C v = C{a[m].x * scale, a[m].y * sgn * scale};
+                        if (PEER) {
+                            int pr = k / n_per, kl = k - pr * n_per;
+                            peers.p[pr][((int64_t)kl * d_total + outer_start + outer) * n_inner + inner0 + b] = v;
+                        } else {
+                            dst[outer * outer_stride + inner0 + (int64_t)k * line_stride + b] = v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();      // the next tile's first stage overwrites the buffer
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // z pass forward: real rows [rows][Nz] -> complex rows [rows][Nz/2+1]
 // packed trick: z[n] = x[2n] + i x[2n+1], Z = FFT_M(z), M = Nz/2,
 //   X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k]) ],  k = 0..M  (Z[M] := Z[0])
@@ -437,6 +573,61 @@ static int pick_B(int N, int csize, int64_t n_inner) {
     return B;
 }
 
+static bool use_reg_lines(int N) {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("NBK_FFT_LINES");
+        mode = (e && strcmp(e, "smem") == 0) ? 0 : 1;
+    }
+    return mode == 1 && N >= 64;
+}
+
+// register-I/O line pass; peer_host != nullptr selects the peer-memory scatter store
+template <typename T>
+static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, int P, int N, int64_t line_stride,
+                           int64_t n_inner, int64_t n_outer, int64_t outer_stride, int64_t outer_start, int inverse,
+                           double scale, cudaStream_t s) {
+    typedef typename C2<T>::type C;
+    int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
+    void *tw;
+    int rc = get_twiddle(N, dtype, s, &tw);
+    if (rc) return rc;
+    int B = 128 / (int)sizeof(C);
+    while (B > 1 && ((size_t)N * (B + 2) * sizeof(C) > 220 * 1024 || B / 2 >= n_inner)) B >>= 1;
+    size_t smem = (size_t)N * (B + 2) * sizeof(C);
+    NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: N=%d does not fit in shared memory", N);
+    int64_t tiles_inner = (n_inner + B - 1) / B;
+    int64_t n_tiles = tiles_inner * n_outer;
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+    const int nthreads = per_sm == 1 ? 512 : 256;
+    PeerPtrs<C> peers;
+    for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
+    const int n_per = peer_host ? N / P : N;
+    const int64_t d_total = peer_host ? n_outer * P : 0;
+#define LAUNCH_RG(BB)                                                                                              \
+    case BB:                                                                                                       \
+        if (peer_host) {                                                                                           \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rg<T, BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_lines_rg<T, BB, true><<<(int)g, nthreads, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
+                ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
+        } else {                                                                                                   \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rg<T, BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_lines_rg<T, BB, false><<<(int)g, nthreads, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
+                ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
+        }                                                                                                          \
+        break;
+    switch (B) {
+        LAUNCH_RG(1) LAUNCH_RG(2) LAUNCH_RG(4) LAUNCH_RG(8) LAUNCH_RG(16)
+        default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
+    }
+#undef LAUNCH_RG
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
 template <typename T>
 static int launch_lines(const void *data, void *dst, int N, int64_t line_stride, int64_t n_inner, int64_t n_outer,
                         int64_t outer_stride, int inverse, double scale, cudaStream_t s) {
@@ -449,6 +640,8 @@ static int launch_lines(const void *data, void *dst, int N, int64_t line_stride,
         }
         return NBK_OK;
     }
+    if (use_reg_lines(N))
+        return launch_lines_rg<T>(data, dst, nullptr, 1, N, line_stride, n_inner, n_outer, outer_stride, 0, inverse, scale, s);
     void *tw;
     int rc = get_twiddle(N, dtype, s, &tw);
     if (rc) return rc;
@@ -509,6 +702,9 @@ extern "C" int nbk_fft_lines_oop(const void *src, void *dst, int dtype, int64_t 
 template <typename T>
 static int launch_lines_scatter(const void *src, void *const *peer_host, int N, int64_t n_inner, int64_t n_outer,
                                 int64_t outer_start, int P, int inverse, double scale, cudaStream_t s) {
+    if (use_reg_lines(N))
+        return launch_lines_rg<T>(src, nullptr, peer_host, P, N, n_inner, n_inner, n_outer, (int64_t)N * n_inner, outer_start,
+                                  inverse, scale, s);
     typedef typename C2<T>::type C;
     int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
     void *tw;

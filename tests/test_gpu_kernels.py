@@ -110,7 +110,8 @@ def test_paint_interlaced_pair(cuda):
     np.testing.assert_allclose(r2.numpy(), w2, rtol=0, atol=2e-5 * w2.max())
 
 
-@pytest.mark.parametrize("N", [[8, 8, 8], [16, 32, 64], [64, 16, 4], [128, 128, 128], [2, 4, 8]])
+@pytest.mark.parametrize("N", [[8, 8, 8], [16, 32, 64], [64, 16, 4], [128, 128, 128], [2, 4, 8], [256, 64, 32], [512, 128, 16],
+                               [1024, 8, 16], [2048, 4, 8]])
 @pytest.mark.parametrize("dtype,tol", [("f8", 1e-13), ("f4", 2e-6)])
 def test_r2c_c2r(cuda, N, dtype, tol):
     from nbodykit_b200.pmesh.pm import RealField
@@ -454,14 +455,15 @@ def test_route_kernels_vs_numpy(cuda):
             start += cnt[r]
 
 
+@pytest.mark.parametrize("shape", [(16, 32, 8), (64, 128, 8), (128, 64, 36)])
 @pytest.mark.parametrize("dtype", ["f8", "f4"])
-def test_fft_scatter_transpose_two_virtual_ranks(cuda, dtype):
+def test_fft_scatter_transpose_two_virtual_ranks(cuda, dtype, shape):
     """nbk_fft_z_forward + nbk_fft_lines_scatter + nbk_fft_lines_oop == r2c, with the slab transpose done by the y
     pass writing into 'peer' buffers (two virtual ranks on one GPU: the peers are two buffers of this device)"""
     import ctypes
     import torch
     from nbodykit_b200 import _lib
-    Nx, Ny, Nz, P = 16, 32, 8, 2
+    (Nx, Ny, Nz), P = shape, 2
     Nzc = Nz // 2 + 1
     rng = np.random.RandomState(17)
     real = rng.standard_normal((Nx, Ny, Nz)).astype(dtype)

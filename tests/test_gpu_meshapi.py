@@ -116,7 +116,8 @@ def test_fftcorr_vs_oracle(cuda, mode, poles):
     from oracle import convpower_oracle as co
     N, L = 32, 256.
     cat = UniformCatalog(nbar=1e-3, BoxSize=L, seed=11)
-    r = FFTCorr(cat, mode=mode, Nmesh=N, Nmu=4, poles=poles)
+    mesh = cat.to_mesh(Nmesh=N, dtype='f8', resampler='cic', compensated=True)
+    r = FFTCorr(mesh, mode=mode, Nmu=4, poles=poles)
     pos, _ = po.uniform_catalog(1e-3, L, 11)
     real, _ = po.paint_field(pos, N, L, 'cic', dtype='f8')
     c = po.compensate('CompensateCICShotnoise', po.k_coords(N, L, 'f4', kind='circular'), po.r2c(real))
