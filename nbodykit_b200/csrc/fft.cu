@@ -313,8 +313,8 @@ __device__ __forceinline__ int rev8(int t, int ndig) {   // reverse the ndig bas
     return r;
 }
 
-template <typename T, int B, bool PEER>
-__global__ void __launch_bounds__(256, 2)
+template <typename T, int B, bool PEER, int NT>
+__global__ void __launch_bounds__(NT, 512 / NT)
 k_fft_lines_rg(const typename C2<T>::type *src, typename C2<T>::type *dst, PeerPtrs<typename C2<T>::type> peers,
                const typename C2<T>::type *__restrict__ tw, int N, int log2n, int64_t line_stride, int64_t n_inner,
                int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride, int n_per, int64_t d_total,
@@ -469,6 +469,140 @@ k_fft_z_r2c(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
     }
 }
 
+// Last DIF stage of B side-by-side length-M lines in shared memory, leaving the spectrum in NATURAL order: every thread
+// first pulls all of its butterflies into registers (V values: M * B <= 256 V; V = 16 for c8, 8 for c16 keeps them in 32 registers), then the CTA
+// synchronises, then the outputs are stored at their frequency rows.
+template <typename C, int B, int R, int V>
+__device__ __forceinline__ void last_stage_natural(C *sm, int M, int ndig) {
+    constexpr int pitch = B + 1;
+    constexpr int NB = V / R;
+    const int NR = M / R;
+    C a[NB][R];
+#pragma unroll
+    for (int it = 0; it < NB; it++) {
+        int w = threadIdx.x + it * 256;
+        if (w < NR * B) {
+            int b = w % B, t = w / B;
+            const C *p = sm + (t * R) * pitch + b;
+#pragma unroll
+            for (int j = 0; j < R; j++) a[it][j] = p[j * pitch];
+            if constexpr (R == 8) {
+                radix8(a[it]);
+            } else if constexpr (R == 4) {
+                dft4(a[it][0], a[it][1], a[it][2], a[it][3]);
+            } else {
+                C x0 = a[it][0], x1 = a[it][1];
+                a[it][0] = cadd(x0, x1);
+                a[it][1] = csub(x0, x1);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < NB; it++) {
+        int w = threadIdx.x + it * 256;
+        if (w < NR * B) {
+            int b = w % B, t = w / B;
+            int k0 = rev8(t, ndig);
+#pragma unroll
+            for (int m = 0; m < R; m++) sm[(k0 + m * NR) * pitch + b] = a[it][m];
+        }
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// z pass forward, register-I/O variant (Nz >= 128).  Same packed-pair algorithm as k_fft_z_r2c; the first radix-8
+// stage reads the real row straight from global memory (lanes along the row: 512-byte runs), the last stage leaves
+// Z in NATURAL frequency order in shared memory (registers carry the permutation across one barrier), so the
+// Hermitian split reads Z[k] and Z[M-k] with unit-stride lanes and no digit-reversal arithmetic.  Shared: tile
+// [M][B+1] | W_N table [N] (W_M^j = W_N^2j serves the butterflies, W_N^k the split).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int B>
+__global__ void __launch_bounds__(256, 2)
+k_fft_z_r2c_rg(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
+               const typename C2<T>::type *__restrict__ twN_g, int Nz, int log2m, int64_t rows, T scale) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    const int M = Nz >> 1;
+    const int Nzc = M + 1;
+    constexpr int pitch = B + 1;
+    const int T_ = blockDim.x;
+    const C *tw = stage_twiddles<C>(sm + (size_t)M * pitch, twN_g, Nz);    // tw[2j] = W_M^j
+    const int n8 = log2m / 3, rrem = log2m - 3 * n8;
+    const int Q1 = M >> 3, lq1 = log2m - 3;
+    const int64_t n_tiles = (rows + B - 1) / B;
+    const T h = (T)0.5 * scale;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * B;
+        const int bvalid = (int)((rows - row0) < B ? (rows - row0) : B);
+        const C *src = reinterpret_cast<const C *>(real + row0 * Nz);    // rows of M packed pairs
+        // ---- first stage: global -> registers -> shared; lanes along the row
+        for (int w = threadIdx.x; w < Q1 * B; w += T_) {
+            int q = w & (Q1 - 1), b = w >> lq1;
+            C a[8];
+            if (b < bvalid) {
+                const C *g = src + (int64_t)b * M + q;
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = g[j * Q1];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = C{0, 0};
+            }
+            radix8(a);
+            C *o = sm + q * pitch + b;
+            o[0] = a[0];
+#pragma unroll
+            for (int m = 1; m < 8; m++) o[m * Q1 * pitch] = cmul(a[m], tw[2 * m * q]);
+        }
+        __syncthreads();
+        // ---- middle stages, in place
+        {
+            const int last8 = rrem ? n8 : n8 - 1;
+            int Ns = Q1, lq = lq1;
+            for (int s = 1; s < last8; s++) {
+                const int Q = Ns >> 3;
+                lq -= 3;
+                const int tws = 2 * (M / Ns);
+                for (int w = threadIdx.x; w < Q1 * B; w += T_) {
+                    int b = w % B, t = w / B;
+                    int blk = t >> lq, q = t & (Q - 1);
+                    C *p = sm + (blk * Ns + q) * pitch + b;
+                    C a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) a[j] = p[j * Q * pitch];
+                    radix8(a);
+                    int ti = q * tws;
+                    p[0] = a[0];
+#pragma unroll
+                    for (int m = 1; m < 8; m++) p[m * Q * pitch] = cmul(a[m], tw[m * ti]);
+                }
+                __syncthreads();
+                Ns = Q;
+            }
+        }
+        // ---- last stage: all M*B/256 <= V values of a thread go to registers, barrier, natural-order write back
+        constexpr int V = sizeof(T) == 4 ? 16 : 8;
+        if (rrem == 0) last_stage_natural<C, B, 8, V>(sm, M, n8 - 1);
+        else if (rrem == 2) last_stage_natural<C, B, 4, V>(sm, M, n8);
+        else last_stage_natural<C, B, 2, V>(sm, M, n8);
+        // ---- Hermitian split, one warp per row, lanes along k
+        C *dst = cplx + row0 * Nzc;
+        for (int b = threadIdx.x >> 5; b < bvalid; b += (T_ >> 5)) {
+            C *drow = dst + (int64_t)b * Nzc;
+            for (int k = threadIdx.x & 31; k < Nzc; k += 32) {
+                C zk = sm[(k & (M - 1)) * pitch + b];
+                C zm = cconj(sm[((M - k) & (M - 1)) * pitch + b]);
+                C e = cadd(zk, zm), o = csub(zk, zm);
+                C wo = cmul(tw[k], o);
+                drow[k] = C{(e.x + wo.y) * h, (e.y - wo.x) * h};
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // z pass backward: complex rows [rows][Nz/2+1] -> real rows [rows][Nz], unnormalised
 //   E = (X[k] + conj X[M-k])/2, O = conj(W_N^k) (X[k] - conj X[M-k])/2, Z[k] = E + i O, k < M
 //   x[2n] + i x[2n+1] = 2 * sum_k Z[k] e^{+2 pi i k n / M} = 2 * conj(FFT_M(conj Z))[n]
@@ -602,26 +736,33 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
     int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
-    const int nthreads = per_sm == 1 ? 512 : 256;
+    const int nthreads = (per_sm == 1 && B >= 4) ? 512 : 256;
     PeerPtrs<C> peers;
     for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
     const int n_per = peer_host ? N / P : N;
     const int64_t d_total = peer_host ? n_outer * P : 0;
-#define LAUNCH_RG(BB)                                                                                              \
+#define LAUNCH_RG(BB, NTT)                                                                                            \
     case BB:                                                                                                       \
         if (peer_host) {                                                                                           \
-            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rg<T, BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_fft_lines_rg<T, BB, true><<<(int)g, nthreads, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rg<T, BB, true, NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_lines_rg<T, BB, true, NTT><<<(int)g, NTT, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
                 ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
         } else {                                                                                                   \
-            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rg<T, BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-            k_fft_lines_rg<T, BB, false><<<(int)g, nthreads, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rg<T, BB, false, NTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_lines_rg<T, BB, false, NTT><<<(int)g, NTT, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
                 ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
         }                                                                                                          \
         break;
-    switch (B) {
-        LAUNCH_RG(1) LAUNCH_RG(2) LAUNCH_RG(4) LAUNCH_RG(8) LAUNCH_RG(16)
-        default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
+    if (nthreads == 512) {
+        switch (B) {
+            LAUNCH_RG(4, 512) LAUNCH_RG(8, 512) LAUNCH_RG(16, 512)
+            default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
+        }
+    } else {
+        switch (B) {
+            LAUNCH_RG(1, 256) LAUNCH_RG(2, 256) LAUNCH_RG(4, 256) LAUNCH_RG(8, 256) LAUNCH_RG(16, 256)
+            default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
+        }
     }
 #undef LAUNCH_RG
     NBK_LAUNCHED();
@@ -760,6 +901,31 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
     if (rc) return rc;
     rc = get_twiddle(Nz, dtype, s, &twN);
     if (rc) return rc;
+    if (forward && M >= 64 && use_reg_lines(M)) {
+        // register-I/O variant: 256 threads hold the whole tile across the last stage (M * B <= 256 V)
+        const int V = sizeof(T) == 4 ? 16 : 8;
+        int B = 16;
+        while (B > 1 && (M * B > 256 * V || B / 2 >= rows)) B >>= 1;
+        size_t smem = ((size_t)M * (B + 1) + Nz) * sizeof(C);
+        NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);
+        int64_t n_tiles = (rows + B - 1) / B;
+        int per_sm = (int)((227 * 1024) / (smem + 1024));
+        if (per_sm < 1) per_sm = 1;
+        if (per_sm > 4) per_sm = 4;
+        int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+#define LAUNCH_ZRG(BB)                                                                                            \
+    case BB:                                                                                                      \
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_z_r2c_rg<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_fft_z_r2c_rg<T, BB><<<(int)g, 256, smem, s>>>((const T *)in, (C *)out, (const C *)twN, Nz, ilog2(M), rows, (T)scale); \
+        break;
+        switch (B) {
+            LAUNCH_ZRG(1) LAUNCH_ZRG(2) LAUNCH_ZRG(4) LAUNCH_ZRG(8) LAUNCH_ZRG(16)
+            default: nbk_set_error("fft z pass: internal tile width %d", B); return NBK_ERR_ARG;
+        }
+#undef LAUNCH_ZRG
+        NBK_LAUNCHED();
+        return NBK_OK;
+    }
     int B = pick_B(M, (int)sizeof(C), rows);
     size_t smem = ((size_t)M * (B + 2) + 8) * sizeof(C);     // tile [M][B+1] (+8 skew) + twiddle table [M]
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);

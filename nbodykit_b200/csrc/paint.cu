@@ -244,6 +244,7 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 // A tile owns the particles whose LEFTMOST stencil cell lies in it, so the halo is one-sided.
 // =============================================================================================
 #define TILE 16
+#define NBK_BLK_SMEM (200 * 1024)   // largest shared-memory tile histogram (CTA-local bucketing)
 
 // tile-ordered particle record: one aligned vector per particle (x, y, z, pad)
 template <typename PT> struct Rec;
@@ -425,6 +426,93 @@ k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t 
             R4 r;
             r.x = pos[3 * i]; r.y = pos[3 * i + 1]; r.z = pos[3 * i + 2]; r.w = 0;
             spos[dst] = r;                       // one 16-byte (f4) / 32-byte (f8) store per particle
+            if (mass) smass[dst] = mass[i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-local bucketing (ntiles * 4 B fits in shared memory): CTA c owns the contiguous particle chunk
+// [c*chunk, (c+1)*chunk).  Pass A histograms its chunk in shared memory (native ATOMS.ADD.U32, no global
+// atomics) and stores the histogram as row c of blk[G][ntiles]; pass B turns every column into an exclusive
+// prefix over c and the column totals into tile offsets; pass C reloads row c as shared cursors and scatters the
+// same chunk.  Slot order inside a tile is arbitrary, the fixed-point accumulation makes the mesh independent of it.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool active, bool want_slot) {
+    const int lane = threadIdx.x & 31;
+    int k0 = __shfl_sync(0xffffffffu, key, 0);
+    if (__all_sync(0xffffffffu, active && key == k0)) {      // spatially coherent catalogue: one add per warp
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(&hist[key], 32u);
+        return want_slot ? __shfl_sync(0xffffffffu, base, 0) + lane : 0u;
+    }
+    return active ? atomicAdd(&hist[key], 1u) : 0u;
+}
+
+template <int SUP, typename PT, typename MT>
+__global__ void __launch_bounds__(1024)
+k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
+                 unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
+    extern __shared__ __align__(16) unsigned s_hist[];
+    for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) s_hist[t] = 0;
+    __syncthreads();
+    const FastTile ft = make_fast_tile(tg);
+    const int64_t b = (int64_t)blockIdx.x * chunk;
+    const int64_t e = (b + chunk < n) ? b + chunk : n;
+    float mx = 0.f;
+    for (int64_t i0 = b; i0 < e; i0 += blockDim.x) {
+        int64_t i = i0 + threadIdx.x;
+        bool in = i < e;
+        int t = in ? tile_of<SUP, PT>(pos, i, tg, ft) : -1;
+        if (in) tile_ids[i] = t;
+        smem_claim(s_hist, t, t >= 0, false);
+        if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);
+    }
+    if (mass) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(absmax_bits, __float_as_uint(mx));
+    }
+    __syncthreads();
+    unsigned *row = blk + (size_t)blockIdx.x * tg.ntiles;
+    for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) row[t] = s_hist[t];
+}
+
+// column pass: blk[c][t] <- sum_{c' < c} blk[c'][t];  counts[t] <- column total
+__global__ void __launch_bounds__(256)
+k_tile_colscan(unsigned *__restrict__ blk, unsigned *__restrict__ counts, int ntiles, int G) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    unsigned run = 0;
+    for (int c = 0; c < G; c++) {
+        unsigned v = blk[(size_t)c * ntiles + t];
+        blk[(size_t)c * ntiles + t] = run;
+        run += v;
+    }
+    counts[t] = run;
+}
+
+template <int SUP, typename PT, typename MT>
+__global__ void __launch_bounds__(1024)
+k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, int ntiles,
+                   const unsigned *__restrict__ offsets, const unsigned *__restrict__ blk,
+                   typename Rec<PT>::type *__restrict__ spos, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
+    typedef typename Rec<PT>::type R4;
+    extern __shared__ __align__(16) unsigned s_cur[];
+    const unsigned *row = blk + (size_t)blockIdx.x * ntiles;
+    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) s_cur[t] = offsets[t] + row[t];
+    __syncthreads();
+    const int64_t b = (int64_t)blockIdx.x * chunk;
+    const int64_t e = (b + chunk < n) ? b + chunk : n;
+    for (int64_t i0 = b; i0 < e; i0 += blockDim.x) {
+        int64_t i = i0 + threadIdx.x;
+        bool in = i < e;
+        int t = in ? tile_ids[i] : -1;
+        R4 r;
+        if (in) { r.x = pos[3 * i]; r.y = pos[3 * i + 1]; r.z = pos[3 * i + 2]; r.w = 0; }
+        unsigned dst = smem_claim(s_cur, t, t >= 0, true);
+        if (t >= 0) {
+            spos[dst] = r;
             if (mass) smass[dst] = mass[i];
         }
     }
@@ -647,6 +735,8 @@ extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_
     bytes += 3 * align256(sizeof(unsigned) * (nt + 1));  // counts, offsets, cursor
     bytes += align256((size_t)n * 4 * (pos_dtype == NBK_F4 ? 4 : 8));   // 16/32-byte records
     bytes += align256((size_t)n * sizeof(int));                          // tile id per particle
+    int64_t nh = nt < NBK_BLK_SMEM / 4 ? nt : NBK_BLK_SMEM / 4;
+    bytes += align256(sizeof(unsigned) * (size_t)nh * NBK_SM_COUNT);    // per-CTA tile histograms (CTA-local bucketing)
     if (mass_dtype) bytes += align256((size_t)n * (mass_dtype == NBK_F4 ? 4 : 8));
     return (int64_t)bytes;
 }
@@ -670,15 +760,42 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     R4 *spos = (R4 *)w; w += align256((size_t)n * sizeof(R4));
     int *tile_ids = (int *)w; w += align256((size_t)n * sizeof(int));
     MT *smass = mass ? (MT *)w : nullptr;
-    NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
-    int g = nbk_grid_for(n, 256, 8);
-    k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, counts, absmax, tile_ids);
-    NBK_LAUNCHED();
-    k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
-    NBK_LAUNCHED();
-    k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass,
-                                                  tile_ids);
-    NBK_LAUNCHED();
+    if (mass) w += align256((size_t)n * sizeof(MT));
+    unsigned *blk = (unsigned *)w;
+    static int blk_mode = -1;
+    if (blk_mode < 0) {
+        const char *e = getenv("NBK_PAINT_BUCKET");
+        blk_mode = (e && e[0] == 'g') ? 0 : 1;          // NBK_PAINT_BUCKET=global forces the global-atomic passes
+    }
+    const size_t hist_bytes = sizeof(unsigned) * (size_t)tg.ntiles;
+    const bool use_blk = blk_mode && hist_bytes <= NBK_BLK_SMEM && n >= 4 * (int64_t)tg.ntiles;
+    if (use_blk) {
+        const int G = NBK_SM_COUNT;
+        const int64_t chunk = (n + G - 1) / G;
+        NBK_CUDA(cudaMemsetAsync(work, 0, 256, s));        // header
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, blk, absmax,
+                                                                  tile_ids);
+        NBK_LAUNCHED();
+        k_tile_colscan<<<(tg.ntiles + 255) / 256, 256, 0, s>>>(blk, counts, tg.ntiles, G);
+        NBK_LAUNCHED();
+        k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
+        NBK_LAUNCHED();
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_scatter_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
+        k_tile_scatter_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg.ntiles, offsets,
+                                                                    blk, spos, smass, tile_ids);
+        NBK_LAUNCHED();
+    } else {
+        NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
+        int g = nbk_grid_for(n, 256, 8);
+        k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, counts, absmax, tile_ids);
+        NBK_LAUNCHED();
+        k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
+        NBK_LAUNCHED();
+        k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass,
+                                                      tile_ids);
+        NBK_LAUNCHED();
+    }
     const int RP = (tg.R + 3) & ~3;
     size_t smem = (size_t)2 * tg.R * tg.R * RP * sizeof(unsigned);
     int per_sm = (int)((220 * 1024) / (smem + 2048));

@@ -353,6 +353,19 @@ def test_paint_tiled_clustered_and_empty_tiles(cuda):
     assert abs(got.sum(dtype="f8") - len(pos)) < 1e-2
 
 
+def test_paint_tiled_many_tiles_uses_global_bucketing(cuda):
+    """more tiles than a shared-memory histogram holds (> 51200): the bucketing falls back to global counters;
+    checked against the direct REDG scatter on the same particles"""
+    N, L = [1024, 1024, 256], [1000., 1000., 250.]
+    pos = _particles(3000000, L, "f4")
+    pm = _pm(N, L, "f4")
+    a = pm.paint(pos, resampler="cic", method='tiled')
+    b = pm.paint(pos, resampler="cic", method='direct')
+    d = (a.value - b.value).abs().max().item()
+    assert d <= 2e-5 * b.value.abs().max().item()
+    assert abs(a.csum() - len(pos)) < 2.0 and abs(b.csum() - len(pos)) < 2.0
+
+
 def test_paint_auto_dispatch_matches(cuda):
     """the default dispatch (tiled for dense catalogues, direct otherwise) is transparent"""
     N, L = 32, 50.
