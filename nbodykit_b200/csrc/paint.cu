@@ -246,10 +246,12 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 #define TILE 16
 #define NBK_BLK_SMEM (200 * 1024)   // largest shared-memory tile histogram (CTA-local bucketing)
 
-// tile-ordered particle record: one aligned vector per particle (x, y, z, pad)
-template <typename PT> struct Rec;
-template <> struct Rec<float> { typedef float4 type; };
-template <> struct Rec<double> { typedef double4 type; };
+// Tile-ordered particle record, 16 bytes for every position dtype: the scatter pass evaluates the grid coordinate
+// in the exact f8 arithmetic once and stores, per axis, the fraction of (g + A) as a 32-bit fixed-point number
+// (truncated: the weights move by < 2^-32, below the 2^-31 deposit quantum) plus the leftmost stencil cell
+// relative to its tile (4 bits per axis).  The paint pass needs no floor / wrap / range logic, and the half-cell
+// shifted mesh of an interlaced pair follows exactly from frac + 1/2 (carry -> next cell).
+typedef uint4 TileRec;     // {frac_x, frac_y, frac_z, lx | ly << 8 | lz << 16}
 
 struct TileGeom {
     PaintGeom gm;
@@ -295,6 +297,25 @@ __device__ __noinline__ int tile_of_exact(const PT *__restrict__ pos, int64_t i,
         c[d] = wrap(i0, tg.gm.n[d]);
     }
     return tile_from_cells(c, tg);
+}
+
+// exact leftmost cell + fixed-point fraction of particle i (the arithmetic of Window<SUP>::eval on the unshifted g)
+template <int SUP, typename PT>
+__device__ __forceinline__ bool make_record(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, TileRec &rec) {
+    double g[3];
+    if (!load_grid(pos, i, tg.gm, 0.0, g)) return false;
+    unsigned u[3];
+    int c[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double a = g[d] + (double)WinOff<SUP>::A;
+        double f = floor(a);
+        u[d] = __double2uint_rz((a - f) * 4294967296.0);
+        c[d] = wrap((long long)f + WinOff<SUP>::B, tg.gm.n[d]);
+    }
+    int lx = (slab_local(c[0], tg) + tg.G) & (TILE - 1);
+    rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
+    return true;
 }
 
 // Tile id of particle i.  float32 positions take a float32 fast path: g32 = x*scale differs from the f8 grid
@@ -382,50 +403,66 @@ k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n,
     }
 }
 
-// single-CTA exclusive scan; also clears the cursors and the tile queue head
+// single-CTA exclusive scan (4 counters per thread and round, warp shuffles + one shared hop); also clears the
+// cursors and the tile queue head
 __global__ void __launch_bounds__(1024)
 k_tile_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ offsets, unsigned *__restrict__ cursor,
             unsigned *__restrict__ queue, int ntiles) {
-    __shared__ unsigned part[1024];
-    int per = (ntiles + 1023) / 1024;
-    int b = threadIdx.x * per, e = min(b + per, ntiles);
-    unsigned s = 0;
-    for (int i = b; i < e; i++) s += counts[i];
-    part[threadIdx.x] = s;
-    __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0;
+    __shared__ unsigned warp_tot[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned carry = 0;
+    for (int base = 0; base < ntiles; base += 4096) {
+        const int i = base + threadIdx.x * 4;
+        unsigned v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (i + j < ntiles) ? counts[i + j] : 0u;
+        const unsigned s = v[0] + v[1] + v[2] + v[3];
+        unsigned inc = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
         __syncthreads();
-        part[threadIdx.x] += v;
+        if (wid == 0) {
+            unsigned x = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned n = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += n;
+            }
+            warp_tot[lane] = x;
+        }
+        __syncthreads();
+        unsigned run = carry + (wid ? warp_tot[wid - 1] : 0u) + inc - s;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            if (i + j < ntiles) { offsets[i + j] = run; cursor[i + j] = 0; }
+            run += v[j];
+        }
+        carry += warp_tot[31];
         __syncthreads();
     }
-    unsigned run = part[threadIdx.x] - s;
-    for (int i = b; i < e; i++) {
-        offsets[i] = run;
-        cursor[i] = 0;
-        run += counts[i];
-    }
-    if (threadIdx.x == 1023) offsets[ntiles] = part[1023];
-    if (threadIdx.x == 0) queue[0] = 0;
+    if (threadIdx.x == 0) { offsets[ntiles] = carry; queue[0] = 0; }
 }
 
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(256)
 k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg,
                const unsigned *__restrict__ offsets, unsigned *__restrict__ cursor,
-               typename Rec<PT>::type *__restrict__ spos, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
-    typedef typename Rec<PT>::type R4;
+               TileRec *__restrict__ recs, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
         int t = in ? tile_ids[i] : -1;
+        TileRec r = make_uint4(0, 0, 0, 0);
+        if (t >= 0) make_record<SUP, PT>(pos, i, tg, r);
         unsigned slot = warp_claim(cursor, t, t >= 0);
         if (t >= 0) {
             int64_t dst = (int64_t)offsets[t] + slot;
-            R4 r;
-            r.x = pos[3 * i]; r.y = pos[3 * i + 1]; r.z = pos[3 * i + 2]; r.w = 0;
-            spos[dst] = r;                       // one 16-byte (f4) / 32-byte (f8) store per particle
+            recs[dst] = r;                       // one 16-byte store per particle
             if (mass) smass[dst] = mass[i];
         }
     }
@@ -478,27 +515,33 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
     for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) row[t] = s_hist[t];
 }
 
-// column pass: blk[c][t] <- sum_{c' < c} blk[c'][t];  counts[t] <- column total
-__global__ void __launch_bounds__(256)
+// column pass: blk[c][t] <- sum_{c' < c} blk[c'][t];  counts[t] <- column total.  16 independent loads in flight
+// per thread (the column is a chain of G dependent adds, not of G dependent memory round trips)
+__global__ void __launch_bounds__(128)
 k_tile_colscan(unsigned *__restrict__ blk, unsigned *__restrict__ counts, int ntiles, int G) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= ntiles) return;
     unsigned run = 0;
-    for (int c = 0; c < G; c++) {
-        unsigned v = blk[(size_t)c * ntiles + t];
-        blk[(size_t)c * ntiles + t] = run;
-        run += v;
+    for (int c0 = 0; c0 < G; c0 += 16) {
+        unsigned v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] = (c0 + j < G) ? blk[(size_t)(c0 + j) * ntiles + t] : 0u;
+#pragma unroll
+        for (int j = 0; j < 16; j++) {
+            if (c0 + j < G) blk[(size_t)(c0 + j) * ntiles + t] = run;
+            run += v[j];
+        }
     }
     counts[t] = run;
 }
 
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(1024)
-k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, int ntiles,
+k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
                    const unsigned *__restrict__ offsets, const unsigned *__restrict__ blk,
-                   typename Rec<PT>::type *__restrict__ spos, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
-    typedef typename Rec<PT>::type R4;
+                   TileRec *__restrict__ recs, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
     extern __shared__ __align__(16) unsigned s_cur[];
+    const int ntiles = tg.ntiles;
     const unsigned *row = blk + (size_t)blockIdx.x * ntiles;
     for (int t = threadIdx.x; t < ntiles; t += blockDim.x) s_cur[t] = offsets[t] + row[t];
     __syncthreads();
@@ -508,28 +551,29 @@ k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int6
         int64_t i = i0 + threadIdx.x;
         bool in = i < e;
         int t = in ? tile_ids[i] : -1;
-        R4 r;
-        if (in) { r.x = pos[3 * i]; r.y = pos[3 * i + 1]; r.z = pos[3 * i + 2]; r.w = 0; }
+        TileRec r = make_uint4(0, 0, 0, 0);
+        if (t >= 0) make_record<SUP, PT>(pos, i, tg, r);
         unsigned dst = smem_claim(s_cur, t, t >= 0, true);
         if (t >= 0) {
-            spos[dst] = r;
+            recs[dst] = r;
             if (mass) smass[dst] = mass[i];
         }
     }
 }
 
-// 64-bit fixed-point cell = two adjacent 32-bit limbs {lo, hi}; deposits are native ATOMS.ADD on the low
-// limb, the carry (seen in the returned old value) goes to the high limb.
-__device__ __forceinline__ void fixed_add(unsigned *acc, int cell, long long q) {
+// 64-bit fixed-point cell = two 32-bit limbs kept in SEPARATE arrays lo[NC] | hi[NC] (so the low-limb atomics, which
+// are nearly all of them, spread over all 32 banks).  Deposits are native ATOMS.ADD on the low limb; the carry (seen
+// in the returned old value) goes to the high limb.
+__device__ __forceinline__ void fixed_add(unsigned *lo, unsigned *hi, int cell, long long q) {
     unsigned ql = (unsigned)q, qh = (unsigned)(q >> 32);
-    unsigned old = atomicAdd(&acc[2 * cell], ql);
+    unsigned old = atomicAdd(&lo[cell], ql);
     unsigned h = qh + (unsigned)(old + ql < old);
-    if (h) atomicAdd(&acc[2 * cell + 1], h);
+    if (h) atomicAdd(&hi[cell], h);
 }
 // non-negative deposit: 0 <= q <= 2^31 fits the low limb
-__device__ __forceinline__ void fixed_add_pos(unsigned *acc, int cell, unsigned ql) {
-    unsigned old = atomicAdd(&acc[2 * cell], ql);
-    if (old + ql < old) atomicAdd(&acc[2 * cell + 1], 1u);
+__device__ __forceinline__ void fixed_add_pos(unsigned *lo, unsigned *hi, int cell, unsigned ql) {
+    unsigned old = atomicAdd(&lo[cell], ql);
+    if (old + ql < old) atomicAdd(&hi[cell], 1u);
 }
 
 __device__ __forceinline__ void tma_reduce_add(double *gdst, const void *ssrc, unsigned bytes) {
@@ -543,16 +587,34 @@ __device__ __forceinline__ void tma_reduce_add(float *gdst, const void *ssrc, un
                  :: "l"(gdst), "r"(sa), "r"(bytes) : "memory");
 }
 
+// window weights from the stencil-relative offset d = g - i0 (d in [0,1) CIC, [0.5,1.5) TSC, [1,2) PCS)
+template <int SUP> struct WinD;
+template <> struct WinD<1> { static constexpr double DMIN = 0.0;
+    __device__ static __forceinline__ void eval(double, double *w) { w[0] = 1.0; } };
+template <> struct WinD<2> { static constexpr double DMIN = 0.0;
+    __device__ static __forceinline__ void eval(double d, double *w) { w[0] = 1.0 - d; w[1] = d; } };
+template <> struct WinD<3> { static constexpr double DMIN = 0.5;
+    __device__ static __forceinline__ void eval(double d, double *w) {
+#pragma unroll
+        for (int r = 0; r < 3; r++) w[r] = tsc_kernel(d - (double)r);
+    } };
+template <> struct WinD<4> { static constexpr double DMIN = 1.0;
+    __device__ static __forceinline__ void eval(double d, double *w) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) w[r] = pcs_kernel(d - (double)r);
+    } };
+
 // FLUSH 0: per-cell read-add-store (exclusive cells) / REDG (halo)   1: TMA bulk reduce-add, one row per op
-template <int SUP, typename PT, typename MT, typename FT, bool SHIFTED, int FLUSH>
+template <int SUP, typename MT, typename FT, bool SHIFTED, int FLUSH>
 __global__ void __launch_bounds__(256)
-k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restrict__ smass, TileGeom tg, double shift,
+k_tile_paint(const TileRec *__restrict__ recs, const MT *__restrict__ smass, TileGeom tg,
              const unsigned *__restrict__ offsets, unsigned *__restrict__ queue,
              const unsigned *__restrict__ absmax_bits, FT *__restrict__ mesh) {
     extern __shared__ __align__(16) unsigned s_acc[];
     constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0);   // == tg.R
     constexpr int RP = (R + 3) & ~3;                         // row pitch in cells: rows start 16-byte aligned
-    constexpr int NC = R * R * RP;
+    constexpr int NC = R * R * RP;                           // multiple of 4
+    unsigned *s_lo = s_acc, *s_hi = s_acc + NC;
     __shared__ int s_tile;
     // scale 2^31 / M, M = power of two >= max |mass|
     double M = 1.0;
@@ -564,6 +626,7 @@ k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restri
     }
     const double S = 2147483648.0 / M, invS = M / 2147483648.0;
     constexpr int H = R - TILE;   // cells with a local coordinate < H may also be written by the preceding tile
+    constexpr int PER = (NC + 255) / 256;
     for (;;) {
         if (threadIdx.x == 0) s_tile = (int)atomicAdd(queue, 1u);
         __syncthreads();
@@ -574,37 +637,29 @@ k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restri
         for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
         int tz = t % tg.nt[2], ty = (t / tg.nt[2]) % tg.nt[1], tx = t / (tg.nt[2] * tg.nt[1]);
         int o[3] = {tx * TILE - tg.G, ty * TILE, tz * TILE};   // region origin (x: slab-local)
-        int gox = o[0] + tg.gm.x_start;                         // ... and as a global plane index
-        if (gox < 0) gox += tg.gm.n[0];
         __syncthreads();
         for (unsigned p = b + threadIdx.x; p < e; p += blockDim.x) {
-            double g[3];
-            {
-                typename Rec<PT>::type r = spos[p];
-                g[0] = (double)r.x * tg.gm.scale[0] + shift;   // two roundings (--fmad=false)
-                g[1] = (double)r.y * tg.gm.scale[1] + shift;
-                g[2] = (double)r.z * tg.gm.scale[2] + shift;
-            }
-            if (!(isfinite(g[0]) && isfinite(g[1]) && isfinite(g[2]))) continue;
-            double m = smass ? (double)smass[p] : 1.0;
-            long long i0[3];
+            const TileRec r = recs[p];
+            unsigned u[3] = {r.x, r.y, r.z};
+            int l[3] = {(int)(r.w & 255u), (int)((r.w >> 8) & 255u), (int)((r.w >> 16) & 255u)};
             double w[3][SUP];
-            int c[3];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
-                Window<SUP>::eval(g[d], i0[d], w[d]);
-                c[d] = wrap(i0[d], tg.gm.n[d]);
+                if (SHIFTED) {                       // frac(g + A + 1/2): carry moves the stencil one cell up
+                    unsigned v = u[d] + 0x80000000u;
+                    l[d] += (v < u[d]) ? 1 : 0;
+                    u[d] = v;
+                }
+                WinD<SUP>::eval(WinD<SUP>::DMIN + (double)u[d] * 2.3283064365386963e-10, w[d]);
             }
-            // region-local coordinates of the leftmost stencil cell (0 .. TILE-1, +1 with the half-cell shift)
-            int l0 = c[0] - gox, l1 = c[1] - o[1], l2 = c[2] - o[2];
-            if (l0 < 0) l0 += tg.gm.n[0];
-            if (l1 < 0) l1 += tg.gm.n[1];
-            if (l2 < 0) l2 += tg.gm.n[2];
-            if ((unsigned)l0 + SUP > (unsigned)R || (unsigned)l1 + SUP > (unsigned)R || (unsigned)l2 + SUP > (unsigned)R)
-                continue;   // cannot happen for a consistent sort; guards shared memory
-            const int base0 = (l0 * R + l1) * RP + l2;
+            const int base0 = (l[0] * R + l[1]) * RP + l[2];
+            const double m = smass ? (double)smass[p] : 1.0;
+            const double mS = m * S;
+            double wz[SUP];
+#pragma unroll
+            for (int rz = 0; rz < SUP; rz++) wz[rz] = w[2][rz] * mS;
             if (m >= 0.0) {
-                // all window weights are >= 0: deposits fit the low limb (the common case; one ATOMS each)
+                // all deposits are in [0, 2^31]: round-to-nearest integer = low word of fma(wxy, wz, 2^52)
 #pragma unroll
                 for (int rx = 0; rx < SUP; rx++)
 #pragma unroll
@@ -612,8 +667,8 @@ k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restri
                         double wxy = w[0][rx] * w[1][ry];
 #pragma unroll
                         for (int rz = 0; rz < SUP; rz++) {
-                            double wt = wxy * w[2][rz] * m;
-                            fixed_add_pos(s_acc, base0 + (rx * R + ry) * RP + rz, __double2uint_rn(wt * S));
+                            unsigned q = (unsigned)__double2loint(__fma_rn(wxy, wz[rz], 4503599627370496.0));
+                            fixed_add_pos(s_lo, s_hi, base0 + (rx * R + ry) * RP + rz, q);
                         }
                     }
             } else {
@@ -623,39 +678,30 @@ k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restri
                     for (int ry = 0; ry < SUP; ry++) {
                         double wxy = w[0][rx] * w[1][ry];
 #pragma unroll
-                        for (int rz = 0; rz < SUP; rz++) {
-                            double wt = wxy * w[2][rz] * m;
-                            fixed_add(s_acc, base0 + (rx * R + ry) * RP + rz, __double2ll_rn(wt * S));
-                        }
+                        for (int rz = 0; rz < SUP; rz++)
+                            fixed_add(s_lo, s_hi, base0 + (rx * R + ry) * RP + rz, __double2ll_rn(wxy * wz[rz]));
                     }
             }
         }
         __syncthreads();
         if (FLUSH == 1) {
-            // ---- convert the region to mesh dtype in place, then one TMA bulk reduce-add per z row
-            constexpr int PER = (NC + 255) / 256;
-            if (sizeof(FT) == 8) {
-                for (int i = threadIdx.x; i < NC; i += blockDim.x) {
-                    unsigned l = s_acc[2 * i], h = s_acc[2 * i + 1];
-                    reinterpret_cast<double *>(s_acc)[i] = (double)(long long)(((unsigned long long)h << 32) | l) * invS;
-                }
-            } else {
-                float v[PER];
+            // ---- convert the region to mesh dtype (through registers: the values overlay the limb arrays), then one
+            // TMA bulk reduce-add per z row
+            FT v[PER];
 #pragma unroll
-                for (int k = 0; k < PER; k++) {
-                    int i = threadIdx.x + k * 256;
-                    v[k] = 0.f;
-                    if (i < NC) {
-                        unsigned l = s_acc[2 * i], h = s_acc[2 * i + 1];
-                        v[k] = (float)((double)(long long)(((unsigned long long)h << 32) | l) * invS);
-                    }
+            for (int k = 0; k < PER; k++) {
+                int i = threadIdx.x + k * 256;
+                v[k] = (FT)0;
+                if (i < NC) {
+                    unsigned lo = s_lo[i], hi = s_hi[i];
+                    v[k] = (FT)((double)(long long)(((unsigned long long)hi << 32) | lo) * invS);
                 }
-                __syncthreads();
+            }
+            __syncthreads();
 #pragma unroll
-                for (int k = 0; k < PER; k++) {
-                    int i = threadIdx.x + k * 256;
-                    if (i < NC) reinterpret_cast<float *>(s_acc)[i] = v[k];
-                }
+            for (int k = 0; k < PER; k++) {
+                int i = threadIdx.x + k * 256;
+                if (i < NC) reinterpret_cast<FT *>(s_acc)[i] = v[k];
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
@@ -678,8 +724,8 @@ k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restri
         } else {
             // ---- per-cell flush: lanes run along z
             for (int i = threadIdx.x; i < NC; i += blockDim.x) {
-                unsigned l = s_acc[2 * i], h = s_acc[2 * i + 1];
-                if ((l | h) == 0u) continue;
+                unsigned lo = s_lo[i], hi = s_hi[i];
+                if ((lo | hi) == 0u) continue;
                 int cz = i % RP, cy = (i / RP) % R, cx = i / (RP * R);
                 int gx = o[0] + cx + tg.gm.x_start;
                 if (gx < 0) gx += tg.gm.n[0];
@@ -688,11 +734,11 @@ k_tile_paint(const typename Rec<PT>::type *__restrict__ spos, const MT *__restri
                 if (ix < 0 || ix >= tg.gm.x_n) continue;
                 int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
                 int iz = o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
-                double v = (double)(long long)(((unsigned long long)h << 32) | l) * invS;
+                double val = (double)(long long)(((unsigned long long)hi << 32) | lo) * invS;
                 FT *dst = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
                 bool exclusive = cx >= H && cx < TILE && cy >= H && cy < TILE && cz >= H && cz < TILE;
-                if (exclusive) *dst = (FT)((double)*dst + v);
-                else atomicAdd(dst, (FT)v);
+                if (exclusive) *dst = (FT)((double)*dst + val);
+                else atomicAdd(dst, (FT)val);
             }
         }
         __syncthreads();
@@ -733,7 +779,8 @@ extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_
     int64_t nt = ((x_n + G + TILE - 1) / TILE) * ((nmesh[1] + TILE - 1) / TILE) * ((nmesh[2] + TILE - 1) / TILE);
     size_t bytes = 256;                                  // header: queue, absmax
     bytes += 3 * align256(sizeof(unsigned) * (nt + 1));  // counts, offsets, cursor
-    bytes += align256((size_t)n * 4 * (pos_dtype == NBK_F4 ? 4 : 8));   // 16/32-byte records
+    (void)pos_dtype;
+    bytes += align256((size_t)n * sizeof(TileRec));                      // 16-byte records
     bytes += align256((size_t)n * sizeof(int));                          // tile id per particle
     int64_t nh = nt < NBK_BLK_SMEM / 4 ? nt : NBK_BLK_SMEM / 4;
     bytes += align256(sizeof(unsigned) * (size_t)nh * NBK_SM_COUNT);    // per-CTA tile histograms (CTA-local bucketing)
@@ -756,8 +803,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     unsigned *counts = (unsigned *)w; w += tb;
     unsigned *offsets = (unsigned *)w; w += tb;
     unsigned *cursor = (unsigned *)w; w += tb;
-    typedef typename Rec<PT>::type R4;
-    R4 *spos = (R4 *)w; w += align256((size_t)n * sizeof(R4));
+    TileRec *spos = (TileRec *)w; w += align256((size_t)n * sizeof(TileRec));
     int *tile_ids = (int *)w; w += align256((size_t)n * sizeof(int));
     MT *smass = mass ? (MT *)w : nullptr;
     if (mass) w += align256((size_t)n * sizeof(MT));
@@ -777,12 +823,12 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, blk, absmax,
                                                                   tile_ids);
         NBK_LAUNCHED();
-        k_tile_colscan<<<(tg.ntiles + 255) / 256, 256, 0, s>>>(blk, counts, tg.ntiles, G);
+        k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);
         NBK_LAUNCHED();
         k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
         NBK_LAUNCHED();
         NBK_CUDA(cudaFuncSetAttribute(k_tile_scatter_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-        k_tile_scatter_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg.ntiles, offsets,
+        k_tile_scatter_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, offsets,
                                                                     blk, spos, smass, tile_ids);
         NBK_LAUNCHED();
     } else {
@@ -796,32 +842,33 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
                                                       tile_ids);
         NBK_LAUNCHED();
     }
-    const int RP = (tg.R + 3) & ~3;
-    size_t smem = (size_t)2 * tg.R * tg.R * RP * sizeof(unsigned);
-    int per_sm = (int)((220 * 1024) / (smem + 2048));
-    if (per_sm > 6) per_sm = 6;
-    if (per_sm < 1) per_sm = 1;
-    int grid = NBK_SM_COUNT * per_sm;
-    if (grid > tg.ntiles) grid = tg.ntiles;
     // tile write-back: TMA bulk reduce-add rows (default) or per-cell stores/REDG (NBK_PAINT_FLUSH=st)
     static int flush_mode = -1;
     if (flush_mode < 0) {
         const char *e = getenv("NBK_PAINT_FLUSH");
         flush_mode = (e && e[0] == 's') ? 0 : 1;
     }
-#define LAUNCH_TP(SH, FL, SHIFTV, MESHP)                                                                              \
+    // the region edge depends on the mesh being painted (one more cell for the half-cell shifted one); tile ids do not
+#define LAUNCH_TP(SH, FL, MESHP)                                                                                       \
     do {                                                                                                              \
-        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, PT, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        const int Rr = TILE + SUP - 1 + ((SH) ? 1 : 0), RPr = (Rr + 3) & ~3;                                          \
+        size_t smem = (size_t)2 * Rr * Rr * RPr * sizeof(unsigned);                                                   \
+        int per_sm = (int)((220 * 1024) / (smem + 2048));                                                             \
+        if (per_sm > 6) per_sm = 6;                                                                                   \
+        if (per_sm < 1) per_sm = 1;                                                                                   \
+        int grid = NBK_SM_COUNT * per_sm;                                                                             \
+        if (grid > tg.ntiles) grid = tg.ntiles;                                                                       \
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                                    \
-        k_tile_paint<SUP, PT, MT, FT, SH, FL><<<grid, 256, smem, s>>>(spos, smass, tg, SHIFTV, offsets, queue, absmax,  \
-                                                                      (FT *)(MESHP));                                 \
+        k_tile_paint<SUP, MT, FT, SH, FL><<<grid, 256, smem, s>>>(spos, smass, tg, offsets, queue, absmax,             \
+                                                                  (FT *)(MESHP));                                     \
         NBK_LAUNCHED();                                                                                               \
     } while (0)
-    if (shifted) { if (flush_mode) LAUNCH_TP(true, 1, shift, mesh); else LAUNCH_TP(true, 0, shift, mesh); }
-    else { if (flush_mode) LAUNCH_TP(false, 1, shift, mesh); else LAUNCH_TP(false, 0, shift, mesh); }
+    if (shift != 0.0) { if (flush_mode) LAUNCH_TP(true, 1, mesh); else LAUNCH_TP(true, 0, mesh); }
+    else { if (flush_mode) LAUNCH_TP(false, 1, mesh); else LAUNCH_TP(false, 0, mesh); }
     if (mesh2) {
         NBK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), s));
-        if (flush_mode) LAUNCH_TP(true, 1, 0.5, mesh2); else LAUNCH_TP(true, 0, 0.5, mesh2);
+        if (flush_mode) LAUNCH_TP(true, 1, mesh2); else LAUNCH_TP(true, 0, mesh2);
     }
 #undef LAUNCH_TP
     return NBK_OK;
