@@ -299,9 +299,10 @@ __device__ __noinline__ int tile_of_exact(const PT *__restrict__ pos, int64_t i,
     return tile_from_cells(c, tg);
 }
 
-// exact leftmost cell + fixed-point fraction of particle i (the arithmetic of Window<SUP>::eval on the unshifted g)
+// exact leftmost cell + fixed-point fraction of particle i (the arithmetic of Window<SUP>::eval on the unshifted g).
+// Slow path: any magnitude, 64-bit cell arithmetic.
 template <int SUP, typename PT>
-__device__ __forceinline__ bool make_record(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, TileRec &rec) {
+__device__ __noinline__ bool make_record_slow(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, TileRec &rec) {
     double g[3];
     if (!load_grid(pos, i, tg.gm, 0.0, g)) return false;
     unsigned u[3];
@@ -318,6 +319,36 @@ __device__ __forceinline__ bool make_record(const PT *__restrict__ pos, int64_t 
     return true;
 }
 
+// Fast path for |g| < 2^31 without any float<->int conversion instruction (they issue at a fraction of the FP64
+// rate): a + 1.5*2^52 holds rint(a) in its low mantissa word; floor and the truncated 32-bit fraction follow with
+// FP64 adds.  Bit-identical to the slow path.
+template <int SUP, typename PT>
+__device__ __forceinline__ bool make_record(const PT *x, const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
+                                            TileRec &rec) {
+    const double K = 6755399441055744.0;      // 1.5 * 2^52
+    unsigned u[3];
+    int c[3];
+    bool fast = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        double a = (double)x[d] * tg.gm.scale[d];
+        if (WinOff<SUP>::A != 0.f) a += (double)WinOff<SUP>::A;
+        fast = fast && (fabs(a) < 2147483000.0);           // false for NaN / inf as well
+        double r = a + K;
+        int ri = __double2loint(r);
+        double rf = r - K;                                  // rint(a)
+        if (rf > a) { rf -= 1.0; ri -= 1; }                 // floor(a)
+        u[d] = (unsigned)__double2loint(__dadd_rz((a - rf) * 4294967296.0, 4503599627370496.0));
+        int cc = ri + WinOff<SUP>::B;
+        if ((unsigned)cc >= (unsigned)tg.gm.n[d]) { cc %= tg.gm.n[d]; if (cc < 0) cc += tg.gm.n[d]; }
+        c[d] = cc;
+    }
+    if (!fast) return make_record_slow<SUP, PT>(pos, i, tg, rec);
+    int lx = (slab_local(c[0], tg) + tg.G) & (TILE - 1);
+    rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
+    return true;
+}
+
 // Tile id of particle i.  float32 positions take a float32 fast path: g32 = x*scale differs from the f8 grid
 // coordinate by < 2^-22 |g|, so unless the fraction of (g32 + A) lies within 3e-7|g| of a cell boundary (or the
 // particle is far outside the box) floor() agrees with the exact arithmetic; the rare rest is recomputed in f8.
@@ -328,9 +359,8 @@ struct FastTile {
     float lim[3];   // accept when |frac(g) - 0.5| < lim  (frac at least eps away from both cell boundaries)
 };
 
-__device__ __forceinline__ FastTile make_fast_tile(const TileGeom &tg) {
+static FastTile make_fast_tile(const TileGeom &tg) {      // host side: passed to the kernels by value
     FastTile f;
-#pragma unroll
     for (int d = 0; d < 3; d++) {
         f.sc[d] = (float)tg.gm.scale[d];
         // |g32 - g_exact| <= 2 float32 roundings of a value below n+2 -> 3e-7 (n+2) + 1e-6 is a safe margin
@@ -344,13 +374,15 @@ __device__ __forceinline__ FastTile make_fast_tile(const TileGeom &tg) {
 // everything else (near-boundary, outside the box, f8 positions) is recomputed in f8.  The id is therefore
 // ALWAYS the exact leftmost cell's tile -- count, scatter and paint passes agree.
 template <int SUP, typename PT>
-__device__ __forceinline__ int tile_of(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, const FastTile &ft) {
+__device__ __forceinline__ int tile_of(const PT *x, const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
+                                       const FastTile &ft) {
     if (sizeof(PT) == 4) {
         int c[3];
         bool ok = true;
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-            float g = (float)pos[3 * i + d] * ft.sc[d] + WinOff<SUP>::A;
+            float g = (float)x[d] * ft.sc[d];
+            if (WinOff<SUP>::A != 0.f) g += WinOff<SUP>::A;
             float f = floorf(g);
             ok = ok && (fabsf((g - f) - 0.5f) < ft.lim[d]);
             c[d] = (int)f + WinOff<SUP>::B;
@@ -383,15 +415,16 @@ __device__ __forceinline__ unsigned warp_claim(unsigned *counter, int key, bool 
 
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(256)
-k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg,
+k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg, FastTile ft,
              unsigned *__restrict__ counts, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float mx = 0.f;
-    const FastTile ft = make_fast_tile(tg);
     int64_t nround = ((n + stride - 1) / stride) * stride;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         bool in = i < n;
-        int t = in ? tile_of<SUP, PT>(pos, i, tg, ft) : -1;
+        PT x[3] = {0, 0, 0};
+        if (in) { x[0] = pos[3 * i]; x[1] = pos[3 * i + 1]; x[2] = pos[3 * i + 2]; }
+        int t = in ? tile_of<SUP, PT>(x, pos, i, tg, ft) : -1;
         if (in) tile_ids[i] = t;          // the scatter pass reuses the id instead of recomputing it
         warp_claim(counts, t, t >= 0);
         if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);
@@ -458,7 +491,10 @@ k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t 
         bool in = i < n;
         int t = in ? tile_ids[i] : -1;
         TileRec r = make_uint4(0, 0, 0, 0);
-        if (t >= 0) make_record<SUP, PT>(pos, i, tg, r);
+        if (t >= 0) {
+            PT x[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+            make_record<SUP, PT>(x, pos, i, tg, r);
+        }
         unsigned slot = warp_claim(cursor, t, t >= 0);
         if (t >= 0) {
             int64_t dst = (int64_t)offsets[t] + slot;
@@ -489,21 +525,37 @@ __device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool act
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(1024)
 k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
-                 unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
+                 FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
     extern __shared__ __align__(16) unsigned s_hist[];
     for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
-    const FastTile ft = make_fast_tile(tg);
     const int64_t b = (int64_t)blockIdx.x * chunk;
     const int64_t e = (b + chunk < n) ? b + chunk : n;
     float mx = 0.f;
-    for (int64_t i0 = b; i0 < e; i0 += blockDim.x) {
-        int64_t i = i0 + threadIdx.x;
-        bool in = i < e;
-        int t = in ? tile_of<SUP, PT>(pos, i, tg, ft) : -1;
-        if (in) tile_ids[i] = t;
-        smem_claim(s_hist, t, t >= 0, false);
-        if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);
+    // 4 particles per thread and round: all 12 coordinate loads are issued before the first is consumed (the pass is
+    // bound by memory latency at 32 warps / SM)
+    constexpr int U = 4;
+    for (int64_t i0 = b; i0 < e; i0 += (int64_t)U * blockDim.x) {
+        PT x[U][3];
+        MT mv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+            bool in = i < e;
+            x[u][0] = in ? pos[3 * i] : (PT)0;
+            x[u][1] = in ? pos[3 * i + 1] : (PT)0;
+            x[u][2] = in ? pos[3 * i + 2] : (PT)0;
+            mv[u] = (mass && in) ? mass[i] : (MT)0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+            bool in = i < e;
+            int t = in ? tile_of<SUP, PT>(x[u], pos, i, tg, ft) : -1;
+            if (in) tile_ids[i] = t;
+            smem_claim(s_hist, t, t >= 0, false);
+            if (mass && t >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
+        }
     }
     if (mass) {
 #pragma unroll
@@ -547,16 +599,32 @@ k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int6
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * chunk;
     const int64_t e = (b + chunk < n) ? b + chunk : n;
-    for (int64_t i0 = b; i0 < e; i0 += blockDim.x) {
-        int64_t i = i0 + threadIdx.x;
-        bool in = i < e;
-        int t = in ? tile_ids[i] : -1;
-        TileRec r = make_uint4(0, 0, 0, 0);
-        if (t >= 0) make_record<SUP, PT>(pos, i, tg, r);
-        unsigned dst = smem_claim(s_cur, t, t >= 0, true);
-        if (t >= 0) {
-            recs[dst] = r;
-            if (mass) smass[dst] = mass[i];
+    constexpr int U = 4;      // independent particles per thread and round (latency hiding, see k_tile_count_blk)
+    for (int64_t i0 = b; i0 < e; i0 += (int64_t)U * blockDim.x) {
+        PT x[U][3];
+        MT mv[U];
+        int tt[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+            bool in = i < e;
+            tt[u] = in ? tile_ids[i] : -1;
+            x[u][0] = in ? pos[3 * i] : (PT)0;
+            x[u][1] = in ? pos[3 * i + 1] : (PT)0;
+            x[u][2] = in ? pos[3 * i + 2] : (PT)0;
+            mv[u] = (mass && in) ? mass[i] : (MT)0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
+            int t = tt[u];
+            TileRec r = make_uint4(0, 0, 0, 0);
+            if (t >= 0) make_record<SUP, PT>(x[u], pos, i, tg, r);
+            unsigned dst = smem_claim(s_cur, t, t >= 0, true);
+            if (t >= 0) {
+                recs[dst] = r;
+                if (mass) smass[dst] = mv[u];
+            }
         }
     }
 }
@@ -638,8 +706,15 @@ k_tile_paint(const TileRec *__restrict__ recs, const MT *__restrict__ smass, Til
         int tz = t % tg.nt[2], ty = (t / tg.nt[2]) % tg.nt[1], tx = t / (tg.nt[2] * tg.nt[1]);
         int o[3] = {tx * TILE - tg.G, ty * TILE, tz * TILE};   // region origin (x: slab-local)
         __syncthreads();
-        for (unsigned p = b + threadIdx.x; p < e; p += blockDim.x) {
-            const TileRec r = recs[p];
+        // the record (and mass) of the next round is requested before this round's deposits are issued
+        unsigned p = b + threadIdx.x;
+        TileRec rn = make_uint4(0, 0, 0, 0);
+        MT mn = (MT)1;
+        if (p < e) { rn = recs[p]; if (smass) mn = smass[p]; }
+        for (; p < e; p += blockDim.x) {
+            const TileRec r = rn;
+            const MT mcur = mn;
+            if (p + blockDim.x < e) { rn = recs[p + blockDim.x]; if (smass) mn = smass[p + blockDim.x]; }
             unsigned u[3] = {r.x, r.y, r.z};
             int l[3] = {(int)(r.w & 255u), (int)((r.w >> 8) & 255u), (int)((r.w >> 16) & 255u)};
             double w[3][SUP];
@@ -650,10 +725,12 @@ k_tile_paint(const TileRec *__restrict__ recs, const MT *__restrict__ smass, Til
                     l[d] += (v < u[d]) ? 1 : 0;
                     u[d] = v;
                 }
-                WinD<SUP>::eval(WinD<SUP>::DMIN + (double)u[d] * 2.3283064365386963e-10, w[d]);
+                // u * 2^-32 via the 2^52 mantissa trick (no I2F)
+                double fr = (__hiloint2double(0x43300000, (int)u[d]) - 4503599627370496.0) * 2.3283064365386963e-10;
+                WinD<SUP>::eval(WinD<SUP>::DMIN != 0.0 ? WinD<SUP>::DMIN + fr : fr, w[d]);
             }
             const int base0 = (l[0] * R + l[1]) * RP + l[2];
-            const double m = smass ? (double)smass[p] : 1.0;
+            const double m = smass ? (double)mcur : 1.0;
             const double mS = m * S;
             double wz[SUP];
 #pragma unroll
@@ -795,6 +872,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     bool shifted = (mesh2 != nullptr) || shift != 0.0;
     int rc = make_tile_geom(gm, SUP, shifted, tg);
     if (rc) return rc;
+    const FastTile ft = make_fast_tile(tg);
     char *w = (char *)work;
     unsigned *queue = (unsigned *)w;
     unsigned *absmax = queue + 1;
@@ -820,7 +898,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         const int64_t chunk = (n + G - 1) / G;
         NBK_CUDA(cudaMemsetAsync(work, 0, 256, s));        // header
         NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, blk, absmax,
+        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax,
                                                                   tile_ids);
         NBK_LAUNCHED();
         k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);
@@ -834,7 +912,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     } else {
         NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
         int g = nbk_grid_for(n, 256, 8);
-        k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, counts, absmax, tile_ids);
+        k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, ft, counts, absmax, tile_ids);
         NBK_LAUNCHED();
         k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
         NBK_LAUNCHED();
