@@ -258,6 +258,10 @@ __device__ __forceinline__ double legendre(int ell, double x) {
     return p1;
 }
 
+template <typename T> struct Pair2;
+template <> struct Pair2<float> { typedef float2 type; };
+template <> struct Pair2<double> { typedef double2 type; };
+
 template <bool SMEM_ACC>
 __device__ __forceinline__ void acc_add(double *p, double v) {
     if (v != 0.0) atomicAdd(p, v);
@@ -338,8 +342,26 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
         roff[3] = ((int64_t)m0 * g.D1 + m1) * rowlen;
         const bool use1 = (m1 != i1), use2 = (m0 != i0), use3 = use1 && use2;
         const double vol_row = ct0 ? P.volume * (ct0[g.start + i0] * ct1[i1]) : P.volume;
+        // values of the (up to four) rows of the group for lane position kz; the load for round it + 1 is issued
+        // before round it is binned (the sweep is bound by memory latency otherwise)
+        typedef typename Pair2<T>::type V2;
+        V2 cur[4], nxt[4];
+        auto load_group = [&](int kz, V2 (&v)[4]) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q].x = 0; v[q].y = 0;
+                if (kz >= g.Nzc) continue;
+                if (q == 1 && !use1) continue;
+                if (q == 2 && !use2) continue;
+                if (q == 3 && !use3) continue;
+                if (P.estride == 2) v[q] = *reinterpret_cast<const V2 *>(c1 + roff[q] + 2 * kz);
+                else v[q].x = c1[roff[q] + kz];
+            }
+        };
+        load_group(lane, cur);
         for (int it = 0; it < kz_iters; it++) {
             const int kz = it * 32 + lane;
+            if (it + 1 < kz_iters) load_group(kz + 32, nxt);
             int key = -1;
             double xs = 0, ms = 0, yr[NELL], yi[NELL];
             unsigned wcnt = 0;
@@ -392,8 +414,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     if (q == 1 && !use1) continue;
                     if (q == 2 && !use2) continue;
                     if (q == 3 && !use3) continue;
-                    const T *p1 = c1 + roff[q] + P.estride * kz;
-                    double a = (double)p1[0], bb = (P.estride == 2) ? (double)p1[1] : 0.0;
+                    double a = (double)cur[q].x, bb = (double)cur[q].y;
                     if (P.is_p3d) { yre += a; yim += bb; }
                     else {
                         double c = a, d = bb;
@@ -480,6 +501,8 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     acc_add<SMEM_ACC>(&a_y[((size_t)l * P.nb + key) * 2 + 1], yi[l]);
                 }
             }
+#pragma unroll
+            for (int q = 0; q < 4; q++) cur[q] = nxt[q];
         }
     }
     if (SMEM_ACC) {
@@ -535,7 +558,7 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
     NBK_CHECK_ARG(smem <= 227 * 1024, "power_bin: too many bin edges for shared memory");
     int64_t rows = (int64_t)P.g.count * P.g.D1;
     int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm > 4) per_sm = 4;
+    if (per_sm > 8) per_sm = 8;
     if (per_sm < 1) per_sm = 1;
     int64_t want = (rows + 7) / 8;
     int grid = (int)(want < (int64_t)NBK_SM_COUNT * per_sm ? want : (int64_t)NBK_SM_COUNT * per_sm);
@@ -546,6 +569,10 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
     do {                                                                                                             \
         NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, ACC, SYMV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       (int)smem));                                                                   \
+        int occ = 1;   /* persistent row loop: exactly one wave of resident CTAs */                                   \
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_power_bin<T, NELL, ACC, SYMV>, 256, smem));    \
+        if (occ < 1) occ = 1;                                                                                        \
+        if ((int64_t)grid > (int64_t)NBK_SM_COUNT * occ) grid = NBK_SM_COUNT * occ;                                   \
         k_power_bin<T, NELL, ACC, SYMV><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,          \
                                                                 (unsigned long long *)nsum, xsum, musum, ysum, kmin, \
                                                                 inv_dk, uniform, ct0, ct1, ctz);                      \

@@ -302,9 +302,9 @@ __device__ __noinline__ int tile_of_exact(const PT *__restrict__ pos, int64_t i,
 // exact leftmost cell + fixed-point fraction of particle i (the arithmetic of Window<SUP>::eval on the unshifted g).
 // Slow path: any magnitude, 64-bit cell arithmetic.
 template <int SUP, typename PT>
-__device__ __noinline__ bool make_record_slow(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, TileRec &rec) {
+__device__ __noinline__ int make_record_slow(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, TileRec &rec) {
     double g[3];
-    if (!load_grid(pos, i, tg.gm, 0.0, g)) return false;
+    if (!load_grid(pos, i, tg.gm, 0.0, g)) return -1;
     unsigned u[3];
     int c[3];
 #pragma unroll
@@ -316,15 +316,15 @@ __device__ __noinline__ bool make_record_slow(const PT *__restrict__ pos, int64_
     }
     int lx = (slab_local(c[0], tg) + tg.G) & (TILE - 1);
     rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
-    return true;
+    return tile_from_cells(c, tg);
 }
 
 // Fast path for |g| < 2^31 without any float<->int conversion instruction (they issue at a fraction of the FP64
 // rate): a + 1.5*2^52 holds rint(a) in its low mantissa word; floor and the truncated 32-bit fraction follow with
 // FP64 adds.  Bit-identical to the slow path.
 template <int SUP, typename PT>
-__device__ __forceinline__ bool make_record(const PT *x, const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
-                                            TileRec &rec) {
+__device__ __forceinline__ int make_record(const PT *x, const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
+                                           TileRec &rec) {
     const double K = 6755399441055744.0;      // 1.5 * 2^52
     unsigned u[3];
     int c[3];
@@ -339,14 +339,40 @@ __device__ __forceinline__ bool make_record(const PT *x, const PT *__restrict__ 
         double rf = r - K;                                  // rint(a)
         if (rf > a) { rf -= 1.0; ri -= 1; }                 // floor(a)
         u[d] = (unsigned)__double2loint(__dadd_rz((a - rf) * 4294967296.0, 4503599627370496.0));
-        int cc = ri + WinOff<SUP>::B;
-        if ((unsigned)cc >= (unsigned)tg.gm.n[d]) { cc %= tg.gm.n[d]; if (cc < 0) cc += tg.gm.n[d]; }
+        int cc = ri + WinOff<SUP>::B;                       // one period of wrap here, anything further in the slow path
+        if (cc < 0) cc += tg.gm.n[d];
+        else if (cc >= tg.gm.n[d]) cc -= tg.gm.n[d];
+        fast = fast && ((unsigned)cc < (unsigned)tg.gm.n[d]);
         c[d] = cc;
     }
     if (!fast) return make_record_slow<SUP, PT>(pos, i, tg, rec);
     int lx = (slab_local(c[0], tg) + tg.G) & (TILE - 1);
     rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
-    return true;
+    return tile_from_cells(c, tg);      // the tile the bucketing pass counted this particle in (both are exact)
+}
+
+// coordinates of the 4 consecutive particles i0 .. i0+3 (i0 % 4 == 0): three 16-byte loads per thread for f4
+// positions when the array is 16-byte aligned (a warp then reads one contiguous 1536-byte run), scalar loads otherwise
+template <typename PT>
+__device__ __forceinline__ void load4(const PT *__restrict__ pos, int64_t i0, int64_t e, bool aligned, PT (&x)[4][3]) {
+    if (aligned && i0 + 3 < e) {
+        constexpr int NV = (int)(12 * sizeof(PT) / 16);
+        const uint4 *v = reinterpret_cast<const uint4 *>(pos + 3 * i0);
+        uint4 r[NV];
+#pragma unroll
+        for (int k = 0; k < NV; k++) r[k] = v[k];
+        const PT *f = reinterpret_cast<const PT *>(r);
+#pragma unroll
+        for (int u = 0; u < 4; u++) { x[u][0] = f[3 * u]; x[u][1] = f[3 * u + 1]; x[u][2] = f[3 * u + 2]; }
+    } else {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            bool in = i0 + u < e;
+            x[u][0] = in ? pos[3 * (i0 + u)] : (PT)0;
+            x[u][1] = in ? pos[3 * (i0 + u) + 1] : (PT)0;
+            x[u][2] = in ? pos[3 * (i0 + u) + 2] : (PT)0;
+        }
+    }
 }
 
 // Tile id of particle i.  float32 positions take a float32 fast path: g32 = x*scale differs from the f8 grid
@@ -493,7 +519,7 @@ k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t 
         TileRec r = make_uint4(0, 0, 0, 0);
         if (t >= 0) {
             PT x[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
-            make_record<SUP, PT>(x, pos, i, tg, r);
+            t = make_record<SUP, PT>(x, pos, i, tg, r);
         }
         unsigned slot = warp_claim(cursor, t, t >= 0);
         if (t >= 0) {
@@ -511,49 +537,47 @@ k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t 
 // prefix over c and the column totals into tile offsets; pass C reloads row c as shared cursors and scatters the
 // same chunk.  Slot order inside a tile is arbitrary, the fixed-point accumulation makes the mesh independent of it.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool active, bool want_slot) {
+// Shared-memory counter claim.  Random catalogues: one native ATOMS per lane.  Spatially coherent catalogues put many
+// lanes of a warp on the same counter, which the atomic unit serialises; when neighbouring lanes agree often, the
+// warp aggregates equal keys first (one ATOMS per distinct key).  Must be called by all 32 lanes.
+__device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool active) {
     const int lane = threadIdx.x & 31;
-    int k0 = __shfl_sync(0xffffffffu, key, 0);
-    if (__all_sync(0xffffffffu, active && key == k0)) {      // spatially coherent catalogue: one add per warp
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&hist[key], 32u);
-        return want_slot ? __shfl_sync(0xffffffffu, base, 0) + lane : 0u;
-    }
-    return active ? atomicAdd(&hist[key], 1u) : 0u;
+    int kn = __shfl_xor_sync(0xffffffffu, key, 1);
+    unsigned same = __ballot_sync(0xffffffffu, active && kn == key);
+    if (__popc(same) < 8) return active ? atomicAdd(&hist[key], 1u) : 0u;
+    unsigned mask = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
+    if (!active) return 0u;
+    int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&hist[key], (unsigned)__popc(mask));
+    return __shfl_sync(mask, base, leader) + __popc(mask & ((1u << lane) - 1));
 }
 
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(1024)
 k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
-                 FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
+                 FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits) {
     extern __shared__ __align__(16) unsigned s_hist[];
     for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * chunk;
     const int64_t e = (b + chunk < n) ? b + chunk : n;
     float mx = 0.f;
-    // 4 particles per thread and round: all 12 coordinate loads are issued before the first is consumed (the pass is
-    // bound by memory latency at 32 warps / SM)
-    constexpr int U = 4;
-    for (int64_t i0 = b; i0 < e; i0 += (int64_t)U * blockDim.x) {
-        PT x[U][3];
-        MT mv[U];
+    // 4 consecutive particles per thread and round: the coordinate loads are issued before the first is consumed (the
+    // pass is bound by memory latency at 32 warps / SM) and, for aligned arrays, are 16-byte vectors
+    const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+    for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // uniform trip count (warp collectives)
+        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        PT x[4][3];
+        MT mv[4];
+        load4(pos, i0, e, aligned, x);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
-            bool in = i < e;
-            x[u][0] = in ? pos[3 * i] : (PT)0;
-            x[u][1] = in ? pos[3 * i + 1] : (PT)0;
-            x[u][2] = in ? pos[3 * i + 2] : (PT)0;
-            mv[u] = (mass && in) ? mass[i] : (MT)0;
-        }
+        for (int u = 0; u < 4; u++) mv[u] = (mass && i0 + u < e) ? mass[i0 + u] : (MT)0;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
-            bool in = i < e;
-            int t = in ? tile_of<SUP, PT>(x[u], pos, i, tg, ft) : -1;
-            if (in) tile_ids[i] = t;
-            smem_claim(s_hist, t, t >= 0, false);
+        for (int u = 0; u < 4; u++) {
+            bool in = i0 + u < e;
+            int t = in ? tile_of<SUP, PT>(x[u], pos, i0 + u, tg, ft) : -1;
+            smem_claim(s_hist, t, t >= 0);
             if (mass && t >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
         }
     }
@@ -591,7 +615,7 @@ template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(1024)
 k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
                    const unsigned *__restrict__ offsets, const unsigned *__restrict__ blk,
-                   TileRec *__restrict__ recs, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
+                   TileRec *__restrict__ recs, MT *__restrict__ smass) {
     extern __shared__ __align__(16) unsigned s_cur[];
     const int ntiles = tg.ntiles;
     const unsigned *row = blk + (size_t)blockIdx.x * ntiles;
@@ -599,28 +623,19 @@ k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int6
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * chunk;
     const int64_t e = (b + chunk < n) ? b + chunk : n;
-    constexpr int U = 4;      // independent particles per thread and round (latency hiding, see k_tile_count_blk)
-    for (int64_t i0 = b; i0 < e; i0 += (int64_t)U * blockDim.x) {
-        PT x[U][3];
-        MT mv[U];
-        int tt[U];
+    const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+    for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // see k_tile_count_blk
+        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        PT x[4][3];
+        MT mv[4];
+        load4(pos, i0, e, aligned, x);
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
-            bool in = i < e;
-            tt[u] = in ? tile_ids[i] : -1;
-            x[u][0] = in ? pos[3 * i] : (PT)0;
-            x[u][1] = in ? pos[3 * i + 1] : (PT)0;
-            x[u][2] = in ? pos[3 * i + 2] : (PT)0;
-            mv[u] = (mass && in) ? mass[i] : (MT)0;
-        }
+        for (int u = 0; u < 4; u++) mv[u] = (mass && i0 + u < e) ? mass[i0 + u] : (MT)0;
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-            int64_t i = i0 + (int64_t)u * blockDim.x + threadIdx.x;
-            int t = tt[u];
+        for (int u = 0; u < 4; u++) {
             TileRec r = make_uint4(0, 0, 0, 0);
-            if (t >= 0) make_record<SUP, PT>(x[u], pos, i, tg, r);
-            unsigned dst = smem_claim(s_cur, t, t >= 0, true);
+            int t = (i0 + u < e) ? make_record<SUP, PT>(x[u], pos, i0 + u, tg, r) : -1;
+            unsigned dst = smem_claim(s_cur, t, t >= 0);
             if (t >= 0) {
                 recs[dst] = r;
                 if (mass) smass[dst] = mv[u];
@@ -895,11 +910,10 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     const bool use_blk = blk_mode && hist_bytes <= NBK_BLK_SMEM && n >= 4 * (int64_t)tg.ntiles;
     if (use_blk) {
         const int G = NBK_SM_COUNT;
-        const int64_t chunk = (n + G - 1) / G;
+        const int64_t chunk = (((n + G - 1) / G) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
         NBK_CUDA(cudaMemsetAsync(work, 0, 256, s));        // header
         NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax,
-                                                                  tile_ids);
+        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax);
         NBK_LAUNCHED();
         k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);
         NBK_LAUNCHED();
@@ -907,7 +921,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         NBK_LAUNCHED();
         NBK_CUDA(cudaFuncSetAttribute(k_tile_scatter_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
         k_tile_scatter_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, offsets,
-                                                                    blk, spos, smass, tile_ids);
+                                                                    blk, spos, smass);
         NBK_LAUNCHED();
     } else {
         NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
