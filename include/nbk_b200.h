@@ -79,6 +79,8 @@ int nbk_paint_interlaced(const void *pos, int pos_dtype, int64_t n, const void *
  * accumulated in shared memory in 64-bit fixed point (order-independent, resolution 2^-31 of the largest
  * |mass|) and flushed once.  mesh2 != NULL paints the +0.5-cell shifted mesh of the interlaced branch from
  * the same buckets (then shift must be 0).  `work`: device scratch of nbk_paint_tiled_workspace() bytes.
+ * clear != 0 gives pm.paint(hold=False): the mesh(es) are zeroed by the call itself (inside the bucketing
+ * pass, no separate fill); clear == 0 accumulates into what is there (hold=True).
  * nbk_paint_tiled_supported() says whether the mesh admits the tiling (sides multiples of 16, >= 32). */
 int nbk_paint_tiled_supported(const int64_t *nmesh_host, int64_t x_n, int window);
 int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_dtype, const int64_t *nmesh_host,
@@ -86,7 +88,7 @@ int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_dtype, cons
 int nbk_paint_tiled(const void *pos, int pos_dtype, int64_t n, const void *mass, int mass_dtype, int window,
                     double shift, const double *boxsize_host, const int64_t *nmesh_host, int64_t x_start,
                     int64_t x_n, void *mesh, void *mesh2, int mesh_dtype, void *work, int64_t work_bytes,
-                    void *stream);
+                    int clear, void *stream);
 
 /* pm.decompose(pos, smoothing) + Layout.exchange (source/mesh/catalog.py:271-284) for the x-slab decomposition:
  * nbk_route_count writes, per particle, the bitmask of OTHER ranks (P <= 32) owning a plane within `smoothing`

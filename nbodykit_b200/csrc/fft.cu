@@ -516,7 +516,7 @@ __device__ __forceinline__ void last_stage_natural(C *sm, int M, int ndig) {
 // stage reads the real row straight from global memory (lanes along the row: 512-byte runs), the last stage leaves
 // Z in NATURAL frequency order in shared memory (registers carry the permutation across one barrier), so the
 // Hermitian split reads Z[k] and Z[M-k] with unit-stride lanes and no digit-reversal arithmetic.  Shared: tile
-// [M][B+1] | W_N table [N] (W_M^j = W_N^2j serves the butterflies, W_N^k the split).
+// [M][B+1] | W_N table [N] (W_M^j = W_N^2j serves the butterflies, W_N^k the split) | first-stage twiddles [7][M/8].
 // ---------------------------------------------------------------------------------------------
 template <typename T, int B>
 __global__ void __launch_bounds__(256, 2)
@@ -529,6 +529,12 @@ k_fft_z_r2c_rg(const T *__restrict__ real, typename C2<T>::type *__restrict__ cp
     const int Nzc = M + 1;
     constexpr int pitch = B + 1;
     const int T_ = blockDim.x;
+    // first-stage twiddles transposed to [m][q] (lanes run along q there: unit stride instead of stride 2m)
+    C *tw1 = sm + (size_t)M * pitch + Nz;
+    for (int i = threadIdx.x; i < 7 * (M >> 3); i += blockDim.x) {
+        int m = i / (M >> 3) + 1, q = i - (m - 1) * (M >> 3);
+        tw1[i] = twN_g[2 * m * q];
+    }
     const C *tw = stage_twiddles<C>(sm + (size_t)M * pitch, twN_g, Nz);    // tw[2j] = W_M^j
     const int n8 = log2m / 3, rrem = log2m - 3 * n8;
     const int Q1 = M >> 3, lq1 = log2m - 3;
@@ -554,7 +560,7 @@ k_fft_z_r2c_rg(const T *__restrict__ real, typename C2<T>::type *__restrict__ cp
             C *o = sm + q * pitch + b;
             o[0] = a[0];
 #pragma unroll
-            for (int m = 1; m < 8; m++) o[m * Q1 * pitch] = cmul(a[m], tw[2 * m * q]);
+            for (int m = 1; m < 8; m++) o[m * Q1 * pitch] = cmul(a[m], tw1[(m - 1) * Q1 + q]);
         }
         __syncthreads();
         // ---- middle stages, in place
@@ -906,7 +912,7 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
         const int V = sizeof(T) == 4 ? 16 : 8;
         int B = 16;
         while (B > 1 && (M * B > 256 * V || B / 2 >= rows)) B >>= 1;
-        size_t smem = ((size_t)M * (B + 1) + Nz) * sizeof(C);
+        size_t smem = ((size_t)M * (B + 1) + Nz + 7 * (M / 8)) * sizeof(C);   // tile | W_N | first-stage twiddles
         NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);
         int64_t n_tiles = (rows + B - 1) / B;
         int per_sm = (int)((227 * 1024) / (smem + 1024));

@@ -259,6 +259,7 @@ struct TileGeom {
     int nt[3];        // tiles per axis
     int R;            // region edge = TILE + support - 1 (+1 when a half-cell shifted mesh is painted)
     int ntiles;
+    int full;         // the slab is the whole mesh (single GPU): no ghost / ownership logic
 };
 
 // local x of a wrapped global cell relative to the slab origin, in [-G, Nx - G)
@@ -277,6 +278,7 @@ template <> struct WinOff<3> { static constexpr float A = 0.5f; static constexpr
 template <> struct WinOff<4> { static constexpr float A = 0.0f; static constexpr int B = -1; };
 
 __device__ __forceinline__ int tile_from_cells(const int *c, const TileGeom &tg) {
+    if (tg.full) return ((c[0] / TILE) * tg.nt[1] + c[1] / TILE) * tg.nt[2] + c[2] / TILE;   // cells are in [0, n)
     int lx = slab_local(c[0], tg);
     if (lx < -tg.G || lx >= tg.gm.x_n) return -1;   // cannot touch my planes
     int tx = (lx + tg.G) / TILE, ty = c[1] / TILE, tz = c[2] / TILE;
@@ -346,7 +348,7 @@ __device__ __forceinline__ int make_record(const PT *x, const PT *__restrict__ p
         c[d] = cc;
     }
     if (!fast) return make_record_slow<SUP, PT>(pos, i, tg, rec);
-    int lx = (slab_local(c[0], tg) + tg.G) & (TILE - 1);
+    int lx = (tg.full ? c[0] : slab_local(c[0], tg) + tg.G) & (TILE - 1);
     rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
     return tile_from_cells(c, tg);      // the tile the bucketing pass counted this particle in (both are exact)
 }
@@ -556,7 +558,8 @@ __device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool act
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(1024)
 k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
-                 FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits) {
+                 FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, uint4 *__restrict__ zero1,
+                 uint4 *__restrict__ zero2, int64_t zero_n) {
     extern __shared__ __align__(16) unsigned s_hist[];
     for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) s_hist[t] = 0;
     __syncthreads();
@@ -566,11 +569,22 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
     // 4 consecutive particles per thread and round: the coordinate loads are issued before the first is consumed (the
     // pass is bound by memory latency at 32 warps / SM) and, for aligned arrays, are 16-byte vectors
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+    // hold=False: this pass also clears the mesh(es) -- zero_n 16-byte vectors each, a contiguous share per CTA, three
+    // stores per round riding in the shadow of the (latency-bound) particle loads; the tile pass runs later in-stream
+    const int64_t zper = zero1 ? (zero_n + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t zend = zero1 ? ((blockIdx.x + 1) * zper < zero_n ? (blockIdx.x + 1) * zper : zero_n) : 0;
+    int64_t zi = (int64_t)blockIdx.x * zper + threadIdx.x;
+    const uint4 zz = make_uint4(0, 0, 0, 0);
     for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // uniform trip count (warp collectives)
         const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
         PT x[4][3];
         MT mv[4];
         load4(pos, i0, e, aligned, x);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (zi < zend) { zero1[zi] = zz; if (zero2) zero2[zi] = zz; }
+            zi += blockDim.x;
+        }
 #pragma unroll
         for (int u = 0; u < 4; u++) mv[u] = (mass && i0 + u < e) ? mass[i0 + u] : (MT)0;
 #pragma unroll
@@ -581,6 +595,7 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
             if (mass && t >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
         }
     }
+    for (; zi < zend; zi += blockDim.x) { zero1[zi] = zz; if (zero2) zero2[zi] = zz; }
     if (mass) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -840,6 +855,7 @@ k_tile_paint(const TileRec *__restrict__ recs, const MT *__restrict__ smass, Til
 static int make_tile_geom(const PaintGeom &gm, int sup, bool shifted, TileGeom &tg) {
     tg.gm = gm;
     tg.G = (gm.x_n == gm.n[0]) ? 0 : sup + 1;
+    tg.full = (gm.x_n == gm.n[0] && gm.x_start == 0) ? 1 : 0;
     tg.R = TILE + sup - 1 + (shifted ? 1 : 0);
     tg.nt[0] = (gm.x_n + tg.G + TILE - 1) / TILE;
     tg.nt[1] = (gm.n[1] + TILE - 1) / TILE;
@@ -882,7 +898,7 @@ extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_
 
 template <int SUP, typename PT, typename MT, typename FT>
 static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGeom &gm, double shift, void *mesh,
-                     void *mesh2, void *work, cudaStream_t s) {
+                     void *mesh2, void *work, bool clear, cudaStream_t s) {
     TileGeom tg;
     bool shifted = (mesh2 != nullptr) || shift != 0.0;
     int rc = make_tile_geom(gm, SUP, shifted, tg);
@@ -907,13 +923,16 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         blk_mode = (e && e[0] == 'g') ? 0 : 1;          // NBK_PAINT_BUCKET=global forces the global-atomic passes
     }
     const size_t hist_bytes = sizeof(unsigned) * (size_t)tg.ntiles;
+    const size_t mesh_bytes = (size_t)gm.x_n * gm.n[1] * gm.n[2] * sizeof(FT);   // multiple of 16 (tiled meshes)
     const bool use_blk = blk_mode && hist_bytes <= NBK_BLK_SMEM && n >= 4 * (int64_t)tg.ntiles;
     if (use_blk) {
         const int G = NBK_SM_COUNT;
         const int64_t chunk = (((n + G - 1) / G) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
         NBK_CUDA(cudaMemsetAsync(work, 0, 256, s));        // header
         NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax);
+        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax,
+                                                                  clear ? (uint4 *)mesh : nullptr, clear ? (uint4 *)mesh2 : nullptr,
+                                                                  (int64_t)(mesh_bytes / 16));
         NBK_LAUNCHED();
         k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);
         NBK_LAUNCHED();
@@ -924,6 +943,10 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
                                                                     blk, spos, smass);
         NBK_LAUNCHED();
     } else {
+        if (clear) {
+            NBK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, s));
+            if (mesh2) NBK_CUDA(cudaMemsetAsync(mesh2, 0, mesh_bytes, s));
+        }
         NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
         int g = nbk_grid_for(n, 256, 8);
         k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, ft, counts, absmax, tile_ids);
@@ -968,24 +991,25 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
 
 template <int SUP, typename PT, typename MT>
 static int run_tiled1(const void *pos, const void *mass, int64_t n, const PaintGeom &gm, double shift, void *mesh,
-                      void *mesh2, int mesh_dtype, void *work, cudaStream_t s) {
-    if (mesh_dtype == NBK_F4) return run_tiled<SUP, PT, MT, float>(pos, mass, n, gm, shift, mesh, mesh2, work, s);
-    return run_tiled<SUP, PT, MT, double>(pos, mass, n, gm, shift, mesh, mesh2, work, s);
+                      void *mesh2, int mesh_dtype, void *work, bool clear, cudaStream_t s) {
+    if (mesh_dtype == NBK_F4) return run_tiled<SUP, PT, MT, float>(pos, mass, n, gm, shift, mesh, mesh2, work, clear, s);
+    return run_tiled<SUP, PT, MT, double>(pos, mass, n, gm, shift, mesh, mesh2, work, clear, s);
 }
 
 template <int SUP>
 static int run_tiled0(const void *pos, int pos_dtype, const void *mass, int mass_dtype, int64_t n, const PaintGeom &gm,
-                      double shift, void *mesh, void *mesh2, int mesh_dtype, void *work, cudaStream_t s) {
+                      double shift, void *mesh, void *mesh2, int mesh_dtype, void *work, bool clear, cudaStream_t s) {
     bool pf4 = pos_dtype == NBK_F4, mf4 = (mass_dtype == NBK_F4);
-    if (pf4 && mf4) return run_tiled1<SUP, float, float>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
-    if (pf4) return run_tiled1<SUP, float, double>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
-    if (mf4) return run_tiled1<SUP, double, float>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
-    return run_tiled1<SUP, double, double>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
+    if (pf4 && mf4) return run_tiled1<SUP, float, float>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear, s);
+    if (pf4) return run_tiled1<SUP, float, double>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear, s);
+    if (mf4) return run_tiled1<SUP, double, float>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear, s);
+    return run_tiled1<SUP, double, double>(pos, mass, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear, s);
 }
 
 extern "C" int nbk_paint_tiled(const void *pos, int pos_dtype, int64_t n, const void *mass, int mass_dtype, int window,
                                double shift, const double *box, const int64_t *nmesh, int64_t x_start, int64_t x_n,
-                               void *mesh, void *mesh2, int mesh_dtype, void *work, int64_t work_bytes, void *stream) {
+                               void *mesh, void *mesh2, int mesh_dtype, void *work, int64_t work_bytes, int clear,
+                               void *stream) {
     NBK_CHECK_ARG(pos_dtype == NBK_F4 || pos_dtype == NBK_F8, "paint_tiled: bad pos dtype %d", pos_dtype);
     NBK_CHECK_ARG(mesh_dtype == NBK_F4 || mesh_dtype == NBK_F8, "paint_tiled: bad mesh dtype %d", mesh_dtype);
     NBK_CHECK_ARG(mass == nullptr || mass_dtype == NBK_F4 || mass_dtype == NBK_F8, "paint_tiled: bad mass dtype %d", mass_dtype);
@@ -997,16 +1021,24 @@ extern "C" int nbk_paint_tiled(const void *pos, int pos_dtype, int64_t n, const 
     PaintGeom gm;
     int rc = make_geom(box, nmesh, x_start, x_n, gm);
     if (rc) return rc;
-    if (n == 0 || x_n == 0) return NBK_OK;
+    if (x_n == 0) return NBK_OK;
+    if (n == 0) {
+        if (clear) {
+            size_t mb = (size_t)x_n * nmesh[1] * nmesh[2] * (mesh_dtype == NBK_F4 ? 4 : 8);
+            NBK_CUDA(cudaMemsetAsync(mesh, 0, mb, (cudaStream_t)stream));
+            if (mesh2) NBK_CUDA(cudaMemsetAsync(mesh2, 0, mb, (cudaStream_t)stream));
+        }
+        return NBK_OK;
+    }
     int md = mass ? mass_dtype : 0;
     NBK_CHECK_ARG(work_bytes >= nbk_paint_tiled_workspace(n, pos_dtype, md, nmesh, x_n), "paint_tiled: workspace too small");
     if (mass == nullptr) mass_dtype = NBK_F8;
     cudaStream_t s = (cudaStream_t)stream;
     switch (window) {
-        case NBK_WINDOW_NNB: return run_tiled0<1>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
-        case NBK_WINDOW_CIC: return run_tiled0<2>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
-        case NBK_WINDOW_TSC: return run_tiled0<3>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
-        case NBK_WINDOW_PCS: return run_tiled0<4>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, s);
+        case NBK_WINDOW_NNB: return run_tiled0<1>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear != 0, s);
+        case NBK_WINDOW_CIC: return run_tiled0<2>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear != 0, s);
+        case NBK_WINDOW_TSC: return run_tiled0<3>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear != 0, s);
+        case NBK_WINDOW_PCS: return run_tiled0<4>(pos, pos_dtype, mass, mass_dtype, n, gm, shift, mesh, mesh2, mesh_dtype, work, clear != 0, s);
     }
     nbk_set_error("paint_tiled: unknown window %d", window);
     return NBK_ERR_ARG;

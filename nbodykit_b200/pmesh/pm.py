@@ -386,18 +386,18 @@ class ParticleMesh(object):
                 m = m.to(torch.float64)
             if m.shape[0] != p.shape[0]:
                 raise ValueError("paint: mass and position length mismatch")
-        if not hold:
-            out[...] = 0
-        target = out
         if scale_after is not None:
+            if not hold:
+                out[...] = 0
             target = RealField(self)
-            target[...] = 0
-        self._scatter(p, m, res, shift, target, None, method)
-        if scale_after is not None:
+            self._scatter(p, m, res, shift, target, None, method, clear=True)
             out.axpy(target, scale_after)
+        else:
+            # hold=False: the tiled path zeroes the mesh inside its bucketing pass, the direct path after a fill
+            self._scatter(p, m, res, shift, out, None, method, clear=not hold)
         return out
 
-    def paint_interlaced(self, pos, mass, resampler, out1, out2, method=None):
+    def paint_interlaced(self, pos, mass, resampler, out1, out2, method=None, hold=True):
         """both meshes of the interlaced branch (catalog.py:289-296) in one pass over the particles"""
         res = _window.FindResampler(resampler)
         if res.code is None:
@@ -411,14 +411,14 @@ class ParticleMesh(object):
             m = as_device_tensor(mass, device=dev)
             if m.dtype not in (torch.float32, torch.float64):
                 m = m.to(torch.float64)
-        self._scatter(p, m, res, 0.0, out1, out2, method)
+        self._scatter(p, m, res, 0.0, out1, out2, method, clear=not hold)
 
     # below this many particles per mesh cell the per-tile overhead of the tiled path outweighs its gain
     TILED_MIN_OCCUPANCY = 0.02
 
-    def _scatter(self, p, m, res, shift, out1, out2, method=None):
+    def _scatter(self, p, m, res, shift, out1, out2, method=None, clear=False):
         """dispatch to the tile-sorted shared-memory path or to the direct REDG path.
-        method: None (choose), 'tiled', 'direct'"""
+        method: None (choose), 'tiled', 'direct'.  clear: zero the mesh(es) first (hold=False)"""
         L = lib()
         n = int(p.shape[0])
         pcode = F4 if p.dtype == torch.float32 else F8
@@ -437,8 +437,12 @@ class ParticleMesh(object):
                 check(L.nbk_paint_tiled(_ptr(p), pcode, n, _ptr(m), mcode, res.code, float(shift), self._box_c,
                                         self._nmesh_c, self.x_start, self.x_n, _ptr(out1.value),
                                         _ptr(out2.value) if out2 is not None else None, code, _ptr(work), nbytes,
-                                        _stream()), "nbk_paint_tiled")
+                                        1 if clear else 0, _stream()), "nbk_paint_tiled")
             return
+        if clear:
+            out1[...] = 0
+            if out2 is not None:
+                out2[...] = 0
         with stage("paint"):
             if out2 is None:
                 check(L.nbk_paint(_ptr(p), pcode, n, _ptr(m), mcode, res.code, float(shift), self._box_c, self._nmesh_c,

@@ -237,17 +237,23 @@ class CatalogMesh(MeshSource):
         if not self.interlaced:
             with stage("H:paint_all"):
                 real = RealField(pm)
-                real[...] = 0
+                first = True          # the first batch clears the mesh inside its own bucketing pass
                 for p, m in batches:
                     if p.shape[0]:
-                        pm.paint(p, mass=m, resampler=resampler, hold=True, out=real)
+                        pm.paint(p, mass=m, resampler=resampler, hold=not first, out=real)
+                        first = False
+                if first:
+                    real[...] = 0
             return real, N, W, W2
         real1, real2 = RealField(pm), RealField(pm)
-        real1[...] = 0
-        real2[...] = 0
+        first = True
         for p, m in batches:
             if p.shape[0]:
-                pm.paint_interlaced(p, None if scalar else m, resampler, real1, real2)
+                pm.paint_interlaced(p, None if scalar else m, resampler, real1, real2, hold=not first)
+                first = False
+        if first:
+            real1[...] = 0
+            real2[...] = 0
         if scalar and mass != 1.0:
             real1 *= mass
             real2 *= mass

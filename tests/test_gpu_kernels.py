@@ -331,12 +331,12 @@ def test_paint_tiled_slab_ghosts(cuda):
     for x0, xn in [(0, 16), (16, 16), (48, 16), (8, 40)]:
         for shift in (0.0, 0.5):
             want = full if shift == 0.0 else po.paint(pos, None, N, L, "tsc", 0.5)
-            mesh = torch.zeros((xn, 32, 32), dtype=torch.float64, device="cuda")
+            mesh = torch.full((xn, 32, 32), 3.0, dtype=torch.float64, device="cuda")   # clear=1 must wipe this
             nb = Lb.nbk_paint_tiled_workspace(len(pos), 4, 0, _lib.iarr(N), xn)
             work = torch.empty(nb, dtype=torch.uint8, device="cuda")
             _lib.check(Lb.nbk_paint_tiled(ctypes.c_void_p(p.data_ptr()), 4, len(pos), None, 8, 3, shift, _lib.darr(L),
                                           _lib.iarr(N), x0, xn, ctypes.c_void_p(mesh.data_ptr()), None, 8,
-                                          ctypes.c_void_p(work.data_ptr()), nb, None))
+                                          ctypes.c_void_p(work.data_ptr()), nb, 1, None))
             torch.cuda.synchronize()
             np.testing.assert_allclose(mesh.cpu().numpy(), want[x0:x0 + xn], rtol=0, atol=1e-7 * want.max())
 
