@@ -3,7 +3,7 @@ Multi-GPU parity check, run under torchrun (one rank per GPU):
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
 Every rank holds a share of the particles; the distributed FFTPower (x-slab paint with ghost routing, all-to-all
 FFT, all-reduced histogram) must equal the single-GPU result computed on rank 0 from the gathered particles:
-mode counts bit-exact, P(k) to 1e-9 (f8) -- and, for the fixed-point tiled paint, the real field itself bit-exact.
+mode counts bit-exact, P(k) to 2e-8 (f8) -- and, for the fixed-point tiled paint, the real field itself bit-exact.
 """
 import os
 import sys
@@ -49,13 +49,15 @@ def main():
             r1 = FFTPower(mesh1, mode=c["mode"], **c["kw"])
             real1 = mesh1.compute(mode="real").numpy()
             full = np.concatenate(slabs, axis=0)
-            tol = 1e-9 if c["dtype"] == "f8" else 2e-5
+            # the tiled paint accumulates in fixed point with a quantum of 2^-31 max|w| per deposit, the ghost batches
+            # go through the f8 REDG path: agreement is a few quanta x sqrt(deposits per cell) (64 per particle for PCS)
+            tol = 2e-8 if c["dtype"] == "f8" else 2e-5
             ok = np.array_equal(r.power["modes"], r1.power["modes"])
             ok &= np.allclose(np.nan_to_num(r.power["power"].real), np.nan_to_num(r1.power["power"].real), rtol=tol,
                               atol=tol * np.nanmax(np.abs(r1.power["power"])))
             ok &= np.allclose(np.nan_to_num(r.power["k"]), np.nan_to_num(r1.power["k"]), rtol=1e-12)
             ok &= r.attrs["N1"] == r1.attrs["N1"] and abs(r.attrs["shotnoise"] - r1.attrs["shotnoise"]) < 1e-9 * r1.attrs["shotnoise"]
-            fieldtol = 1e-9 if c["dtype"] == "f8" else 3e-5
+            fieldtol = 2e-8 if c["dtype"] == "f8" else 3e-5
             ok &= np.allclose(full, real1, rtol=0, atol=fieldtol * np.abs(real1).max())
             if "poles" in c["kw"]:
                 ok &= np.allclose(np.nan_to_num(r.poles["power_2"].real), np.nan_to_num(r1.poles["power_2"].real),
