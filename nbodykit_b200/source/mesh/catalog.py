@@ -158,7 +158,7 @@ class CatalogMesh(MeshSource):
 
     def _host_streamed_paint(self):
         """Host-resident positions with unit weights on one GPU: copy in `paint_chunk_size`-sized pieces on a side
-        stream and scatter each piece (direct REDG path) while the next one is in flight, so the paint hides behind
+        stream and scatter each piece (usual tiled / direct dispatch, first piece clears the mesh) while the next one is in flight, so the paint hides behind
         the PCIe transfer instead of following it.  Returns None when the catalogue does not qualify."""
         pm = self.pm
         if pm.comm.size != 1:
@@ -184,9 +184,7 @@ class CatalogMesh(MeshSource):
         dev = current_device()
         main = torch.cuda.current_stream()
         side = torch.cuda.Stream(device=dev)
-        reals = [RealField(pm)] + ([RealField(pm)] if self.interlaced else [])
-        for r in reals:
-            r[...] = 0
+        reals = [RealField(pm)] + ([RealField(pm)] if self.interlaced else [])    # cleared by the first chunk's paint
         bufs = [torch.empty((chunk, 3), dtype=t.dtype, device=dev) for _ in range(2)]
         free = [torch.cuda.Event(), torch.cuda.Event()]
         for k, lo in enumerate(range(0, n, chunk)):
@@ -199,9 +197,9 @@ class CatalogMesh(MeshSource):
                 ready.record(side)
             main.wait_event(ready)
             if self.interlaced:
-                pm.paint_interlaced(b[:hi - lo], None, resampler, reals[0], reals[1], method='direct')
+                pm.paint_interlaced(b[:hi - lo], None, resampler, reals[0], reals[1], hold=(k > 0))
             else:
-                pm.paint(b[:hi - lo], mass=1.0, resampler=resampler, hold=True, out=reals[0], method='direct')
+                pm.paint(b[:hi - lo], mass=1.0, resampler=resampler, hold=(k > 0), out=reals[0])
             free[k % 2].record(main)
         if w * v != 1.0:
             for r in reals:
