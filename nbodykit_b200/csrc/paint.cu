@@ -555,6 +555,45 @@ __device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool act
     return __shfl_sync(mask, base, leader) + __popc(mask & ((1u << lane) - 1));
 }
 
+// float32 fast path of tile_of without the fallback: ok == false means "recompute exactly"
+template <int SUP, typename PT>
+__device__ __forceinline__ int tile_fast(const PT *x, const TileGeom &tg, const FastTile &ft, bool &ok) {
+    ok = sizeof(PT) == 4;
+    int c[3] = {0, 0, 0};
+    if (sizeof(PT) == 4) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float g = (float)x[d] * ft.sc[d];
+            if (WinOff<SUP>::A != 0.f) g += WinOff<SUP>::A;
+            float f = floorf(g);
+            ok = ok && (fabsf((g - f) - 0.5f) < ft.lim[d]);
+            c[d] = (int)f + WinOff<SUP>::B;
+            ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
+        }
+    }
+    return ok ? tile_from_cells(c, tg) : -1;
+}
+
+// Claim slots for the (up to) four particles of a thread's quad.  Coherent input: when every lane's quad lies in one
+// tile, the quad is claimed as a unit (then usually the whole warp as one ATOMS); otherwise particle by particle.
+// Returns the slot of the quad's first particle in `slot[0..3]`.  All 32 lanes must call.
+__device__ __forceinline__ void quad_claim(unsigned *hist, const int (&t)[4], unsigned (&slot)[4]) {
+    const bool uni = (t[0] == t[1]) && (t[1] == t[2]) && (t[2] == t[3]) && (t[0] >= 0);
+    if (__all_sync(0xffffffffu, uni)) {
+        const int lane = threadIdx.x & 31;
+        unsigned mask = __match_any_sync(0xffffffffu, t[0]);
+        int leader = __ffs(mask) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&hist[t[0]], 4u * (unsigned)__popc(mask));
+        base = __shfl_sync(mask, base, leader) + 4u * (unsigned)__popc(mask & ((1u << lane) - 1));
+#pragma unroll
+        for (int u = 0; u < 4; u++) slot[u] = base + u;
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) slot[u] = smem_claim(hist, t[u], t[u] >= 0);
+}
+
 template <int SUP, typename PT, typename MT>
 __global__ void __launch_bounds__(1024)
 k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
@@ -577,6 +616,7 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
     const uint4 zz = make_uint4(0, 0, 0, 0);
     for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // uniform trip count (warp collectives)
         const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        const int nv = (int)((e - i0) < 4 ? ((e - i0) < 0 ? 0 : (e - i0)) : 4);      // valid particles of my quad
         PT x[4][3];
         MT mv[4];
         load4(pos, i0, e, aligned, x);
@@ -586,13 +626,30 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
             zi += blockDim.x;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) mv[u] = (mass && i0 + u < e) ? mass[i0 + u] : (MT)0;
+        for (int u = 0; u < 4; u++) mv[u] = (mass && u < nv) ? mass[i0 + u] : (MT)0;
+        int t[4];
+        bool redo = false;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            bool in = i0 + u < e;
-            int t = in ? tile_of<SUP, PT>(x[u], pos, i0 + u, tg, ft) : -1;
-            smem_claim(s_hist, t, t >= 0);
-            if (mass && t >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
+            bool ok;
+            t[u] = tile_fast<SUP, PT>(x[u], tg, ft, ok);
+            redo = redo || (!ok && u < nv);
+        }
+        if (redo) {                                  // rare: near a cell boundary / outside the box / f8 positions
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                bool ok;
+                tile_fast<SUP, PT>(x[u], tg, ft, ok);
+                if (!ok && u < nv) t[u] = tile_of_exact<SUP, PT>(pos, i0 + u, tg);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (u >= nv) t[u] = -1;
+        unsigned slot[4];
+        quad_claim(s_hist, t, slot);
+        if (mass) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) if (t[u] >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
         }
     }
     for (; zi < zend; zi += blockDim.x) { zero1[zi] = zz; if (zero2) zero2[zi] = zz; }
@@ -641,19 +698,26 @@ k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int6
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
     for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // see k_tile_count_blk
         const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
+        const int nv = (int)((e - i0) < 4 ? ((e - i0) < 0 ? 0 : (e - i0)) : 4);
         PT x[4][3];
         MT mv[4];
         load4(pos, i0, e, aligned, x);
 #pragma unroll
-        for (int u = 0; u < 4; u++) mv[u] = (mass && i0 + u < e) ? mass[i0 + u] : (MT)0;
+        for (int u = 0; u < 4; u++) mv[u] = (mass && u < nv) ? mass[i0 + u] : (MT)0;
+        TileRec r[4];
+        int t[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            TileRec r = make_uint4(0, 0, 0, 0);
-            int t = (i0 + u < e) ? make_record<SUP, PT>(x[u], pos, i0 + u, tg, r) : -1;
-            unsigned dst = smem_claim(s_cur, t, t >= 0);
-            if (t >= 0) {
-                recs[dst] = r;
-                if (mass) smass[dst] = mv[u];
+            r[u] = make_uint4(0, 0, 0, 0);
+            t[u] = (u < nv) ? make_record<SUP, PT>(x[u], pos, i0 + u, tg, r[u]) : -1;
+        }
+        unsigned slot[4];
+        quad_claim(s_cur, t, slot);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (t[u] >= 0) {
+                recs[slot[u]] = r[u];
+                if (mass) smass[slot[u]] = mv[u];
             }
         }
     }
