@@ -278,7 +278,8 @@ template <> struct WinOff<3> { static constexpr float A = 0.5f; static constexpr
 template <> struct WinOff<4> { static constexpr float A = 0.0f; static constexpr int B = -1; };
 
 __device__ __forceinline__ int tile_from_cells(const int *c, const TileGeom &tg) {
-    if (tg.full) return ((c[0] / TILE) * tg.nt[1] + c[1] / TILE) * tg.nt[2] + c[2] / TILE;   // cells are in [0, n)
+    if (tg.full)   // cells are in [0, n)
+        return (int)((((unsigned)c[0] / TILE) * tg.nt[1] + (unsigned)c[1] / TILE) * tg.nt[2] + (unsigned)c[2] / TILE);
     int lx = slab_local(c[0], tg);
     if (lx < -tg.G || lx >= tg.gm.x_n) return -1;   // cannot touch my planes
     int tx = (lx + tg.G) / TILE, ty = c[1] / TILE, tz = c[2] / TILE;
@@ -356,10 +357,11 @@ __device__ __forceinline__ int make_record(const PT *x, const PT *__restrict__ p
 // coordinates of the 4 consecutive particles i0 .. i0+3 (i0 % 4 == 0): three 16-byte loads per thread for f4
 // positions when the array is 16-byte aligned (a warp then reads one contiguous 1536-byte run), scalar loads otherwise
 template <typename PT>
-__device__ __forceinline__ void load4(const PT *__restrict__ pos, int64_t i0, int64_t e, bool aligned, PT (&x)[4][3]) {
-    if (aligned && i0 + 3 < e) {
+__device__ __forceinline__ void load4(const PT *__restrict__ cpos, int j0, int nv, bool aligned, PT (&x)[4][3]) {
+    // cpos = first particle of the CTA's chunk, j0 = chunk-relative index of the quad (j0 % 4 == 0), nv = valid ones
+    if (aligned && nv == 4) {
         constexpr int NV = (int)(12 * sizeof(PT) / 16);
-        const uint4 *v = reinterpret_cast<const uint4 *>(pos + 3 * i0);
+        const uint4 *v = reinterpret_cast<const uint4 *>(cpos + 3 * j0);
         uint4 r[NV];
 #pragma unroll
         for (int k = 0; k < NV; k++) r[k] = v[k];
@@ -369,10 +371,10 @@ __device__ __forceinline__ void load4(const PT *__restrict__ pos, int64_t i0, in
     } else {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
-            bool in = i0 + u < e;
-            x[u][0] = in ? pos[3 * (i0 + u)] : (PT)0;
-            x[u][1] = in ? pos[3 * (i0 + u) + 1] : (PT)0;
-            x[u][2] = in ? pos[3 * (i0 + u) + 2] : (PT)0;
+            bool in = u < nv;
+            x[u][0] = in ? cpos[3 * (j0 + u)] : (PT)0;
+            x[u][1] = in ? cpos[3 * (j0 + u) + 1] : (PT)0;
+            x[u][2] = in ? cpos[3 * (j0 + u) + 2] : (PT)0;
         }
     }
 }
@@ -594,7 +596,7 @@ __device__ __forceinline__ void quad_claim(unsigned *hist, const int (&t)[4], un
     for (int u = 0; u < 4; u++) slot[u] = smem_claim(hist, t[u], t[u] >= 0);
 }
 
-template <int SUP, typename PT, typename MT>
+template <int SUP, typename PT, typename MT, bool HASM>
 __global__ void __launch_bounds__(1024)
 k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
                  FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, uint4 *__restrict__ zero1,
@@ -604,6 +606,9 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * chunk;
     const int64_t e = (b + chunk < n) ? b + chunk : n;
+    const int cn = e > b ? (int)(e - b) : 0;           // particles of this CTA (chunk-relative 32-bit indices below)
+    const PT *cpos = pos + 3 * b;
+    const MT *cmass = HASM ? mass + b : nullptr;
     float mx = 0.f;
     // 4 consecutive particles per thread and round: the coordinate loads are issued before the first is consumed (the
     // pass is bound by memory latency at 32 warps / SM) and, for aligned arrays, are 16-byte vectors
@@ -611,22 +616,26 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
     // hold=False: this pass also clears the mesh(es) -- zero_n 16-byte vectors each, a contiguous share per CTA, three
     // stores per round riding in the shadow of the (latency-bound) particle loads; the tile pass runs later in-stream
     const int64_t zper = zero1 ? (zero_n + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t zend = zero1 ? ((blockIdx.x + 1) * zper < zero_n ? (blockIdx.x + 1) * zper : zero_n) : 0;
-    int64_t zi = (int64_t)blockIdx.x * zper + threadIdx.x;
+    const int64_t zbeg = (int64_t)blockIdx.x * zper;
+    const int zcnt = zero1 ? (int)((zbeg + zper < zero_n ? zbeg + zper : zero_n) - zbeg) : 0;   // may be <= 0
+    uint4 *z1 = zero1 ? zero1 + zbeg : nullptr, *z2 = zero2 ? zero2 + zbeg : nullptr;
+    int zi = threadIdx.x;
     const uint4 zz = make_uint4(0, 0, 0, 0);
-    for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // uniform trip count (warp collectives)
-        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
-        const int nv = (int)((e - i0) < 4 ? ((e - i0) < 0 ? 0 : (e - i0)) : 4);      // valid particles of my quad
+    for (int base = 0; base < cn; base += 4 * (int)blockDim.x) {     // uniform trip count (warp collectives)
+        const int j0 = base + 4 * (int)threadIdx.x;
+        const int nv = min(4, max(0, cn - j0));                       // valid particles of my quad
         PT x[4][3];
         MT mv[4];
-        load4(pos, i0, e, aligned, x);
+        load4(cpos, j0, nv, aligned, x);
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            if (zi < zend) { zero1[zi] = zz; if (zero2) zero2[zi] = zz; }
+            if (zi < zcnt) { z1[zi] = zz; if (z2) z2[zi] = zz; }
             zi += blockDim.x;
         }
+        if (HASM) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) mv[u] = (mass && u < nv) ? mass[i0 + u] : (MT)0;
+            for (int u = 0; u < 4; u++) mv[u] = (u < nv) ? cmass[j0 + u] : (MT)0;
+        }
         int t[4];
         bool redo = false;
 #pragma unroll
@@ -640,20 +649,20 @@ k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_
             for (int u = 0; u < 4; u++) {
                 bool ok;
                 tile_fast<SUP, PT>(x[u], tg, ft, ok);
-                if (!ok && u < nv) t[u] = tile_of_exact<SUP, PT>(pos, i0 + u, tg);
+                if (!ok && u < nv) t[u] = tile_of_exact<SUP, PT>(cpos, j0 + u, tg);
             }
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) if (u >= nv) t[u] = -1;
         unsigned slot[4];
         quad_claim(s_hist, t, slot);
-        if (mass) {
+        if (HASM) {
 #pragma unroll
             for (int u = 0; u < 4; u++) if (t[u] >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
         }
     }
-    for (; zi < zend; zi += blockDim.x) { zero1[zi] = zz; if (zero2) zero2[zi] = zz; }
-    if (mass) {
+    for (; zi < zcnt; zi += blockDim.x) { z1[zi] = zz; if (z2) z2[zi] = zz; }
+    if (HASM) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(absmax_bits, __float_as_uint(mx));
@@ -683,7 +692,7 @@ k_tile_colscan(unsigned *__restrict__ blk, unsigned *__restrict__ counts, int nt
     counts[t] = run;
 }
 
-template <int SUP, typename PT, typename MT>
+template <int SUP, typename PT, typename MT, bool HASM>
 __global__ void __launch_bounds__(1024)
 k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
                    const unsigned *__restrict__ offsets, const unsigned *__restrict__ blk,
@@ -695,21 +704,26 @@ k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int6
     __syncthreads();
     const int64_t b = (int64_t)blockIdx.x * chunk;
     const int64_t e = (b + chunk < n) ? b + chunk : n;
+    const int cn = e > b ? (int)(e - b) : 0;
+    const PT *cpos = pos + 3 * b;
+    const MT *cmass = HASM ? mass + b : nullptr;
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
-    for (int64_t base = b; base < e; base += 4 * (int64_t)blockDim.x) {     // see k_tile_count_blk
-        const int64_t i0 = base + 4 * (int64_t)threadIdx.x;
-        const int nv = (int)((e - i0) < 4 ? ((e - i0) < 0 ? 0 : (e - i0)) : 4);
+    for (int base = 0; base < cn; base += 4 * (int)blockDim.x) {     // see k_tile_count_blk
+        const int j0 = base + 4 * (int)threadIdx.x;
+        const int nv = min(4, max(0, cn - j0));
         PT x[4][3];
         MT mv[4];
-        load4(pos, i0, e, aligned, x);
+        load4(cpos, j0, nv, aligned, x);
+        if (HASM) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) mv[u] = (mass && u < nv) ? mass[i0 + u] : (MT)0;
+            for (int u = 0; u < 4; u++) mv[u] = (u < nv) ? cmass[j0 + u] : (MT)0;
+        }
         TileRec r[4];
         int t[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             r[u] = make_uint4(0, 0, 0, 0);
-            t[u] = (u < nv) ? make_record<SUP, PT>(x[u], pos, i0 + u, tg, r[u]) : -1;
+            t[u] = (u < nv) ? make_record<SUP, PT>(x[u], cpos, j0 + u, tg, r[u]) : -1;
         }
         unsigned slot[4];
         quad_claim(s_cur, t, slot);
@@ -717,7 +731,7 @@ k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int6
         for (int u = 0; u < 4; u++) {
             if (t[u] >= 0) {
                 recs[slot[u]] = r[u];
-                if (mass) smass[slot[u]] = mv[u];
+                if (HASM) smass[slot[u]] = mv[u];
             }
         }
     }
@@ -993,19 +1007,26 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         const int G = NBK_SM_COUNT;
         const int64_t chunk = (((n + G - 1) / G) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
         NBK_CUDA(cudaMemsetAsync(work, 0, 256, s));        // header
-        NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-        k_tile_count_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax,
-                                                                  clear ? (uint4 *)mesh : nullptr, clear ? (uint4 *)mesh2 : nullptr,
-                                                                  (int64_t)(mesh_bytes / 16));
-        NBK_LAUNCHED();
-        k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);
-        NBK_LAUNCHED();
-        k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
-        NBK_LAUNCHED();
-        NBK_CUDA(cudaFuncSetAttribute(k_tile_scatter_blk<SUP, PT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_bytes));
-        k_tile_scatter_blk<SUP, PT, MT><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, offsets,
-                                                                    blk, spos, smass);
-        NBK_LAUNCHED();
+#define LAUNCH_BLK(HM)                                                                                               \
+        do {                                                                                                         \
+            NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)hist_bytes));                                                         \
+            k_tile_count_blk<SUP, PT, MT, HM><<<G, 1024, hist_bytes, s>>>(                                             \
+                (const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax, clear ? (uint4 *)mesh : nullptr,   \
+                clear ? (uint4 *)mesh2 : nullptr, (int64_t)(mesh_bytes / 16));                                       \
+            NBK_LAUNCHED();                                                                                          \
+            k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);                        \
+            NBK_LAUNCHED();                                                                                          \
+            k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);                                \
+            NBK_LAUNCHED();                                                                                          \
+            NBK_CUDA(cudaFuncSetAttribute(k_tile_scatter_blk<SUP, PT, MT, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)hist_bytes));                                                         \
+            k_tile_scatter_blk<SUP, PT, MT, HM><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, \
+                                                                          offsets, blk, spos, smass);                \
+            NBK_LAUNCHED();                                                                                          \
+        } while (0)
+        if (mass) LAUNCH_BLK(true); else LAUNCH_BLK(false);
+#undef LAUNCH_BLK
     } else {
         if (clear) {
             NBK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, s));
