@@ -741,6 +741,15 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
     }
     int B = (peer_host ? peer_run : 128) / (int)sizeof(C);
     if (B > 16) B = 16;
+    // experiment knobs: NBK_FFT_LINE_B (tile width), NBK_FFT_LINE_NT (threads per CTA: 128 / 256 / 512)
+    static int knob_b = -1, knob_nt = -1;
+    if (knob_b < 0) {
+        const char *e = getenv("NBK_FFT_LINE_B");
+        knob_b = e ? atoi(e) : 0;
+        e = getenv("NBK_FFT_LINE_NT");
+        knob_nt = e ? atoi(e) : 0;
+    }
+    if (!peer_host && (knob_b == 2 || knob_b == 4 || knob_b == 8 || knob_b == 16)) B = knob_b;
     while (B > 1 && ((size_t)N * (B + 2) * sizeof(C) > 220 * 1024 || B / 2 >= n_inner)) B >>= 1;
     size_t smem = (size_t)N * (B + 2) * sizeof(C);
     NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: N=%d does not fit in shared memory", N);
@@ -749,8 +758,13 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 4) per_sm = 4;
+    int nthreads = (per_sm == 1 && B >= 4) ? 512 : 256;
+    if (!peer_host && knob_nt == 128 && B >= 2 && B <= 8) nthreads = 128;
+    if (!peer_host && knob_nt == 512 && B >= 4) nthreads = 512;
+    if (nthreads == 128 && per_sm > 4) per_sm = 4;
+    if (nthreads == 256 && per_sm > 2) per_sm = 2;       // 128 registers per thread
+    if (nthreads == 512) per_sm = 1;
     int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
-    const int nthreads = (per_sm == 1 && B >= 4) ? 512 : 256;
     PeerPtrs<C> peers;
     for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
     const int n_per = peer_host ? N / P : N;
@@ -767,7 +781,12 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
                 ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
         }                                                                                                          \
         break;
-    if (nthreads == 512) {
+    if (nthreads == 128) {
+        switch (B) {
+            LAUNCH_RG(2, 128) LAUNCH_RG(4, 128) LAUNCH_RG(8, 128)
+            default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
+        }
+    } else if (nthreads == 512) {
         switch (B) {
             LAUNCH_RG(4, 512) LAUNCH_RG(8, 512) LAUNCH_RG(16, 512)
             default: nbk_set_error("fft_lines: internal tile width %d", B); return NBK_ERR_ARG;
