@@ -91,15 +91,17 @@ int nbk_paint_tiled(const void *pos, int pos_dtype, int64_t n, const void *mass,
                     int clear, void *stream);
 
 /* pm.decompose(pos, smoothing) + Layout.exchange (source/mesh/catalog.py:271-284) for the x-slab decomposition:
- * nbk_route_count writes, per particle, the bitmask of OTHER ranks (P <= 32) owning a plane within `smoothing`
- * cells of it (periodic), and accumulates per-destination counts (device uint64[P], zero first);
- * nbk_route_scatter compacts (pos[, mass]) of the flagged particles into per-destination segments of a send
+ * nbk_route_count finds the particles with a plane within `smoothing` cells (periodic) owned by ANOTHER rank
+ * (P <= 32) and appends one entry per such particle to `list` (device uint64[n] capacity, any order):
+ * index in the low 32 bits, destination bitmask in the high 32 bits.  `counts`: device uint64[P+1], zero first;
+ * [0..P) receive the per-destination counts, [P] the number of list entries.
+ * nbk_route_scatter copies (pos[, mass]) of the listed particles into per-destination segments of a send
  * buffer (`offsets`: device int64[P] exclusive scan of the counts; `cursor`: device uint64[P], zero first).
  * Local particles are never copied: each rank paints its own array plus what it receives. */
 int nbk_route_count(const void *pos, int pos_dtype, int64_t n, double smoothing, const double *boxsize_host,
-                    const int64_t *nmesh_host, int P, int rank, uint64_t *counts, uint32_t *flags, void *stream);
-int nbk_route_scatter(const void *pos, int pos_dtype, const void *mass, int mass_dtype, int64_t n, int P,
-                      const uint32_t *flags, const int64_t *offsets, uint64_t *cursor, void *send_pos,
+                    const int64_t *nmesh_host, int P, int rank, uint64_t *counts, uint64_t *list, void *stream);
+int nbk_route_scatter(const void *pos, int pos_dtype, const void *mass, int mass_dtype, const uint64_t *list,
+                      int64_t n_list, int P, const int64_t *offsets, uint64_t *cursor, void *send_pos,
                       void *send_mass, void *stream);
 
 /* leftmost stencil cell (wrapped) of every particle, [n][3] int32 -- the bit-exact part of the

@@ -105,15 +105,15 @@ _PEER_STAGE_CACHE = {}
 
 
 class SlabLayout(object):
-    """device-side routing plan (nbk_route_count): per-particle bitmask of REMOTE destination slabs.  Local
-    particles are never moved -- `route()` returns only what arrives from other ranks; `exchange()` keeps the
-    pmesh contract (local + received in one array)."""
+    """device-side routing plan (nbk_route_count): compact list of the particles with REMOTE destination slabs
+    (index | bitmask << 32).  Local particles are never moved -- `route()` returns only what arrives from other
+    ranks; `exchange()` keeps the pmesh contract (local + received in one array)."""
 
-    def __init__(self, pm, n, flags, sendcounts, recvcounts):
+    def __init__(self, pm, n, ghosts, sendcounts, recvcounts):
         self.pm = pm
         self.comm = pm.comm
         self.n = n
-        self.flags = flags
+        self.ghosts = ghosts
         self.sendcounts = sendcounts
         self.recvcounts = recvcounts
         self.sendlength = int(sum(sendcounts))
@@ -132,8 +132,8 @@ class SlabLayout(object):
             with stage("route_scatter"):
                 check(lib().nbk_route_scatter(_ptr(pos), F4 if pos.dtype == torch.float32 else F8, _ptr(mass),
                                               (F4 if mass.dtype == torch.float32 else F8) if mass is not None else F8,
-                                              self.n, P, _ptr(self.flags), _ptr(off), _ptr(cur), _ptr(spos), _ptr(smass),
-                                              _stream()), "nbk_route_scatter")
+                                              _ptr(self.ghosts), int(self.ghosts.shape[0]), P, _ptr(off), _ptr(cur), _ptr(spos),
+                                              _ptr(smass), _stream()), "nbk_route_scatter")
         rpos = torch.empty((nrecv, 3), dtype=pos.dtype, device=dev)
         with stage("route_alltoall"):
             self.comm.all_to_all_single(rpos, spos, list(self.recvcounts), list(self.sendcounts))
@@ -147,8 +147,9 @@ class SlabLayout(object):
         t = as_device_tensor(data) if not isinstance(data, torch.Tensor) else data
         P = self.comm.size
         parts, counts = [], []
+        gidx, gmask = self.ghosts & 0xffffffff, self.ghosts >> 32
         for r in range(P):
-            idx = torch.nonzero((self.flags >> r) & 1, as_tuple=False).reshape(-1)
+            idx = gidx[((gmask >> r) & 1) != 0]
             parts.append(t.index_select(0, idx))
             counts.append(int(idx.numel()))
         send = torch.cat(parts) if parts else t[:0]
@@ -339,15 +340,16 @@ class ParticleMesh(object):
         if pos.dtype not in (torch.float32, torch.float64):
             pos = pos.to(torch.float64)
         pos = pos.contiguous()
-        flags = torch.empty(n, dtype=torch.int32, device=pos.device)
-        counts = torch.zeros(P, dtype=torch.int64, device=pos.device)
+        ghosts = torch.empty(max(n, 1), dtype=torch.int64, device=pos.device)    # capacity; only the entries written are read
+        counts = torch.zeros(P + 1, dtype=torch.int64, device=pos.device)
         with stage("route_count"):
             check(lib().nbk_route_count(_ptr(pos), F4 if pos.dtype == torch.float32 else F8, n, smoothing, self._box_c,
-                                        self._nmesh_c, P, self.comm.rank, _ptr(counts), _ptr(flags), _stream()),
+                                        self._nmesh_c, P, self.comm.rank, _ptr(counts), _ptr(ghosts), _stream()),
                   "nbk_route_count")
-        sendcounts = [int(v) for v in counts.cpu().tolist()]
+        c = [int(v) for v in counts.cpu().tolist()]
+        sendcounts, nlist = c[:P], c[P]
         recvcounts = self.comm.alltoall_ints(sendcounts)
-        return SlabLayout(self, n, flags, sendcounts, recvcounts)
+        return SlabLayout(self, n, ghosts[:nlist], sendcounts, recvcounts)
 
     # ---- paint (source/mesh/catalog.py:287,295-296)
     def paint(self, pos, mass=1.0, resampler=None, transform=None, hold=False, gradient=None, layout=None, out=None,

@@ -428,10 +428,10 @@ def test_route_kernels_vs_numpy(cuda):
     Lb = _lib.lib()
     p = torch.from_numpy(pos).cuda(); m = torch.from_numpy(mass).cuda()
     for smoothing in (1.0, 1.5, 3.0):
-        flags = torch.empty(len(pos), dtype=torch.int32, device="cuda")
-        counts = torch.zeros(P, dtype=torch.int64, device="cuda")
+        ghosts = torch.empty(len(pos), dtype=torch.int64, device="cuda")
+        counts = torch.zeros(P + 1, dtype=torch.int64, device="cuda")
         _lib.check(Lb.nbk_route_count(ctypes.c_void_p(p.data_ptr()), 4, len(pos), smoothing, _lib.darr(L), _lib.iarr(N), P, rank,
-                                      ctypes.c_void_p(counts.data_ptr()), ctypes.c_void_p(flags.data_ptr()), None))
+                                      ctypes.c_void_p(counts.data_ptr()), ctypes.c_void_p(ghosts.data_ptr()), None))
         gx = pos[:, 0].astype("f8") * (N[0] / L[0])
         want = np.zeros(len(pos), dtype="i8")
         for c in range(-4, 5):
@@ -443,16 +443,20 @@ def test_route_kernels_vs_numpy(cuda):
             r = (cell % N[0]) // (N[0] // P)
             want |= np.where(ok, 1 << r, 0)
         want &= ~(1 << rank)
-        got = flags.cpu().numpy().astype("i8")
-        assert np.array_equal(got, want)
+        nl = int(counts[P].item())
+        ent = ghosts[:nl].cpu().numpy()
+        got = np.zeros(len(pos), dtype="i8")
+        assert len(np.unique(ent & 0xffffffff)) == nl                 # every travelling particle listed once
+        got[ent & 0xffffffff] = ent >> 32
+        assert np.array_equal(got, want) and nl == int((want != 0).sum())
         cnt = [int(((want >> r) & 1).sum()) for r in range(P)]
-        assert counts.cpu().tolist() == cnt and cnt[rank] == 0
+        assert counts[:P].cpu().tolist() == cnt and cnt[rank] == 0
         off = torch.tensor([0] + list(np.cumsum(cnt)[:-1]), dtype=torch.int64, device="cuda")
         cur = torch.zeros(P, dtype=torch.int64, device="cuda")
         spos = torch.empty((sum(cnt), 3), dtype=torch.float32, device="cuda")
         smass = torch.empty(sum(cnt), dtype=torch.float64, device="cuda")
-        _lib.check(Lb.nbk_route_scatter(ctypes.c_void_p(p.data_ptr()), 4, ctypes.c_void_p(m.data_ptr()), 8, len(pos), P,
-                                        ctypes.c_void_p(flags.data_ptr()), ctypes.c_void_p(off.data_ptr()),
+        _lib.check(Lb.nbk_route_scatter(ctypes.c_void_p(p.data_ptr()), 4, ctypes.c_void_p(m.data_ptr()), 8,
+                                        ctypes.c_void_p(ghosts.data_ptr()), nl, P, ctypes.c_void_p(off.data_ptr()),
                                         ctypes.c_void_p(cur.data_ptr()), ctypes.c_void_p(spos.data_ptr()),
                                         ctypes.c_void_p(smass.data_ptr()), None))
         torch.cuda.synchronize()
