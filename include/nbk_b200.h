@@ -104,6 +104,21 @@ int nbk_route_scatter(const void *pos, int pos_dtype, const void *mass, int mass
                       int64_t n_list, int P, const int64_t *offsets, uint64_t *cursor, void *send_pos,
                       void *send_mass, void *stream);
 
+/* RealField.readout(pos, resampler=, transform=, out=) (pmesh; called from algorithms/fftrecon.py:239-244): the gather
+ * transposed to nbk_paint -- out[p] (= or +=, `accumulate`) sum over the stencil of W * mesh[cell], same grid
+ * coordinate / window / slab semantics (planes outside [x_start, x_start+x_n) contribute nothing: per-rank partial
+ * sums).  out: device [n] of out_dtype. */
+int nbk_readout(const void *mesh, int mesh_dtype, const void *pos, int pos_dtype, int64_t n, int window, double shift,
+                const double *boxsize_host, const int64_t *nmesh_host, int64_t x_start, int64_t x_n, void *out,
+                int out_dtype, int accumulate, void *stream);
+
+/* reconstruction displacement modes (algorithms/fftrecon.py:213-230, Field.apply(kernel(d), kind='wavenumber')):
+ * out = i k_axis / k^2 * in * exp(-k^2 R^2 / 2) / (bias (1 + f/bias mu^2)), mu = k.los/|k|, the k = 0 mode -> 0.
+ * Out of place on the Hermitian-compressed field (same layout flags as nbk_compensate). */
+int nbk_recon_displacement(const void *in, void *out, int dtype, const int64_t *nmesh_host, const double *boxsize_host,
+                           int transposed, int64_t start, int64_t count, int axis, double R, double bias, double f,
+                           const double *los_host, void *stream);
+
 /* leftmost stencil cell (wrapped) of every particle, [n][3] int32 -- the bit-exact part of the
  * paint contract, exported for parity tests and for pm.decompose (catalog.py:271-273) */
 int nbk_cell_index(const void *pos, int pos_dtype, int64_t n, int window, double shift,

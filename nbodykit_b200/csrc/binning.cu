@@ -179,6 +179,75 @@ extern "C" int nbk_compensate(void *cplx, int dtype, int kind, const int64_t *nm
 }
 
 // ---------------------------------------------------------------------------------------------
+// reconstruction displacement transfer function (algorithms/fftrecon.py:213-230), kind='wavenumber':
+//   out = i k_d / k^2 * in * exp(-k^2 R^2 / 2) / (bias (1 + f/bias mu^2)),  mu = k.los / |k|,  k^2 = 0 -> 1
+// out of place (the density modes are reused for the three directions); f8 arithmetic, lanes along kz.
+// ---------------------------------------------------------------------------------------------
+struct ReconParams {
+    double kf[3];      // 2 pi / L_d
+    double los[3];
+    double R, bias, f;
+    int axis;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_recon_displacement(const T *__restrict__ in, T *__restrict__ out, SlabGeom g, ReconParams q) {
+    int64_t rows = (int64_t)g.count * g.D1;
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        int i0 = (int)(row / g.D1), i1 = (int)(row - (int64_t)i0 * g.D1);
+        int jx, jy, jz0;
+        slab_freqs(g, i0, i1, 0, jx, jy, jz0);
+        const double kx = (double)jx * q.kf[0], ky = (double)jy * q.kf[1];
+        const double kp2 = kx * kx + ky * ky;
+        const double lp = kx * q.los[0] + ky * q.los[1];
+        const T *pi = in + row * (int64_t)g.Nzc * 2;
+        T *po = out + row * (int64_t)g.Nzc * 2;
+        for (int k = threadIdx.x; k < g.Nzc; k += blockDim.x) {
+            const double kz = (double)nbk_freq(k, g.N[2]) * q.kf[2];
+            double k2 = kp2 + kz * kz;
+            if (k2 == 0.0) k2 = 1.0;
+            const double mu = (lp + kz * q.los[2]) / sqrt(k2);
+            const double frac = q.bias * (1.0 + q.f / q.bias * (mu * mu));
+            const double kd = q.axis == 0 ? kx : (q.axis == 1 ? ky : kz);
+            const double a = kd / k2 * (exp(-0.5 * k2 * (q.R * q.R)) / frac);
+            const double re = (double)pi[2 * k], im = (double)pi[2 * k + 1];
+            po[2 * k] = (T)(-a * im);          // i a (re + i im) = -a im + i a re
+            po[2 * k + 1] = (T)(a * re);
+        }
+    }
+}
+
+extern "C" int nbk_recon_displacement(const void *in, void *out, int dtype, const int64_t *nmesh, const double *box,
+                                      int transposed, int64_t start, int64_t count, int axis, double R, double bias,
+                                      double f, const double *los, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "recon_displacement: bad dtype %d", dtype);
+    NBK_CHECK_ARG(axis >= 0 && axis < 3, "recon_displacement: bad axis %d", axis);
+    NBK_CHECK_ARG(bias != 0.0, "recon_displacement: bias must be non-zero");
+    NBK_CHECK_ARG(in != nullptr && out != nullptr, "recon_displacement: null field");
+    SlabGeom g;
+    int rc = make_slab(nmesh, transposed, start, count, 1, g);
+    if (rc) return rc;
+    if (count == 0) return NBK_OK;
+    ReconParams q;
+    const double TWO_PI = 6.283185307179586476925286766559;
+    for (int d = 0; d < 3; d++) {
+        NBK_CHECK_ARG(box[d] > 0, "recon_displacement: bad BoxSize");
+        q.kf[d] = TWO_PI / box[d];
+        q.los[d] = los[d];
+    }
+    q.R = R; q.bias = bias; q.f = f; q.axis = axis;
+    cudaStream_t s = (cudaStream_t)stream;
+    int64_t rows = (int64_t)g.count * g.D1;
+    int grid = (int)(rows < (int64_t)NBK_SM_COUNT * 16 ? rows : (int64_t)NBK_SM_COUNT * 16);
+    int block = g.Nzc >= 256 ? 256 : 64;
+    if (dtype == NBK_F4) k_recon_displacement<float><<<grid, block, 0, s>>>((const float *)in, (float *)out, g, q);
+    else k_recon_displacement<double><<<grid, block, 0, s>>>((const double *)in, (double *)out, g, q);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // interlacing combine: s1 = 0.5 s1 + 0.5 s2 exp(0.5 i sum_d k_d H_d), k_d H_d = 2 pi j_d / N_d
 // ---------------------------------------------------------------------------------------------
 template <typename T>

@@ -1167,3 +1167,83 @@ extern "C" int nbk_cell_index(const void *pos, int pos_dtype, int64_t n, int win
     NBK_LAUNCHED();
     return NBK_OK;
 }
+
+// =============================================================================================
+// readout (gather): value_p = sum over the stencil of W * mesh[cell] -- pmesh `RealField.readout`, the transpose of the
+// scatter above (algorithms/fftrecon.py:239-244 reads the displacement field at the particle positions).  Same grid
+// coordinate, window and slab semantics as `scatter`: planes outside [x_start, x_start + x_n) contribute nothing,
+// so with x slabs every rank produces the partial sum of its own planes.  One particle per thread, support^3 cached
+// loads, f8 accumulation in the order (x, y, z) of the stencil.
+// =============================================================================================
+template <int SUP, typename PT, typename FT, typename OT>
+__global__ void __launch_bounds__(256)
+k_readout(const PT *__restrict__ pos, int64_t n, PaintGeom gm, double shift, const FT *__restrict__ mesh,
+          OT *__restrict__ out, int accumulate) {
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double g[3];
+        double acc = 0.0;
+        if (load_grid(pos, i, gm, shift, g)) {
+            long long i0[3];
+            double w[3][SUP];
+#pragma unroll
+            for (int d = 0; d < 3; d++) Window<SUP>::eval(g[d], i0[d], w[d]);
+            int iz[SUP], iy[SUP];
+#pragma unroll
+            for (int r = 0; r < SUP; r++) {
+                iz[r] = wrap(i0[2] + r, gm.n[2]);
+                iy[r] = wrap(i0[1] + r, gm.n[1]);
+            }
+#pragma unroll
+            for (int rx = 0; rx < SUP; rx++) {
+                int ix = wrap(i0[0] + rx, gm.n[0]) - gm.x_start;
+                if (ix < 0 || ix >= gm.x_n) continue;
+#pragma unroll
+                for (int ry = 0; ry < SUP; ry++) {
+                    double wxy = w[0][rx] * w[1][ry];
+                    int64_t row = ((int64_t)ix * gm.n[1] + iy[ry]) * gm.n[2];
+#pragma unroll
+                    for (int rz = 0; rz < SUP; rz++) acc += (wxy * w[2][rz]) * (double)mesh[row + iz[rz]];
+                }
+            }
+        }
+        out[i] = accumulate ? (OT)((double)out[i] + acc) : (OT)acc;
+    }
+}
+
+template <int SUP>
+static int launch_readout(const void *pos, int pos_dtype, int64_t n, const PaintGeom &gm, double shift, const void *mesh,
+                          int mesh_dtype, void *out, int out_dtype, int accumulate, cudaStream_t s) {
+    int g = nbk_grid_for(n, 256, 8);
+#define RO(PT, FT, OT) k_readout<SUP, PT, FT, OT><<<g, 256, 0, s>>>((const PT *)pos, n, gm, shift, (const FT *)mesh, (OT *)out, accumulate)
+    const bool pf = pos_dtype == NBK_F4, ff = mesh_dtype == NBK_F4, of = out_dtype == NBK_F4;
+    if (pf) { if (ff) { if (of) RO(float, float, float); else RO(float, float, double); }
+              else { if (of) RO(float, double, float); else RO(float, double, double); } }
+    else { if (ff) { if (of) RO(double, float, float); else RO(double, float, double); }
+           else { if (of) RO(double, double, float); else RO(double, double, double); } }
+#undef RO
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+extern "C" int nbk_readout(const void *mesh, int mesh_dtype, const void *pos, int pos_dtype, int64_t n, int window,
+                           double shift, const double *box, const int64_t *nmesh, int64_t x_start, int64_t x_n,
+                           void *out, int out_dtype, int accumulate, void *stream) {
+    NBK_CHECK_ARG(pos_dtype == NBK_F4 || pos_dtype == NBK_F8, "readout: bad pos dtype %d", pos_dtype);
+    NBK_CHECK_ARG(mesh_dtype == NBK_F4 || mesh_dtype == NBK_F8, "readout: bad mesh dtype %d", mesh_dtype);
+    NBK_CHECK_ARG(out_dtype == NBK_F4 || out_dtype == NBK_F8, "readout: bad out dtype %d", out_dtype);
+    NBK_CHECK_ARG(n >= 0 && mesh != nullptr && (n == 0 || out != nullptr), "readout: null mesh / out or negative count");
+    PaintGeom gm;
+    int rc = make_geom(box, nmesh, x_start, x_n, gm);
+    if (rc) return rc;
+    if (n == 0) return NBK_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (window) {
+        case NBK_WINDOW_NNB: return launch_readout<1>(pos, pos_dtype, n, gm, shift, mesh, mesh_dtype, out, out_dtype, accumulate, s);
+        case NBK_WINDOW_CIC: return launch_readout<2>(pos, pos_dtype, n, gm, shift, mesh, mesh_dtype, out, out_dtype, accumulate, s);
+        case NBK_WINDOW_TSC: return launch_readout<3>(pos, pos_dtype, n, gm, shift, mesh, mesh_dtype, out, out_dtype, accumulate, s);
+        case NBK_WINDOW_PCS: return launch_readout<4>(pos, pos_dtype, n, gm, shift, mesh, mesh_dtype, out, out_dtype, accumulate, s);
+    }
+    nbk_set_error("readout: unknown window %d", window);
+    return NBK_ERR_ARG;
+}

@@ -700,6 +700,42 @@ class RealField(Field):
     def dtype(self):
         return self.pm.dtype
 
+    def readout(self, pos, out=None, resampler=None, transform=None, gradient=None, layout=None):
+        """values of the field at `pos` through the window (pmesh `RealField.readout`, used by
+        algorithms/fftrecon.py:239-244): out[p] = sum_stencil W * field[cell].  Device tensors in -> device tensor
+        out, numpy in -> numpy out.  Single-GPU meshes only (x slabs would need the partial sums exchanged)."""
+        pm = self.pm
+        if gradient is not None:
+            raise NotImplementedError("gradient readout is not part of the FFTPower path")
+        if pm.comm.size > 1:
+            raise NotImplementedError("readout on a slab-decomposed mesh (comm.size > 1) is not implemented")
+        res = pm.resampler if resampler is None else _window.FindResampler(resampler)
+        if res.code is None:
+            raise NotImplementedError("no CUDA readout kernel for window '%s'" % res.name)
+        shift = 0.0
+        if transform is not None:
+            shift = float(numpy.atleast_1d(transform.translate - pm.affine.translate).ravel()[0])
+        was_numpy = not isinstance(pos, torch.Tensor)
+        p = as_device_tensor(pos, device=self.value.device)
+        if p.dtype not in (torch.float32, torch.float64):
+            p = p.to(torch.float64)
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise ValueError("readout: position must have shape (n, 3)")
+        p = p.contiguous()
+        n = int(p.shape[0])
+        o = out
+        if o is None or not isinstance(o, torch.Tensor):
+            o = torch.empty(n, dtype=_TORCH_REAL[pm.typestr], device=p.device)
+        if o.dtype not in (torch.float32, torch.float64) or not o.is_contiguous() or o.shape[0] != n:
+            raise ValueError("readout: `out` must be a contiguous float32/float64 array of length n")
+        check(lib().nbk_readout(_ptr(self.value), _CODE[pm.typestr], _ptr(p), F4 if p.dtype == torch.float32 else F8, n,
+                                res.code, shift, pm._box_c, pm._nmesh_c, pm.x_start, pm.x_n, _ptr(o),
+                                F4 if o.dtype == torch.float32 else F8, 0, _stream()), "nbk_readout")
+        if out is not None and not isinstance(out, torch.Tensor):
+            out[...] = o.cpu().numpy()
+            return out
+        return o.cpu().numpy() if was_numpy else o
+
     def r2c(self, out=None, scale=1.0):
         """forward FFT, normalised by 1/prod(N).  out=Ellipsis has no in-place meaning here (the
         transform is out of place); the real buffer stays valid.  `scale` (extension) multiplies the
