@@ -200,6 +200,77 @@ class FFTPower(FFTBase):
         return power, poles
 
 
+class ProjectedFFTPower(FFTBase):
+    """
+    Power spectrum of a field projected (summed) over one or two axes of the box -- the "1d" / "2d" power of
+    Lyman-alpha forest or lensing maps (fftpower.py:361-505).  The 3-D work (paint, r2c, Fourier-space actions, c2r
+    and the projection) runs on the device; what is left is a 1-D / 2-D FFT of Nmesh or Nmesh^2 numbers, done on
+    the host with numpy exactly as the reference does.  Results: `.edges`, `.power` (BinnedStatistic with k, power,
+    modes), computed in __init__.
+    """
+    logger = logging.getLogger('ProjectedFFTPower')
+
+    def __init__(self, first, Nmesh=None, BoxSize=None, second=None, axes=(0, 1), dk=None, kmin=0.):
+        FFTBase.__init__(self, first, second, Nmesh, BoxSize)
+        assert len(axes) in (1, 2), "length of ``axes`` in ProjectedFFTPower should be 1 or 2"
+        if dk is None:
+            dk = 2 * numpy.pi / self.attrs['BoxSize'].min()
+        self.attrs['dk'] = dk
+        self.attrs['kmin'] = kmin
+        self.attrs['axes'] = axes
+        self.run()
+
+    def _projected_modes(self, source):
+        """rfftn of the real field summed over the axes that are not kept, normalised by prod(Nmesh)"""
+        c = source.compute(Nmesh=self.attrs['Nmesh'], mode='complex')
+        r = c.c2r().preview(axes=self.attrs['axes'])
+        return numpy.fft.rfftn(r) / self.attrs['Nmesh'].prod()
+
+    def run(self):
+        c1 = self._projected_modes(self.first)
+        c2 = c1 if self.first is self.second else self._projected_modes(self.second)
+        pk = c1 * c2.conj()
+        pk.flat[0] = 0
+        axes = list(self.attrs['axes'])
+        shape = numpy.array([self.attrs['Nmesh'][i] for i in axes], dtype='int')
+        boxsize = numpy.array([self.attrs['BoxSize'][i] for i in axes])
+        # broadcastable wavenumbers of the kept axes (the last one is Hermitian-compressed)
+        k = []
+        for d, (N, L) in enumerate(zip(shape, boxsize)):
+            kd = numpy.fft.fftfreq(N, 1. / (N * 2 * numpy.pi / L))[:pk.shape[d]]
+            sh = [1] * len(shape)
+            sh[d] = -1
+            k.append(kd.reshape(sh))
+        kmag = sum(ki ** 2 for ki in k) ** 0.5
+        # Hermitian weights along the compressed axis: 2, except its first and last plane
+        W = numpy.empty(pk.shape, dtype='f4')
+        W[...] = 2.0
+        W[..., 0] = 1.0
+        W[..., -1] = 1.0
+        dk, kmin = self.attrs['dk'], self.attrs['kmin']
+        kedges = numpy.arange(kmin, numpy.pi * self.attrs['Nmesh'][axes].min() / self.attrs['BoxSize'][axes].max() + dk / 2, dk)
+        nb = len(kedges) + 1
+        dig = numpy.digitize(kmag.flat, kedges)
+        xsum = numpy.bincount(dig, weights=(W * kmag).flat, minlength=nb).astype('f8')
+        Psum = numpy.bincount(dig, weights=(W * pk.real).flat, minlength=nb) \
+            + 1j * numpy.bincount(dig, weights=(W * pk.imag).flat, minlength=nb)
+        Nsum = numpy.bincount(dig, weights=W.flat, minlength=nb).astype('f8')
+        power = numpy.empty(len(kedges) - 1, dtype=[('k', 'f8'), ('power', 'c16'), ('modes', 'f8')])
+        with numpy.errstate(invalid='ignore', divide='ignore'):
+            power['k'] = (xsum / Nsum)[1:-1]
+            power['power'] = (Psum / Nsum)[1:-1] * boxsize.prod()     # dimension is 'volume' of the kept axes
+            power['modes'] = Nsum[1:-1]
+        self.edges = kedges
+        self.power = BinnedStatistic(['k'], [self.edges], power)
+
+    def __getstate__(self):
+        return dict(edges=self.edges, power=self.power.data, attrs=self.attrs)
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self.power = BinnedStatistic(['k'], [self.edges], self.power)
+
+
 def _los_coord_mode(los, coord_dtype):
     """which arithmetic `MeshSlab.mu` runs in (meshtools.py:136): with float32 coordinate arrays,
     Python-number los components keep mu in float32, NumPy float64 components promote it to float64

@@ -700,6 +700,29 @@ class RealField(Field):
     def dtype(self):
         return self.pm.dtype
 
+    def preview(self, Nmesh=None, axes=None):
+        """the field, optionally summed over the axes NOT listed in `axes`, as a numpy array on every rank (pmesh
+        `Field.preview`; fftpower.py:432).  The reduction over dropped axes runs on the device; only the projected
+        array crosses PCIe."""
+        pm = self.pm
+        if Nmesh is not None and any(numpy.ones(3, 'i8') * Nmesh != pm.Nmesh):
+            raise NotImplementedError("preview at a different resolution is not implemented")
+        if axes is None:
+            axes = [0, 1, 2]
+        axes = [axes] if numpy.isscalar(axes) else list(axes)
+        drop = tuple(a for a in range(3) if a not in axes)
+        local = self.value.sum(dim=drop, dtype=torch.float64) if drop else self.value
+        local = local.cpu().numpy()
+        if pm.comm.size > 1:
+            if 0 in axes:                  # x is kept: concatenate the slabs
+                local = numpy.concatenate(pm.comm.allgather(local), axis=0)
+            else:                          # x is summed over: add the slabs
+                local = pm.comm.allreduce(local)
+        kept = [a for a in range(3) if a in axes]      # current axis order (ascending)
+        if axes != kept:
+            local = local.transpose([kept.index(a) for a in axes])
+        return local
+
     def readout(self, pos, out=None, resampler=None, transform=None, gradient=None, layout=None):
         """values of the field at `pos` through the window (pmesh `RealField.readout`, used by
         algorithms/fftrecon.py:239-244): out[p] = sum_stencil W * field[cell].  Device tensors in -> device tensor

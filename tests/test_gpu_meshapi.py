@@ -139,3 +139,36 @@ def test_fftcorr_vs_oracle(cuda, mode, poles):
         np.testing.assert_allclose(np.nan_to_num(r.poles['corr_2'].real), np.nan_to_num(pres[1][1].real), rtol=1e-6,
                                    atol=1e-7 * scale)
     assert r.attrs['N1'] == len(pos)
+
+
+def test_projected_fftpower_reference_assertions(cuda):
+    """algorithms/tests/test_fftpower.py:137-155 re-run: zero mode cleared, projected power consistent with the 3-D
+    power; plus a numpy restatement of the projection from the oracle's field"""
+    from nbodykit_b200.lab import UniformCatalog, FFTPower, ProjectedFFTPower
+    source = UniformCatalog(nbar=3e-4, BoxSize=512., seed=42)
+    Nmesh = 64
+    rp1 = ProjectedFFTPower(source, Nmesh=Nmesh, axes=[1])
+    assert rp1.power['power'][0] == 0
+    rp2 = ProjectedFFTPower(source, Nmesh=Nmesh, axes=[0, 1])
+    assert rp2.power['power'][0] == 0
+    rf = FFTPower(source, Nmesh=Nmesh, mode='1d')
+    L = source.attrs['BoxSize'][0]
+    np.testing.assert_allclose(rp1.power['power'][1:].mean() * L ** 2, rf.power['power'][1:].mean(), rtol=2 * (Nmesh / 2) ** -0.5)
+    np.testing.assert_allclose(rp2.power['power'][1:].mean() * L, rf.power['power'][1:].mean(),
+                               rtol=2 * (Nmesh ** 2 / 2) ** -0.5 * 10)
+    # numpy restatement from the oracle's compensated field
+    pos, _ = po.uniform_catalog(3e-4, 512., 42)
+    real, _ = po.paint_field(pos, Nmesh, 512., 'cic', dtype='f8')
+    c = po.compensate('CompensateCICShotnoise', po.k_coords(Nmesh, 512., 'f4', kind='circular'), po.r2c(real))
+    r = po.c2r(c, Nmesh).sum(axis=2)                       # keep axes (0, 1)
+    cp = np.fft.rfftn(r) / Nmesh ** 3
+    pk = (cp * cp.conj()).real
+    pk.flat[0] = 0
+    kx = np.fft.fftfreq(Nmesh, 1. / (Nmesh * 2 * np.pi / 512.))
+    kmag = np.sqrt(kx[:, None] ** 2 + kx[None, :Nmesh // 2 + 1] ** 2)
+    W = np.full(pk.shape, 2.0); W[..., 0] = 1.0; W[..., -1] = 1.0
+    dig = np.digitize(kmag.flat, rp2.edges)
+    nb = len(rp2.edges) + 1
+    want = (np.bincount(dig, weights=(W * pk).flat, minlength=nb) / np.bincount(dig, weights=W.flat, minlength=nb))[1:-1] * 512. ** 2
+    np.testing.assert_allclose(rp2.power['power'].real, want, rtol=1e-6, atol=1e-9 * np.nanmax(want))
+    assert np.array_equal(rp2.power['modes'], np.bincount(dig, weights=W.flat, minlength=nb)[1:-1])
