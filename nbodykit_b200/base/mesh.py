@@ -161,24 +161,10 @@ class MeshSource(object):
         return var
 
     def preview(self, axes=None, Nmesh=None, root=0):
-        """gather the real field on the host as a numpy array (optionally projected onto `axes`)"""
+        """the real field as a numpy array on the host, optionally summed over the axes not in `axes`
+        (base/mesh.py:340-365); the projection runs on the device"""
         field = self.to_field(mode='real')
-        if Nmesh is not None and any(numpy.ones(3, 'i8') * Nmesh != self.pm.Nmesh):
-            raise NotImplementedError("preview at reduced resolution is not implemented")
-        import torch
-        local = field.value
-        if self.comm.size > 1:
-            parts = self.comm.allgather(local.cpu().numpy())
-            full = numpy.concatenate(parts, axis=0)
-        else:
-            full = local.cpu().numpy()
-        if axes is not None:
-            axes = [axes] if numpy.isscalar(axes) else list(axes)
-            drop = tuple(a for a in range(3) if a not in axes)
-            full = full.sum(axis=drop)
-            if axes != sorted(axes):
-                full = full.transpose(numpy.argsort(numpy.argsort(axes)))
-        return full
+        return field.preview(Nmesh=Nmesh, axes=axes)
 
     def save(self, output, dataset='Field', mode='real'):
         raise NotImplementedError("bigfile output is outside the B200 FFTPower path (SURVEY.md §8f); "
