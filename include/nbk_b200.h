@@ -96,13 +96,15 @@ int nbk_paint_tiled(const void *pos, int pos_dtype, int64_t n, const void *mass,
  * index in the low 32 bits, destination bitmask in the high 32 bits.  `counts`: device uint64[P+1], zero first;
  * [0..P) receive the per-destination counts, [P] the number of list entries.
  * nbk_route_scatter copies (pos[, mass]) of the listed particles into per-destination segments of a send
- * buffer (`offsets`: device int64[P] exclusive scan of the counts; `cursor`: device uint64[P], zero first).
+ * buffer (`offsets`: device int64[P] exclusive scan of the counts; `cursor`: device uint64[P], zero first);
+ * `send_index` (optional, device int64[sum counts]) receives the source row of every sent row, so that per-row
+ * results computed by the destination (readout partial sums) can be added back after the return all-to-all.
  * Local particles are never copied: each rank paints its own array plus what it receives. */
 int nbk_route_count(const void *pos, int pos_dtype, int64_t n, double smoothing, const double *boxsize_host,
                     const int64_t *nmesh_host, int P, int rank, uint64_t *counts, uint64_t *list, void *stream);
 int nbk_route_scatter(const void *pos, int pos_dtype, const void *mass, int mass_dtype, const uint64_t *list,
                       int64_t n_list, int P, const int64_t *offsets, uint64_t *cursor, void *send_pos,
-                      void *send_mass, void *stream);
+                      void *send_mass, int64_t *send_index, void *stream);
 
 /* RealField.readout(pos, resampler=, transform=, out=) (pmesh; called from algorithms/fftrecon.py:239-244): the gather
  * transposed to nbk_paint -- out[p] (= or +=, `accumulate`) sum over the stencil of W * mesh[cell], same grid

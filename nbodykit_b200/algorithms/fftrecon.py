@@ -59,8 +59,6 @@ class FFTRecon(MeshSource):
         self.attrs['revert_rsd_random'] = bool(revert_rsd_random)
         self.data = data
         self.ran = ran
-        if comm.size > 1:
-            raise NotImplementedError("FFTRecon on more than one GPU needs the distributed readout (not implemented)")
         if self.comm.rank == 0:
             self.logger.info("Reconstruction for bias=%g, f=%g, smoothing R=%g los=%s" % (bias, f, R, str(los)))
             self.logger.info("Reconstruction scheme = %s" % scheme)
@@ -86,6 +84,12 @@ class FFTRecon(MeshSource):
         if s is not None:
             pos = pos - s
         delta = pm.paint(pos, mass=1.0, resampler='cic', hold=False)
+        if pm.comm.size > 1:
+            # x slabs: the local scatter keeps the planes this rank owns; rows reaching other slabs travel there
+            lay = pm.decompose(pos, smoothing=1.0)
+            rpos, _ = lay.route(pos, None)
+            if rpos.shape[0]:
+                pm.paint(rpos, mass=1.0, resampler='cic', hold=True, out=delta)
         nbar = 1.0 * cat.csize / pm.Nmesh.prod()
         delta /= nbar
         return delta

@@ -72,7 +72,7 @@ template <typename PT, typename MT>
 __global__ void __launch_bounds__(256)
 k_route_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, const unsigned long long *__restrict__ list,
                 int64_t n_list, int P, const long long *__restrict__ offsets, unsigned long long *__restrict__ cursor,
-                PT *__restrict__ spos, MT *__restrict__ smass) {
+                PT *__restrict__ spos, MT *__restrict__ smass, long long *__restrict__ sindex) {
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t nround = ((n_list + stride - 1) / stride) * stride;
     const int lane = threadIdx.x & 31;
@@ -92,6 +92,7 @@ k_route_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, const u
                 spos[3 * dst + 1] = pos[3 * i + 1];
                 spos[3 * dst + 2] = pos[3 * i + 2];
                 if (mass) smass[dst] = mass[i];
+                if (sindex) sindex[dst] = (long long)i;      // where the row came from (for results travelling back)
             }
         }
     }
@@ -118,7 +119,7 @@ extern "C" int nbk_route_count(const void *pos, int pos_dtype, int64_t n, double
 
 extern "C" int nbk_route_scatter(const void *pos, int pos_dtype, const void *mass, int mass_dtype, const uint64_t *list,
                                  int64_t n_list, int P, const int64_t *offsets, uint64_t *cursor, void *send_pos,
-                                 void *send_mass, void *stream) {
+                                 void *send_mass, int64_t *send_index, void *stream) {
     NBK_CHECK_ARG(pos_dtype == NBK_F4 || pos_dtype == NBK_F8, "route_scatter: bad pos dtype %d", pos_dtype);
     NBK_CHECK_ARG(mass == nullptr || mass_dtype == NBK_F4 || mass_dtype == NBK_F8, "route_scatter: bad mass dtype");
     if (n_list <= 0) return NBK_OK;
@@ -126,7 +127,7 @@ extern "C" int nbk_route_scatter(const void *pos, int pos_dtype, const void *mas
     int grid = nbk_grid_for(n_list, 256, 8);
     const long long *off = (const long long *)offsets;
     unsigned long long *cur = (unsigned long long *)cursor;
-#define RS(PT, MT) k_route_scatter<PT, MT><<<grid, 256, 0, s>>>((const PT *)pos, (const MT *)mass, (const unsigned long long *)list, n_list, P, off, cur, (PT *)send_pos, (MT *)send_mass)
+#define RS(PT, MT) k_route_scatter<PT, MT><<<grid, 256, 0, s>>>((const PT *)pos, (const MT *)mass, (const unsigned long long *)list, n_list, P, off, cur, (PT *)send_pos, (MT *)send_mass, (long long *)send_index)
     bool pf = pos_dtype == NBK_F4, mf = (mass != nullptr && mass_dtype == NBK_F4);
     if (pf && mf) RS(float, float); else if (pf) RS(float, double); else if (mf) RS(double, float); else RS(double, double);
 #undef RS

@@ -119,13 +119,15 @@ class SlabLayout(object):
         self.sendlength = int(sum(sendcounts))
         self.recvlength = n + int(sum(recvcounts))     # pmesh semantics: what this rank will paint
 
-    def route(self, pos, mass=None):
-        """(received positions, received masses | None): copies for remote slabs travel in one all-to-all per column"""
+    def route(self, pos, mass=None, want_index=False):
+        """(received positions, received masses | None): copies for remote slabs travel in one all-to-all per column.
+        want_index=True additionally returns the source row of every SENT row (for `gather_back`)."""
         P = self.comm.size
         dev = pos.device
         nsend, nrecv = int(sum(self.sendcounts)), int(sum(self.recvcounts))
         spos = torch.empty((nsend, 3), dtype=pos.dtype, device=dev)
         smass = torch.empty(nsend, dtype=mass.dtype, device=dev) if mass is not None else None
+        sidx = torch.empty(nsend, dtype=torch.int64, device=dev) if want_index else None
         if nsend:
             off = torch.tensor([0] + list(numpy.cumsum(self.sendcounts)[:-1]), dtype=torch.int64, device=dev)
             cur = torch.zeros(P, dtype=torch.int64, device=dev)
@@ -133,7 +135,7 @@ class SlabLayout(object):
                 check(lib().nbk_route_scatter(_ptr(pos), F4 if pos.dtype == torch.float32 else F8, _ptr(mass),
                                               (F4 if mass.dtype == torch.float32 else F8) if mass is not None else F8,
                                               _ptr(self.ghosts), int(self.ghosts.shape[0]), P, _ptr(off), _ptr(cur), _ptr(spos),
-                                              _ptr(smass), _stream()), "nbk_route_scatter")
+                                              _ptr(smass), _ptr(sidx), _stream()), "nbk_route_scatter")
         rpos = torch.empty((nrecv, 3), dtype=pos.dtype, device=dev)
         with stage("route_alltoall"):
             self.comm.all_to_all_single(rpos, spos, list(self.recvcounts), list(self.sendcounts))
@@ -141,7 +143,19 @@ class SlabLayout(object):
             if mass is not None:
                 rmass = torch.empty(nrecv, dtype=mass.dtype, device=dev)
                 self.comm.all_to_all_single(rmass, smass, list(self.recvcounts), list(self.sendcounts))
+        if want_index:
+            return rpos, rmass, sidx
         return rpos, rmass
+
+    def gather_back(self, values, sidx, out):
+        """reverse of `route` for per-row results: `values[k]` was computed by the destination for the k-th row it
+        received; they travel back and are ADDED to out[source row] (pmesh `layout.gather(mode='sum')`)"""
+        nsend = int(sum(self.sendcounts))
+        back = torch.empty(nsend, dtype=values.dtype, device=values.device)
+        self.comm.all_to_all_single(back, values.contiguous(), list(self.sendcounts), list(self.recvcounts))
+        if nsend:
+            out.index_add_(0, sidx, back.to(out.dtype))
+        return out
 
     def exchange(self, data):
         t = as_device_tensor(data) if not isinstance(data, torch.Tensor) else data
@@ -726,12 +740,10 @@ class RealField(Field):
     def readout(self, pos, out=None, resampler=None, transform=None, gradient=None, layout=None):
         """values of the field at `pos` through the window (pmesh `RealField.readout`, used by
         algorithms/fftrecon.py:239-244): out[p] = sum_stencil W * field[cell].  Device tensors in -> device tensor
-        out, numpy in -> numpy out.  Single-GPU meshes only (x slabs would need the partial sums exchanged)."""
+        out, numpy in -> numpy out.  With x slabs the partial sums of the owning ranks are exchanged and added."""
         pm = self.pm
         if gradient is not None:
             raise NotImplementedError("gradient readout is not part of the FFTPower path")
-        if pm.comm.size > 1:
-            raise NotImplementedError("readout on a slab-decomposed mesh (comm.size > 1) is not implemented")
         res = pm.resampler if resampler is None else _window.FindResampler(resampler)
         if res.code is None:
             raise NotImplementedError("no CUDA readout kernel for window '%s'" % res.name)
@@ -751,9 +763,24 @@ class RealField(Field):
             o = torch.empty(n, dtype=_TORCH_REAL[pm.typestr], device=p.device)
         if o.dtype not in (torch.float32, torch.float64) or not o.is_contiguous() or o.shape[0] != n:
             raise ValueError("readout: `out` must be a contiguous float32/float64 array of length n")
-        check(lib().nbk_readout(_ptr(self.value), _CODE[pm.typestr], _ptr(p), F4 if p.dtype == torch.float32 else F8, n,
-                                res.code, shift, pm._box_c, pm._nmesh_c, pm.x_start, pm.x_n, _ptr(o),
-                                F4 if o.dtype == torch.float32 else F8, 0, _stream()), "nbk_readout")
+        def gather(pp, oo):
+            check(lib().nbk_readout(_ptr(self.value), _CODE[pm.typestr], _ptr(pp), F4 if pp.dtype == torch.float32 else F8,
+                                    int(pp.shape[0]), res.code, shift, pm._box_c, pm._nmesh_c, pm.x_start, pm.x_n, _ptr(oo),
+                                    F4 if oo.dtype == torch.float32 else F8, 0, _stream()), "nbk_readout")
+        if pm.comm.size == 1:
+            gather(p, o)
+        else:
+            # x slabs: every rank sums its own planes for its local rows and for the rows whose stencil reaches it
+            # (the ghost list of decompose); the partial sums travel back and are added (layout.gather, mode='sum')
+            lay = layout if isinstance(layout, SlabLayout) else pm.decompose(p, smoothing=0.5 * res.support + abs(shift))
+            rpos, _, sidx = lay.route(p, None, want_index=True)
+            acc = torch.empty(n, dtype=torch.float64, device=p.device)
+            gather(p, acc)
+            part = torch.empty(int(rpos.shape[0]), dtype=torch.float64, device=p.device)
+            if rpos.shape[0]:
+                gather(rpos.contiguous(), part)
+            lay.gather_back(part, sidx, acc)
+            o.copy_(acc.to(o.dtype))
         if out is not None and not isinstance(out, torch.Tensor):
             out[...] = o.cpu().numpy()
             return out

@@ -455,12 +455,15 @@ def test_route_kernels_vs_numpy(cuda):
         cur = torch.zeros(P, dtype=torch.int64, device="cuda")
         spos = torch.empty((sum(cnt), 3), dtype=torch.float32, device="cuda")
         smass = torch.empty(sum(cnt), dtype=torch.float64, device="cuda")
+        sidx = torch.empty(sum(cnt), dtype=torch.int64, device="cuda")
         _lib.check(Lb.nbk_route_scatter(ctypes.c_void_p(p.data_ptr()), 4, ctypes.c_void_p(m.data_ptr()), 8,
                                         ctypes.c_void_p(ghosts.data_ptr()), nl, P, ctypes.c_void_p(off.data_ptr()),
                                         ctypes.c_void_p(cur.data_ptr()), ctypes.c_void_p(spos.data_ptr()),
-                                        ctypes.c_void_p(smass.data_ptr()), None))
+                                        ctypes.c_void_p(smass.data_ptr()), ctypes.c_void_p(sidx.data_ptr()), None))
         torch.cuda.synchronize()
         sp, sm = spos.cpu().numpy(), smass.cpu().numpy()
+        # the source-row column points back at the rows that were copied
+        assert np.array_equal(pos[sidx.cpu().numpy()], sp)
         start = 0
         for r in range(P):
             sel = ((want >> r) & 1).astype(bool)
