@@ -79,8 +79,9 @@ def main():
     rec = FFTRecon(data=dcat, ran=rcat, Nmesh=N, bias=1.4, f=0.3, R=40., scheme="LF2").compute(mode="real")
     slabs = comm.allgather(rec.numpy())
     if rank == 0:
-        d1 = ArrayCatalog({"Position": torch.from_numpy(dat).cuda()}, comm=SelfComm(), BoxSize=L)
-        r1 = ArrayCatalog({"Position": torch.from_numpy(ran).cuda()}, comm=SelfComm(), BoxSize=L)
+        one = SelfComm()
+        d1 = ArrayCatalog({"Position": torch.from_numpy(dat).cuda()}, comm=one, BoxSize=L)
+        r1 = ArrayCatalog({"Position": torch.from_numpy(ran).cuda()}, comm=one, BoxSize=L)
         ref = FFTRecon(data=d1, ran=r1, Nmesh=N, bias=1.4, f=0.3, R=40., scheme="LF2").compute(mode="real").numpy()
         full = np.concatenate(slabs, axis=0)
         ok = np.abs(full - ref).max() <= 1e-4 * np.abs(ref).max()
