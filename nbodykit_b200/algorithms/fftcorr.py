@@ -11,7 +11,7 @@ import numpy
 from .._lib import check, lib
 from ..binned_statistic import BinnedStatistic
 from ..pmesh.pm import ComplexField, _CODE, _ptr, _stream
-from .fftpower import FFTBase, project_to_basis_device
+from .fftpower import _find_unique_edges, FFTBase, project_to_basis_device
 
 
 class FFTCorr(FFTBase):
@@ -66,12 +66,14 @@ class FFTCorr(FFTBase):
         dr, rmin, rmax = self.attrs['dr'], self.attrs['rmin'], self.attrs['rmax']
         if rmax is None:
             rmax = 0.5 * pm.BoxSize.min() + dr / 2
-        if dr <= 0:
-            raise NotImplementedError("dr = 0 (unique separations) is not implemented for FFTCorr")
-        redges = numpy.arange(rmin, rmax, dr)
+        if dr > 0:
+            redges = numpy.arange(rmin, rmax, dr)
+            rcenters = None
+        else:
+            redges, rcenters = _find_unique_edges(pm, rmax, real=True)
         muedges = numpy.linspace(0, 1, self.attrs['Nmu'] + 1, endpoint=True)
         edges = [redges, muedges]
-        coords = [None, None]
+        coords = [rcenters, None]
         result, pole_result = project_to_basis_device(y3d, edges, poles=self.attrs['poles'], los=self.attrs['los'],
                                                       is_p3d=True)
         if self.attrs['mode'] == "1d":

@@ -392,22 +392,22 @@ def _cast_source(source, BoxSize, Nmesh):
     return source
 
 
-def _find_unique_edges(pm, xmax):
-    """`dk=0`: one bin per distinct |k| on the lattice (fftpower.py:732-769).
+def _find_unique_edges(pm, xmax, real=False):
+    """`dk=0` / `dr=0`: one bin per distinct |k| (or, real=True, per distinct separation |x|) on the lattice
+    (fftpower.py:732-769; fftcorr.py:167).
 
-    The reference broadcasts a full k^2 array per rank and uniquifies it; the distinct values are the
+    The reference broadcasts a full x^2 array per rank and uniquifies it; the distinct values are the
     distinct sums of three squared 1-D coordinates, found here from the 1-D arrays alone (host, O(N^2)).
-    Same quantisation: ix2 = int64(fx2 / (0.05 k_f)^2 + 0.5), first occurrence kept."""
-    x = pm.create_coords("complex")            # float32 arrays, storage-shaped; full extent on every rank
+    Same quantisation: ix2 = int64(fx2 / (0.05 x0)^2 + 0.5), first occurrence kept."""
     N = [int(v) for v in pm.Nmesh]
-    x0 = 2 * numpy.pi / pm.BoxSize
-    ct = x[0].dtype.type
+    x0 = (pm.BoxSize / pm.Nmesh) if real else (2 * numpy.pi / pm.BoxSize)
+    ct = numpy.float32                         # coordinate arrays of the fields are float32 (SURVEY B.5)
     full = []
     for d in range(3):
-        n = pm.Nzc if d == 2 else N[d]
+        n = N[d] if (real or d != 2) else pm.Nzc
         j = numpy.arange(n)
         j[j >= (N[d] + 1) // 2] -= N[d]
-        full.append(j.astype(ct) * ct(2 * numpy.pi / pm.BoxSize[d]))
+        full.append(j.astype(ct) * ct(x0[d]))
     binning = (x0.min() * 0.05) ** 2
     xy = (0 + full[0][:, None] ** 2) + full[1][None, :] ** 2      # same association order as sum(xi**2)
     best = {}

@@ -172,3 +172,14 @@ def test_projected_fftpower_reference_assertions(cuda):
     want = (np.bincount(dig, weights=(W * pk).flat, minlength=nb) / np.bincount(dig, weights=W.flat, minlength=nb))[1:-1] * 512. ** 2
     np.testing.assert_allclose(rp2.power['power'].real, want, rtol=1e-6, atol=1e-9 * np.nanmax(want))
     assert np.array_equal(rp2.power['modes'], np.bincount(dig, weights=W.flat, minlength=nb)[1:-1])
+
+
+def test_fftcorr_unique_and_padding(cuda):
+    """algorithms/tests/test_fftcorr.py: dr=0 -> one bin per distinct separation (bin centres == mean r), and a
+    catalogue painted on a larger box keeps N1 / N2"""
+    from nbodykit_b200.lab import UniformCatalog, FFTCorr
+    source = UniformCatalog(nbar=3e-4, BoxSize=512., seed=42)
+    p = FFTCorr(source, mode='1d', Nmesh=32, dr=0).corr
+    np.testing.assert_allclose(p.coords['r'], p['r'], rtol=1e-6)
+    r = FFTCorr(source, mode='1d', BoxSize=1024, Nmesh=32)
+    assert r.attrs['N1'] != 0 and r.attrs['N2'] != 0
