@@ -210,3 +210,26 @@ def test_find_unique_edges_matches_reference_formula():
     fx = fx[fx < kmax]
     np.testing.assert_array_equal(centers, fx)
     assert edges[0] == 0 and len(edges) == len(centers) + 1 and np.all(np.diff(edges) > 0)
+
+
+def test_fftrecon_and_projected_power_argument_checks():
+    """host-side validation mirrors the reference (fftrecon.py:76-129, fftpower.py:393-399); nothing touches the GPU"""
+    import warnings
+    from nbodykit_b200.lab import ArrayCatalog, FFTRecon, ProjectedFFTPower
+    rng = np.random.RandomState(0)
+    d = ArrayCatalog({'Position': rng.uniform(0, 100., size=(50, 3)), 'Other': np.zeros(50)}, BoxSize=100., Nmesh=8)
+    r = ArrayCatalog({'Position': rng.uniform(0, 100., size=(80, 3))}, BoxSize=100.)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = FFTRecon(data=d, ran=r, Nmesh=None, bias=2.0, f=0.5, los=[0, 0, 2], R=20., scheme='LF2')
+    assert list(m.attrs['Nmesh']) == [8, 8, 8] and list(m.attrs['BoxSize']) == [100., 100., 100.]
+    np.testing.assert_allclose(m.attrs['los'], [0, 0, 0.5])          # los / sum(los^2), as the reference does
+    assert m.attrs['scheme'] == 'LF2' and m.attrs['revert_rsd_random'] is False and m.dtype == 'f8'
+    with pytest.raises(AssertionError):
+        FFTRecon(data=d, ran=r, Nmesh=8, scheme='XYZ')
+    with pytest.raises(AssertionError):
+        FFTRecon(data=d, ran=r, Nmesh=8, position='Other')            # the randoms have no such column
+    with pytest.warns(UserWarning):
+        FFTRecon(data=d, ran=r, Nmesh=8, R=1.0)                       # smoothing below the cell size
+    with pytest.raises(AssertionError):
+        ProjectedFFTPower(d, Nmesh=8, axes=(0, 1, 2))
