@@ -934,7 +934,7 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
     if (rc) return rc;
     rc = get_twiddle(Nz, dtype, s, &twN);
     if (rc) return rc;
-    if (forward && M >= 64 && use_reg_lines(M)) {
+    if (forward && M >= 64 && M <= 256 * (sizeof(T) == 4 ? 16 : 8) && use_reg_lines(M)) {   // the tile must fit the registers
         // register-I/O variant: 256 threads hold the whole tile across the last stage (M * B <= 256 V)
         const int V = sizeof(T) == 4 ? 16 : 8;
         int B = 16;
