@@ -189,6 +189,9 @@ int nbk_interlace_combine(void *c1, const void *c2, int dtype, const int64_t *nm
  * (ells[0] must be 0).  coord_dtype NBK_F4 (fixture-faithful) | NBK_F8.
  * comp1 / comp2 (NBK_COMP_*): window compensation applied on the fly to c1 / c2 (the fused equivalent of
  * running nbk_compensate on each field first); NBK_COMP_NONE when the fields are already compensated.
+ * hermitian: 0 full field, 1 Hermitian-compressed last axis with y(-k) = conj y(k), 2 compressed with
+ * y(-k) = -conj y(k) (the odd multipoles of ConvolvedFFTPower, A0 conj(A_l): what the reference obtains from a full
+ * 'c16' mesh, convpower/catalog.py:169-176); the mirror half is folded in accordingly.
  * real_input != 0: c1 is a REAL [count][D1][Nz] statistic (FFTCorr, algorithms/fftcorr.py:148-176; needs is_p3d,
  * hermitian == 0).  coord_unit_host: per-axis coordinate of index 1 (NULL -> 2 pi / L, the wavenumbers; FFTCorr
  * passes the cell size L/N so that coordinates are the wrapped separations).

@@ -72,12 +72,12 @@ class FKPCatalog(MultipleSpeciesCatalog):
             BoxSize = self.attrs['BoxSize']
         return BoxSize, BoxCenter
 
-    def to_mesh(self, Nmesh=None, BoxSize=None, BoxCenter=None, dtype='f8', interlaced=False, compensated=False,
+    def to_mesh(self, Nmesh=None, BoxSize=None, BoxCenter=None, dtype='c16', interlaced=False, compensated=False,
                 resampler='cic', fkp_weight='FKPWeight', comp_weight='Weight', selection='Selection',
                 position='Position', bbox_from_species=None, window=None, nbar=None):
-        """mesh that paints the FKP field.  NOTE: the reference defaults to ``dtype='c16'`` (full complex mesh,
-        needed only for odd multipoles under wide-angle effects); complex meshes are not implemented here, the
-        default is the Hermitian ``'f8'`` the reference's own benchmark and tests use."""
+        """mesh that paints the FKP field (convpower/catalog.py:151-259).  dtype 'c16' / 'c8' (default, as in the
+        reference) recovers the odd multipoles correctly; 'f8' / 'f4' reproduce the reference's Hermitian short-cut.
+        Either way the field is stored Hermitian-compressed on the device (see FKPCatalogMesh)."""
         from .catalogmesh import FKPCatalogMesh
         if window is not None:
             import warnings

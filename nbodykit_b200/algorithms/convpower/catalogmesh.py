@@ -23,6 +23,13 @@ class FKPCatalogMesh(MultipleSpeciesCatalogMesh):
         weight = '_TotalWeight'
         self.attrs.update(source.attrs)
         self.recenter_box(BoxSize, BoxCenter)
+        # 'c16' / 'c8' (the reference's default, convpower/catalog.py:151,169-176): the FKP field is real-valued in
+        # configuration space, so its transform is stored Hermitian-compressed here as well; what the full complex mesh
+        # buys the reference -- correct ODD multipoles -- is obtained by folding the mirror half with the
+        # anti-Hermitian sign in the binning kernel (ConvolvedFFTPower._compute_multipoles)
+        self.complex_mesh = numpy.dtype(dtype).kind == 'c'
+        if self.complex_mesh:
+            dtype = 'f8' if numpy.dtype(dtype).itemsize == 16 else 'f4'
         MultipleSpeciesCatalogMesh.__init__(self, source=source, BoxSize=BoxSize, Nmesh=Nmesh, dtype=dtype,
                                             weight=weight, value=value, selection=selection, position=position,
                                             interlaced=interlaced, compensated=compensated, resampler=resampler)

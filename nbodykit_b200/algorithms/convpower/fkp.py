@@ -10,7 +10,8 @@ Where the O(Nmesh^3) work runs (reference line numbers):
                      formed on the fly)                                                     (:571-597)
   P_l = <norm A_0 A_l^*>_k   nbk_power_bin(c1 = FFT[F], c2 = sum_m ..., volume = norm 4 pi V^2, comp1, comp2),
                      zero mode NOT cleared, mu edges (-1, 1)                                (:605-623, 631-643)
-Meshes are Hermitian real ('f4'/'f8'); the reference's default 'c16' complex mesh is not implemented.
+Meshes are stored Hermitian-compressed; the reference's default 'c16' complex mesh is accepted and reproduced through
+the anti-Hermitian fold of the odd multipoles (no c2c transform is needed: the FKP field is real in configuration space).
 """
 import logging
 import time
@@ -249,9 +250,13 @@ class ConvolvedFFTPower(object):
             if rank == 0:
                 self.logger.info('ell = %d done; %s r2c completed' % (ell, 2 * ell + 1))
             # P_l = < norm * (V c1 / comp1) * conj(4 pi V Aell / comp2) >
+            # full complex ('c16') meshes give the reference the true sum over all modes; for odd ell the statistic is
+            # anti-Hermitian and the compressed half must be folded with that sign.  Hermitian ('f8'/'f4') meshes keep the
+            # reference's own (documented as incorrect for odd ell) Hermitian fold.
+            anti = bool(getattr(self.first, 'complex_mesh', False)) and (ell % 2 == 1)
             proj, _ = project_to_basis_device(c1, edges, second=Aell, is_p3d=False,
                                               volume=norm * 4 * numpy.pi * volume * volume, compensation=comp,
-                                              clear_zero=False)
+                                              clear_zero=False, antihermitian=anti)
             result['power_%d' % ell][:] = numpy.squeeze(proj[2])
         if rank == 0:
             self.logger.info("higher order multipoles computed in elapsed time %s" % timer(start, time.time()))
@@ -326,8 +331,7 @@ def _cast_mesh(mesh, Nmesh):
     if not isinstance(mesh, (FKPCatalogMesh, FKPCatalog)):
         raise TypeError("input sources should be a FKPCatalog or FKPCatalogMesh")
     if isinstance(mesh, FKPCatalog):
-        # the reference casts with dtype='c16'; complex meshes are not implemented -> Hermitian f8
-        mesh = mesh.to_mesh(Nmesh=Nmesh, dtype='f8', compensated=False)
+        mesh = mesh.to_mesh(Nmesh=Nmesh, dtype='c16', compensated=False)      # as the reference does (fkp.py:774)
     if Nmesh is not None and any(mesh.attrs['Nmesh'] != Nmesh):
         raise ValueError(("Mismatched Nmesh between __init__ and mesh.attrs; "
                           "if trying to re-sample with a different mesh, specify "

@@ -283,7 +283,7 @@ def _los_coord_mode(los, coord_dtype):
 
 
 def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4", is_p3d=True, second=None,
-                            volume=1.0, compensation=(None, None), clear_zero=True):
+                            volume=1.0, compensation=(None, None), clear_zero=True, antihermitian=False):
     """
     project_to_basis (fftpower.py:507-701) for a device ComplexField.
 
@@ -291,6 +291,8 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     ``is_p3d=False`` the statistic is `y3d * conj(second or y3d) * volume` with the k=0 mode
     cleared, formed on the fly (fftpower.py:115-128) -- the FFTPower fast path; `compensation` then names
     the window transfer functions (`Compensate*`) still to be divided out of `y3d` / `second`, also on the fly.
+    ``antihermitian=True``: the statistic obeys y(-k) = -conj y(k) (odd FKP multipoles A0 conj(A_l)); the mirror half
+    of the compressed field is folded in with that sign, which is what a full complex ('c16') mesh gives the reference.
 
     Returns exactly what the reference returns:
     ``(xmean_2d, mumean_2d, y2d, N_2d), (xmean_1d, poles, N_1d) | None``.
@@ -333,7 +335,7 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
             _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
             1 if is_p3d else 0, float(volume), 1 if clear_zero else 0, pm._nmesh_c, pm._box_c, tr, start, count,
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
-            _lib.i32arr(_poles), Nell, 0 if is_real else 1, _lib.COMP.get(compensation[0], 0),
+            _lib.i32arr(_poles), Nell, 0 if is_real else (2 if antihermitian else 1), _lib.COMP.get(compensation[0], 0),
             _lib.COMP.get(compensation[1], 0), 1 if is_real else 0, coord_unit,
             _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
     with stage("H:bin_reduce"):

@@ -302,6 +302,7 @@ struct BinParams {
     int Nell;
     int ells[NBK_MAX_ELL];
     int hermitian, is_p3d, clear_zero, has_c2;
+    int anti;         // the statistic obeys y(-k) = -conj y(k) (odd FKP multipoles): the fold of the mirror half flips
     int estride;     // 2: complex input (re, im interleaved)   1: real input (a RealField statistic, FFTCorr)
     double volume;
 };
@@ -503,8 +504,8 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     int ell = P.ells[l];
                     double f = legendre(ell, mu) * (2.0 * ell + 1.0);
                     double re = f * yre, im = f * yim;
-                    if (nonsing) {
-                        if (ell & 1) { re = 0.0; im *= 2.0; }
+                    if (nonsing) {   // add the mirror mode: Leg(l)(-mu) * (+/-) conj(y)
+                        if ((ell & 1) != P.anti) { re = 0.0; im *= 2.0; }
                         else { re *= 2.0; im = 0.0; }
                     }
                     yr[l] = re;
@@ -700,6 +701,7 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
     for (int l = 0; l < NBK_MAX_ELL; l++) P.ells[l] = l < Nell ? ells[l] : 0;
     for (int l = 0; l < Nell; l++) NBK_CHECK_ARG(ells[l] >= 0 && ells[l] <= 64, "power_bin: bad multipole %d", ells[l]);
     P.hermitian = hermitian ? 1 : 0;
+    P.anti = hermitian == 2 ? 1 : 0;
     P.is_p3d = is_p3d ? 1 : 0;
     P.estride = real_input ? 1 : 2;
     NBK_CHECK_ARG(!real_input || (is_p3d && !hermitian), "power_bin: a real input must be a full (non-Hermitian) 3-D statistic");

@@ -114,3 +114,65 @@ def convpower(dpos, rpos, wd, wr, nbar_d, nbar_r, Nmesh, BoxSize, BoxCenter, pol
     out["k"] = np.squeeze(res[0])
     out["modes"] = np.squeeze(res[3])
     return out
+
+
+def convpower_full(dpos, rpos, wd, wr, nbar_d, nbar_r, Nmesh, BoxSize, BoxCenter, poles, resampler="cic",
+                   dk=None, kmin=0., coord_dtype="f4"):
+    """ConvolvedFFTPower on a FULL complex mesh (the reference's default dtype='c16', convpower/catalog.py:169-176):
+    complex-to-complex transforms of the N^3 field and project_to_basis over every mode (hermitian_symmetric=False,
+    fftpower.py:572).  Restated with numpy.fft.fftn; it is what pins the odd multipoles of the GPU path, which stores
+    the same fields Hermitian-compressed and folds the mirror half with the anti-Hermitian sign."""
+    N = (np.asarray(Nmesh, dtype="i8") * np.ones(3, dtype="i8"))
+    L = np.asarray(BoxSize, dtype="f8") * np.ones(3)
+    C = np.asarray(BoxCenter, dtype="f8") * np.ones(3)
+    F, alpha = fkp_field(dpos, rpos, wd, wr, N, L, C, resampler, "f8")
+    V = L.prod()
+    ct = np.dtype(coord_dtype).type
+    # full (uncompressed) coordinate arrays on all three axes
+    kx3, wc = [], []
+    for d in range(3):
+        j = po.freq_index(int(N[d]))
+        shape = [1, 1, 1]
+        shape[d] = int(N[d])
+        kx3.append((j.astype(ct) * ct(2 * np.pi / L[d])).reshape(shape))
+        wc.append((j.astype(ct) * ct(2 * np.pi / N[d])).reshape(shape))
+    comp = po.COMPENSATION.get((False, resampler))
+
+    def c2c(x):
+        return np.fft.fftn(x) / float(np.prod(N))
+    cfield = c2c(F)
+    if comp is not None:
+        cfield = po.compensate(comp, wc, cfield)
+    A0 = cfield * V
+    (wcd, wfd), (wcr, wfr) = wd, wr
+    norm_r = float((nbar_r * wcr * wfr * wfr).sum()) * alpha
+    norm = 1.0 / norm_r
+    if dk is None:
+        dk = 2 * np.pi / L.min()
+    kmax = np.pi * N.min() / L.max() + dk / 2
+    kedges = np.arange(kmin, kmax, dk)
+    edges = [kedges, np.linspace(-1, 1, 2)]
+    offset = C + 0.5 * L / N
+    xg = [x.astype("f8") + offset[i] for i, x in enumerate(x_coords(N, L, coord_dtype))]
+    xnorm = np.sqrt(sum(x ** 2 for x in xg))
+    xg = [x / xnorm for x in xg]
+    kg = [k.astype("f8") for k in kx3]
+    knorm = np.sqrt(sum(k ** 2 for k in kg))
+    knorm[knorm == 0.] = np.inf
+    kg = [k / knorm for k in kg]
+    out = dict(alpha=alpha, kedges=kedges)
+    for ell in sorted(poles):
+        if ell == 0:
+            P = norm * A0 * np.conj(A0)
+        else:
+            Aell = np.zeros_like(A0)
+            for m in range(-ell, ell + 1):
+                Aell += c2c(F * real_ylm(ell, m, xg[0], xg[1], xg[2])) * real_ylm(ell, m, kg[0], kg[1], kg[2])
+            if comp is not None:
+                Aell = po.compensate(comp, wc, Aell)
+            P = norm * A0 * np.conj(Aell * (4 * np.pi * V))
+        res, _ = po.project_to_basis(P, kx3, edges, hermitian_symmetric=False)
+        out["power_%d" % ell] = np.squeeze(res[2])
+        out["k"] = np.squeeze(res[0])
+        out["modes"] = np.squeeze(res[3])
+    return out

@@ -131,6 +131,39 @@ def test_convolved_power_vs_oracle(cuda, resampler):
     assert pkmu.shape == (len(res.poles['k']), 3)
 
 
+def test_convolved_power_complex_mesh_odd_multipoles(cuda):
+    """dtype='c16' (the reference default): odd multipoles equal the sum over ALL modes of a full complex mesh
+    (oracle: fftn + project_to_basis(hermitian_symmetric=False)); even ones equal the Hermitian result; with an 'f8'
+    mesh the odd multipoles keep the reference's Hermitian fold (documented there as incorrect)"""
+    from nbodykit_b200.lab import ConvolvedFFTPower
+    fkp, d, r = _fkp()
+    mesh = fkp.to_mesh(Nmesh=32)                       # default dtype, as in the reference
+    assert mesh.complex_mesh
+    res = ConvolvedFFTPower(mesh, poles=[0, 1, 2, 3], dk=0.02)
+    C, L = mesh.attrs['BoxCenter'], mesh.attrs['BoxSize']
+    wfd = 1. / (1 + 1e4 * NBAR)
+    args = (np.asarray(d['Position']), np.asarray(r['Position']),
+            (np.asarray(d['Weight']), wfd * np.ones(d.size)), (np.ones(r.size), wfd * np.ones(r.size)),
+            NBAR * np.ones(d.size), NBAR * np.ones(r.size), 32, L, C, [0, 1, 2, 3])
+    o = co.convpower_full(*args, dk=0.02)
+    assert np.array_equal(res.poles['modes'], o['modes'])
+    np.testing.assert_allclose(res.poles['k'], o['k'], rtol=1e-6, equal_nan=True)
+    scale = np.nanmax(np.abs(o['power_0']))
+    for ell in (0, 1, 2, 3):
+        got, want = res.poles['power_%d' % ell], o['power_%d' % ell]
+        np.testing.assert_allclose(np.nan_to_num(got.real), np.nan_to_num(want.real), rtol=1e-5, atol=2e-6 * scale)
+        np.testing.assert_allclose(np.nan_to_num(got.imag), np.nan_to_num(want.imag), rtol=1e-5, atol=2e-6 * scale)
+    # the odd multipoles of a survey-like geometry are imaginary and do not vanish
+    assert np.nanmax(np.abs(res.poles['power_1'].imag)) > 1e-3 * scale
+    assert np.nanmax(np.abs(res.poles['power_1'].real)) < 1e-5 * scale
+    # Hermitian mesh: the reference's own (Hermitian) fold -> the restatement with hermitian_symmetric=True
+    res8 = ConvolvedFFTPower(fkp.to_mesh(Nmesh=32, dtype='f8'), poles=[1], dk=0.02)
+    o8 = co.convpower(*args[:-1], [1], dk=0.02)
+    for part in ('real', 'imag'):
+        np.testing.assert_allclose(np.nan_to_num(getattr(res8.poles['power_1'], part)),
+                                   np.nan_to_num(getattr(o8['power_1'], part)), rtol=1e-5, atol=2e-6 * scale)
+
+
 def test_convolved_power_errors_and_io(cuda, tmp_path):
     from nbodykit_b200.lab import ConvolvedFFTPower
     fkp, d, r = _fkp()
