@@ -233,14 +233,15 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 // cell = round-to-nearest sum of w_i * 2^31/M, M = power of two >= max|mass| (exact integer
 // adds, resolution 4.7e-10 M per deposit).
 //
-//   pass A  k_tile_count   : tile id of every particle (same f8 index arithmetic as the scatter),
-//                            warp-aggregated REDG into counts[tile]
-//   pass B  k_tile_scan    : exclusive scan counts -> offsets
-//   pass C  k_tile_scatter : copy (pos[, mass]) into tile order (claim slots with one atomic per
-//                            tile per warp)
-//   pass D  k_tile_paint   : persistent CTAs pull tiles from a queue; region = (T + halo)^3 cells
-//                            in shared memory; cells no other tile can touch are written back with
-//                            plain coalesced read-add-store, halo cells with REDG
+//   pass A  k_tile_count_blk   : CTA c histograms the tile ids of its contiguous particle chunk in shared memory
+//                                (native ATOMS.ADD.U32; row c of blk[G][ntiles]); with `clear` it also zeroes the mesh
+//   pass B  k_tile_colscan/_scan : per-tile prefix over the CTA histograms, tile offsets
+//   pass C  k_tile_scatter_blk : the same CTA re-reads its chunk, evaluates the exact f8 grid coordinate once and
+//                                emits a 16-byte record per particle (32-bit fixed-point fractions + in-tile cell)
+//   pass D  k_tile_paint       : persistent CTAs pull tiles from a queue; region = (T + halo)^3 cells in shared
+//                                memory as two u32 limbs; one TMA bulk reduce-add per z row writes it back
+// (k_tile_count / k_tile_scatter are the global-atomic variants of A and C for meshes with more tiles than a shared
+// histogram holds.)
 // A tile owns the particles whose LEFTMOST stencil cell lies in it, so the halo is one-sided.
 // =============================================================================================
 #define TILE 16
