@@ -6,10 +6,12 @@
 //   z pass  : rows are contiguous; real row of Nz -> packed complex FFT of Nz/2 -> Nz/2+1 modes
 //   y pass  : lines strided by Nzc, tiles of B adjacent kz columns  (B*sizeof(cplx) >= 64 B runs)
 //   x pass  : lines strided by Ny*Nzc, tiles of B adjacent (y,kz) elements
-// Every pass stages a [N][B] tile (pitch B+1: conflict-free both for the butterfly access and for
-// the transposed fill of the z pass) in shared memory, runs an in-place decimation-in-frequency FFT
-// with register-resident radix-8 butterflies (+ one radix-4 / radix-2 stage for the remainder), and
-// writes frequencies out through the mixed-radix digit-reversal map, so no ping-pong buffer is needed.
+// Every pass works on tiles of B side-by-side lines ([N][B+1] in shared memory, B * sizeof(complex) = 128 bytes) with
+// a decimation-in-frequency FFT whose radix-8 butterflies live in registers (+ one radix-4 / radix-2 stage for the
+// remainder of log2 N).  The default kernels (k_fft_lines_rg, k_fft_z_r2c_rg; N >= 64) load the first stage straight
+// from global memory and store the last stage straight to the digit-reversed frequency rows, so shared memory only
+// carries the exchanges between stages; the older kernels (k_fft_lines with cp.async double buffering, k_fft_z_r2c,
+// k_fft_z_c2r) stage whole tiles and serve short lines, the backward z pass and NBK_FFT_LINES=smem.
 // Twiddles: f8-accurate table built on the device with sincospi, staged in shared memory.  Sizes: 2^k.
 #include "common.cuh"
 #include <map>
