@@ -132,6 +132,21 @@ def test_r2c_c2r(cuda, N, dtype, tol):
     np.testing.assert_array_equal(c.numpy(), got)
 
 
+@pytest.mark.parametrize("N", [[8, 8, 256], [4, 8, 512], [4, 4, 1024], [2, 4, 2048], [4, 4, 4096]])
+@pytest.mark.parametrize("dtype,tol", [("f8", 1e-13), ("f4", 2e-6)])
+def test_r2c_long_rows(cuda, N, dtype, tol):
+    """long z rows: packed lengths 128 .. 2048 cover every last-stage radix (8 / 4 / 2) of the register-I/O z pass"""
+    from nbodykit_b200.pmesh.pm import RealField
+    rng = np.random.RandomState(1)
+    real = rng.standard_normal(N).astype(dtype)
+    pm = _pm(N, 1.0, dtype)
+    f = RealField(pm)
+    f[...] = real
+    got = f.r2c().numpy()
+    want = np.fft.rfftn(real.astype("f8")) / real.size
+    assert np.abs(got - want).max() <= tol * np.sqrt((np.abs(want) ** 2).mean()) * np.log2(real.size)
+
+
 @pytest.mark.parametrize("name", sorted(["CompensateCIC", "CompensateTSC", "CompensatePCS", "CompensateCICShotnoise",
                                          "CompensateTSCShotnoise", "CompensatePCSShotnoise"]))
 @pytest.mark.parametrize("dtype,tol", [("f8", 2e-6), ("f4", 3e-6)])
