@@ -36,3 +36,26 @@ def test_displacement_modes_and_schemes():
     lf2, _, _ = ro.fftrecon(data, ran, N, L, bias=2.0, f=0.0, R=20., scheme="LF2")
     np.testing.assert_allclose(lf2, lgs * (3.0 / 7.0) + lrr * (4.0 / 7.0), rtol=0, atol=1e-12)
     assert s_d.dtype == np.float32 and s_d.shape == (3000, 3) and abs(lgs.mean()) < 1e-10
+
+
+def test_convpower_full_mesh_oracle_agrees_with_the_hermitian_one_for_even_multipoles():
+    """oracle/convpower_oracle.py: the full complex-mesh restatement (fftn, hermitian_symmetric=False) and the
+    Hermitian one coincide for even multipoles and mode counts; odd multipoles of the full mesh are purely imaginary"""
+    from oracle import convpower_oracle as co
+    rng = np.random.RandomState(4)
+    L = np.array([300., 300., 300.])
+    C = np.array([500., 100., 50.])
+    d = rng.uniform(-130, 130, size=(3000, 3)) + C
+    r = rng.uniform(-130, 130, size=(9000, 3)) + C
+    nb = 1e-4
+    wf = 1. / (1 + 1e4 * nb)
+    args = (d, r, (np.ones(len(d)), wf * np.ones(len(d))), (np.ones(len(r)), wf * np.ones(len(r))),
+            nb * np.ones(len(d)), nb * np.ones(len(r)), 16, L, C)
+    full = co.convpower_full(*args, [0, 1, 2], dk=0.05)
+    herm = co.convpower(*args, [0, 1, 2], dk=0.05)
+    assert np.array_equal(full['modes'], herm['modes'])
+    scale = np.nanmax(np.abs(herm['power_0']))
+    for ell in (0, 2):
+        assert np.nanmax(np.abs(full['power_%d' % ell] - herm['power_%d' % ell])) < 1e-12 * scale
+    assert np.nanmax(np.abs(full['power_1'].real[:-1])) < 1e-10 * scale
+    assert np.nanmax(np.abs(full['power_1'].imag)) > 1e-3 * scale
