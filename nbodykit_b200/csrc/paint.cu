@@ -223,8 +223,8 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 
 // =============================================================================================
 // Path "tiled": bucket particles by 16^3-cell tile, accumulate each tile in shared memory with
-// native 32-bit integer atomics (ATOMS.ADD) on a 64-bit fixed-point representation, flush the
-// tile once.
+// native 32-bit integer atomics (ATOMS.ADD) on a 64-bit fixed-point representation, write every
+// mesh cell exactly once.
 //
 // Measured on B200 (tools/atomics_bench.cu): shared u32 ATOMS sustain ~2.5e12 op/s chip-wide in a
 // CIC pattern (3e11 particles/s), the REDG path of "direct" 5e9 (random) .. 4e10 (cell-sorted)
@@ -233,26 +233,39 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 // cell = round-to-nearest sum of w_i * 2^31/M, M = power of two >= max|mass| (exact integer
 // adds, resolution 4.7e-10 M per deposit).
 //
-//   pass A  k_tile_count_blk   : CTA c histograms the tile ids of its contiguous particle chunk in shared memory
-//                                (native ATOMS.ADD.U32; row c of blk[G][ntiles]); with `clear` it also zeroes the mesh
-//   pass B  k_tile_colscan/_scan : per-tile prefix over the CTA histograms, tile offsets
-//   pass C  k_tile_scatter_blk : the same CTA re-reads its chunk, evaluates the exact f8 grid coordinate once and
-//                                emits a 16-byte record per particle (32-bit fixed-point fractions + in-tile cell)
-//   pass D  k_tile_paint       : persistent CTAs pull tiles from a queue; region = (T + halo)^3 cells in shared
-//                                memory as two u32 limbs; one TMA bulk reduce-add per z row writes it back
-// (k_tile_count / k_tile_scatter are the global-atomic variants of A and C for meshes with more tiles than a shared
-// histogram holds.)
+//   probe   k_bucket_probe    : samples neighbouring particle pairs: is the input spatially coherent (e.g. the
+//                               cell-sorted output of a mock generator)?  Picks the bucketing configuration ON THE
+//                               DEVICE (no host round trip): both configurations are launched, the other one exits.
+//   pass A  k_bucket_count    : every CTA owns contiguous particle chunks, staged into shared memory by the TMA
+//                               engine (cp.async.bulk + mbarrier, double buffered), and histograms the tile ids in a
+//                               shared-memory WINDOW of tile indices (native ATOMS.ADD.U32); one global atomic per
+//                               (chunk, tile) reserves the chunk's share of the tile's bucket.  Particles whose tile
+//                               lies outside the window are counted with (warp-aggregated) global atomics.
+//                               coherent input : window = 16384 tiles (a few x planes of tiles), 2 CTAs / SM
+//                               scattered input: window = all tiles when they fit in 200 KB (<= 51200 tiles)
+//   pass B  k_tile_scan       : exclusive scan of the tile counts -> bucket offsets; clears cursors and flags
+//   pass C  k_bucket_scatter  : same chunks, same windows: evaluates the exact f8 grid coordinate once and emits a
+//                               12-byte record per particle (per axis: 4-bit cell-in-tile | 28-bit fraction)
+//   pass D  k_tile_paint      : persistent CTAs pull tiles from a queue IN TILE ORDER; region = (T + halo)^3 cells in
+//                               shared memory as two u32 limbs.  Write-back without a cleared mesh and without
+//                               read-modify-write of DRAM-resident lines: of all tiles touching a cell the FIRST in
+//                               queue order stores it (plain coalesced stores), publishes a per-tile flag
+//                               (release), and the later ones add their share (REDG, L2-resident) after acquiring
+//                               the flags of the earlier tiles they overlap.  hold=True (accumulate into an existing
+//                               mesh) uses one TMA bulk reduce-add per z row instead.
 // A tile owns the particles whose LEFTMOST stencil cell lies in it, so the halo is one-sided.
 // =============================================================================================
 #define TILE 16
-#define NBK_BLK_SMEM (200 * 1024)   // largest shared-memory tile histogram (CTA-local bucketing)
+#define NBK_BLK_SMEM (200 * 1024)   // largest shared-memory tile window (scattered input)
+#define NBK_WIN_COHERENT 16384      // tile window of the coherent configuration (64 KB)
+#define NBK_CHUNKS_COHERENT (4 * NBK_SM_COUNT)
+#define NBK_CHUNKS_SCATTERED NBK_SM_COUNT
 
-// Tile-ordered particle record, 16 bytes for every position dtype: the scatter pass evaluates the grid coordinate
-// in the exact f8 arithmetic once and stores, per axis, the fraction of (g + A) as a 32-bit fixed-point number
-// (truncated: the weights move by < 2^-32, below the 2^-31 deposit quantum) plus the leftmost stencil cell
-// relative to its tile (4 bits per axis).  The paint pass needs no floor / wrap / range logic, and the half-cell
-// shifted mesh of an interlaced pair follows exactly from frac + 1/2 (carry -> next cell).
-typedef uint4 TileRec;     // {frac_x, frac_y, frac_z, lx | ly << 8 | lz << 16}
+// Tile-ordered particle record, 12 bytes for every position dtype: the scatter pass evaluates the grid coordinate
+// in the exact f8 arithmetic once and stores, per axis, one word = leftmost stencil cell relative to its tile
+// (high 4 bits) | fraction of (g + A) as 28-bit fixed point (truncated: the weights move by < 2^-28 = 3.7e-9).
+// The paint pass needs no floor / wrap / range logic, and the half-cell shifted mesh of an interlaced pair follows
+// exactly from frac + 1/2 (carry -> next cell).
 
 struct TileGeom {
     PaintGeom gm;
@@ -287,39 +300,45 @@ __device__ __forceinline__ int tile_from_cells(const int *c, const TileGeom &tg)
     return (tx * tg.nt[1] + ty) * tg.nt[2] + tz;
 }
 
-// exact (f8) tile id: the arithmetic of the scatter itself
+// exact (f8) tile id of the particle at x[0..2]: the arithmetic of the scatter itself
 template <int SUP, typename PT>
-__device__ __noinline__ int tile_of_exact(const PT *__restrict__ pos, int64_t i, const TileGeom &tg) {
-    double g[3];
-    if (!load_grid(pos, i, tg.gm, 0.0, g)) return -1;
+__device__ __noinline__ int tile_of_exact(const PT *x, const TileGeom &tg) {
     int c[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
+        double g = (double)x[d] * tg.gm.scale[d];
+        if (!isfinite(g)) return -1;
         long long i0;
         double w[SUP];
-        Window<SUP>::eval(g[d], i0, w);
+        Window<SUP>::eval(g, i0, w);
         c[d] = wrap(i0, tg.gm.n[d]);
     }
     return tile_from_cells(c, tg);
 }
 
-// exact leftmost cell + fixed-point fraction of particle i (the arithmetic of Window<SUP>::eval on the unshifted g).
+__device__ __forceinline__ void pack_record(const unsigned *u, const int *c, const TileGeom &tg, unsigned *rec) {
+    int lx = (tg.full ? c[0] : slab_local(c[0], tg) + tg.G) & (TILE - 1);
+    rec[0] = (u[0] >> 4) | ((unsigned)lx << 28);
+    rec[1] = (u[1] >> 4) | ((unsigned)(c[1] & (TILE - 1)) << 28);
+    rec[2] = (u[2] >> 4) | ((unsigned)(c[2] & (TILE - 1)) << 28);
+}
+
+// exact leftmost cell + fixed-point fraction (the arithmetic of Window<SUP>::eval on the unshifted g).
 // Slow path: any magnitude, 64-bit cell arithmetic.
 template <int SUP, typename PT>
-__device__ __noinline__ int make_record_slow(const PT *__restrict__ pos, int64_t i, const TileGeom &tg, TileRec &rec) {
-    double g[3];
-    if (!load_grid(pos, i, tg.gm, 0.0, g)) return -1;
+__device__ __noinline__ int make_record_slow(const PT *x, const TileGeom &tg, unsigned *rec) {
     unsigned u[3];
     int c[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-        double a = g[d] + (double)WinOff<SUP>::A;
+        double g = (double)x[d] * tg.gm.scale[d];
+        if (!isfinite(g)) return -1;
+        double a = g + (double)WinOff<SUP>::A;
         double f = floor(a);
         u[d] = __double2uint_rz((a - f) * 4294967296.0);
         c[d] = wrap((long long)f + WinOff<SUP>::B, tg.gm.n[d]);
     }
-    int lx = (slab_local(c[0], tg) + tg.G) & (TILE - 1);
-    rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
+    pack_record(u, c, tg, rec);
     return tile_from_cells(c, tg);
 }
 
@@ -327,8 +346,7 @@ __device__ __noinline__ int make_record_slow(const PT *__restrict__ pos, int64_t
 // rate): a + 1.5*2^52 holds rint(a) in its low mantissa word; floor and the truncated 32-bit fraction follow with
 // FP64 adds.  Bit-identical to the slow path.
 template <int SUP, typename PT>
-__device__ __forceinline__ int make_record(const PT *x, const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
-                                           TileRec &rec) {
+__device__ __forceinline__ int make_record(const PT *x, const TileGeom &tg, unsigned *rec) {
     const double K = 6755399441055744.0;      // 1.5 * 2^52
     unsigned u[3];
     int c[3];
@@ -349,17 +367,171 @@ __device__ __forceinline__ int make_record(const PT *x, const PT *__restrict__ p
         fast = fast && ((unsigned)cc < (unsigned)tg.gm.n[d]);
         c[d] = cc;
     }
-    if (!fast) return make_record_slow<SUP, PT>(pos, i, tg, rec);
-    int lx = (tg.full ? c[0] : slab_local(c[0], tg) + tg.G) & (TILE - 1);
-    rec = make_uint4(u[0], u[1], u[2], (unsigned)lx | ((unsigned)(c[1] & (TILE - 1)) << 8) | ((unsigned)(c[2] & (TILE - 1)) << 16));
+    if (!fast) return make_record_slow<SUP, PT>(x, tg, rec);
+    pack_record(u, c, tg, rec);
     return tile_from_cells(c, tg);      // the tile the bucketing pass counted this particle in (both are exact)
 }
 
-// coordinates of the 4 consecutive particles i0 .. i0+3 (i0 % 4 == 0): three 16-byte loads per thread for f4
-// positions when the array is 16-byte aligned (a warp then reads one contiguous 1536-byte run), scalar loads otherwise
+// per-launch constants of the float32 fast path of the tile id
+struct FastTile {
+    float sc[3];    // float32 scale N/L
+    float lim[3];   // accept when |frac(g) - 0.5| < lim  (frac at least eps away from both cell boundaries)
+};
+
+static FastTile make_fast_tile(const TileGeom &tg) {      // host side: passed to the kernels by value
+    FastTile f;
+    for (int d = 0; d < 3; d++) {
+        f.sc[d] = (float)tg.gm.scale[d];
+        // |g32 - g_exact| <= 2 float32 roundings of a value below n+2 -> 3e-7 (n+2) + 1e-6 is a safe margin
+        f.lim[d] = 0.5f - (3e-7f * (float)(tg.gm.n[d] + 2) + 1e-6f);
+    }
+    return f;
+}
+
+// Tile id of a particle.  float32 in-box positions take a float32 fast path: unless the fraction of
+// (x*scale + A) lies within the rounding margin of a cell boundary, floor() agrees with the exact f8 arithmetic;
+// everything else (near-boundary, outside the box, f8 positions) is recomputed in f8 (ok == false).  The id is
+// therefore ALWAYS the exact leftmost cell's tile -- count, scatter and paint passes agree.
+template <int SUP, typename PT>
+__device__ __forceinline__ int tile_fast(const PT *x, const TileGeom &tg, const FastTile &ft, bool &ok) {
+    ok = sizeof(PT) == 4;
+    int c[3] = {0, 0, 0};
+    if (sizeof(PT) == 4) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float g = (float)x[d] * ft.sc[d];
+            if (WinOff<SUP>::A != 0.f) g += WinOff<SUP>::A;
+            float f = floorf(g);
+            ok = ok && (fabsf((g - f) - 0.5f) < ft.lim[d]);
+            c[d] = (int)f + WinOff<SUP>::B;
+            ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
+        }
+    }
+    return ok ? tile_from_cells(c, tg) : -1;
+}
+
+// one atomic per distinct key per warp; returns this lane's slot.  All 32 lanes must call.
+__device__ __forceinline__ unsigned warp_claim(unsigned *counter, int key, bool active) {
+    const int lane = threadIdx.x & 31;
+    unsigned mask = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
+    if (!active) return 0;
+    int leader = __ffs(mask) - 1;
+    unsigned rank = __popc(mask & ((1u << lane) - 1));
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&counter[key], (unsigned)__popc(mask));
+    base = __shfl_sync(mask, base, leader);
+    return base + rank;
+}
+
+// Shared-memory counter claim.  Random catalogues: one native ATOMS per lane.  Spatially coherent catalogues put many
+// lanes of a warp on the same counter, which the atomic unit serialises; when neighbouring lanes agree often, the
+// warp aggregates equal keys first (one ATOMS per distinct key).  Must be called by all 32 lanes.
+__device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool active) {
+    const int lane = threadIdx.x & 31;
+    int kn = __shfl_xor_sync(0xffffffffu, key, 1);
+    unsigned same = __ballot_sync(0xffffffffu, active && kn == key);
+    if (__popc(same) < 8) return active ? atomicAdd(&hist[key], 1u) : 0u;
+    unsigned mask = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
+    if (!active) return 0u;
+    int leader = __ffs(mask) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&hist[key], (unsigned)__popc(mask));
+    return __shfl_sync(mask, base, leader) + __popc(mask & ((1u << lane) - 1));
+}
+
+// Claim slots for the (up to) four particles of a thread's quad (k[u] = window-relative tile, -1 = none).
+// Coherent input: when every lane's quad lies in one tile, the quad is claimed as a unit (then usually the whole warp
+// as one ATOMS); otherwise particle by particle.  All 32 lanes must call.
+__device__ __forceinline__ void quad_claim(unsigned *hist, const int (&k)[4], unsigned (&slot)[4]) {
+    const bool uni = (k[0] == k[1]) && (k[1] == k[2]) && (k[2] == k[3]) && (k[0] >= 0);
+    if (__all_sync(0xffffffffu, uni)) {
+        const int lane = threadIdx.x & 31;
+        unsigned mask = __match_any_sync(0xffffffffu, k[0]);
+        int leader = __ffs(mask) - 1;
+        unsigned base = 0;
+        if (lane == leader) base = atomicAdd(&hist[k[0]], 4u * (unsigned)__popc(mask));
+        base = __shfl_sync(mask, base, leader) + 4u * (unsigned)__popc(mask & ((1u << lane) - 1));
+#pragma unroll
+        for (int u = 0; u < 4; u++) slot[u] = base + u;
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) slot[u] = smem_claim(hist, k[u], k[u] >= 0);
+}
+
+// ---- TMA bulk copy global -> shared with an mbarrier (1-D: no tensor map needed)
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NBK_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NBK_DONE;\n"
+        "bra NBK_WAIT;\n"
+        "NBK_DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// workspace header words
+enum { HDR_QUEUE = 0, HDR_ABSMAX = 1, HDR_MODE = 2, HDR_WORDS = 64 };
+
+struct BucketPlan {          // one bucketing configuration (host side, by value)
+    int mode;                // value of the probe flag that selects this configuration
+    int W;                   // tile window (entries of the shared histogram)
+    int nchunks;             // particle chunks (CTAs loop over them)
+    int64_t chunk;           // particles per chunk, multiple of 4
+    int staged;              // particle coordinates staged by TMA bulk copies (needs a 16-byte aligned array)
+};
+
+// Is the catalogue spatially coherent in array order?  256 threads sample neighbouring pairs (i, i+1): coherent pairs
+// lie within one plane of tiles of each other.  mode <- 1 (coherent) when >= 3/4 of the valid pairs are.
+template <int SUP, typename PT>
+__global__ void __launch_bounds__(256)
+k_bucket_probe(const PT *__restrict__ pos, int64_t n, TileGeom tg, unsigned *__restrict__ hdr) {
+    __shared__ int s_ok, s_tot;
+    if (threadIdx.x == 0) { s_ok = 0; s_tot = 0; }
+    __syncthreads();
+    const int plane = tg.nt[1] * tg.nt[2];
+    int64_t j = (n > 1) ? (int64_t)((double)threadIdx.x / 256.0 * (double)(n - 1)) : 0;
+    if (j + 1 < n) {
+        PT a[3] = {pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]};
+        PT b[3] = {pos[3 * j + 3], pos[3 * j + 4], pos[3 * j + 5]};
+        int ta = tile_of_exact<SUP, PT>(a, tg), tb = tile_of_exact<SUP, PT>(b, tg);
+        if (ta >= 0 && tb >= 0) {
+            atomicAdd(&s_tot, 1);
+            int d = ta / plane - tb / plane;
+            if (d >= -1 && d <= 1) atomicAdd(&s_ok, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) hdr[HDR_MODE] = (s_tot > 0 && 4 * s_ok >= 3 * s_tot) ? 1u : 0u;
+}
+
+// quad of this thread from the staged chunk (shared memory) or straight from global memory
 template <typename PT>
-__device__ __forceinline__ void load4(const PT *__restrict__ cpos, int j0, int nv, bool aligned, PT (&x)[4][3]) {
-    // cpos = first particle of the CTA's chunk, j0 = chunk-relative index of the quad (j0 % 4 == 0), nv = valid ones
+__device__ __forceinline__ void load_quad_smem(const PT *sbuf, PT (&x)[4][3]) {
+    constexpr int NV = (int)(12 * sizeof(PT) / 16);
+    const uint4 *v = reinterpret_cast<const uint4 *>(sbuf + 12 * threadIdx.x);
+    uint4 r[NV];
+#pragma unroll
+    for (int k = 0; k < NV; k++) r[k] = v[k];
+    const PT *f = reinterpret_cast<const PT *>(r);
+#pragma unroll
+    for (int u = 0; u < 4; u++) { x[u][0] = f[3 * u]; x[u][1] = f[3 * u + 1]; x[u][2] = f[3 * u + 2]; }
+}
+template <typename PT>
+__device__ __forceinline__ void load_quad_gmem(const PT *__restrict__ cpos, int j0, int nv, bool aligned, PT (&x)[4][3]) {
     if (aligned && nv == 4) {
         constexpr int NV = (int)(12 * sizeof(PT) / 16);
         const uint4 *v = reinterpret_cast<const uint4 *>(cpos + 3 * j0);
@@ -380,98 +552,167 @@ __device__ __forceinline__ void load4(const PT *__restrict__ cpos, int j0, int n
     }
 }
 
-// Tile id of particle i.  float32 positions take a float32 fast path: g32 = x*scale differs from the f8 grid
-// coordinate by < 2^-22 |g|, so unless the fraction of (g32 + A) lies within 3e-7|g| of a cell boundary (or the
-// particle is far outside the box) floor() agrees with the exact arithmetic; the rare rest is recomputed in f8.
-// The result is therefore ALWAYS the exact leftmost cell -- count, scatter and paint passes agree.
-// per-launch constants of the float32 fast path
-struct FastTile {
-    float sc[3];    // float32 scale N/L
-    float lim[3];   // accept when |frac(g) - 0.5| < lim  (frac at least eps away from both cell boundaries)
-};
-
-static FastTile make_fast_tile(const TileGeom &tg) {      // host side: passed to the kernels by value
-    FastTile f;
-    for (int d = 0; d < 3; d++) {
-        f.sc[d] = (float)tg.gm.scale[d];
-        // |g32 - g_exact| <= 2 float32 roundings of a value below n+2 -> 3e-7 (n+2) + 1e-6 is a safe margin
-        f.lim[d] = 0.5f - (3e-7f * (float)(tg.gm.n[d] + 2) + 1e-6f);
-    }
-    return f;
+__device__ __forceinline__ double load_mass(const void *mass, int mass_f4, int64_t i) {
+    return mass_f4 ? (double)((const float *)mass)[i] : ((const double *)mass)[i];
 }
 
-// Tile id of particle i.  float32 in-box positions take a float32 fast path: unless the fraction of
-// (x*scale + A) lies within the rounding margin of a cell boundary, floor() agrees with the exact f8 arithmetic;
-// everything else (near-boundary, outside the box, f8 positions) is recomputed in f8.  The id is therefore
-// ALWAYS the exact leftmost cell's tile -- count, scatter and paint passes agree.
-template <int SUP, typename PT>
-__device__ __forceinline__ int tile_of(const PT *x, const PT *__restrict__ pos, int64_t i, const TileGeom &tg,
-                                       const FastTile &ft) {
-    if (sizeof(PT) == 4) {
-        int c[3];
-        bool ok = true;
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            float g = (float)x[d] * ft.sc[d];
-            if (WinOff<SUP>::A != 0.f) g += WinOff<SUP>::A;
-            float f = floorf(g);
-            ok = ok && (fabsf((g - f) - 0.5f) < ft.lim[d]);
-            c[d] = (int)f + WinOff<SUP>::B;
-            ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
+// The chunk loop shared by the count and the scatter pass.  Rounds of 4 * blockDim particles: every thread owns one
+// aligned quad per round.  STAGED: thread 0 keeps two rounds in flight as TMA bulk copies into a shared-memory ring
+// (full rounds only; the ragged tail of the last chunk is read directly).  `body(j0, nv, x)` is called by ALL threads
+// (nv = 0 for idle ones) so that it may use warp collectives.
+template <typename PT, bool STAGED, typename F>
+__device__ __forceinline__ void chunk_rounds(const PT *__restrict__ cpos, int cn, PT *sring, uint64_t *bars,
+                                             unsigned &seq, bool aligned, F body) {
+    const int SP = 4 * (int)blockDim.x;                       // particles per round
+    const int nround = (cn + SP - 1) / SP;
+    const unsigned rbytes = (unsigned)(SP * 3 * sizeof(PT));
+    const int nfull = STAGED ? cn / SP : 0;                   // rounds that are copied whole
+    if (STAGED && threadIdx.x == 0) {
+        for (int s = 0; s < 2 && s < nfull; s++) {
+            const unsigned q = seq + s;
+            mbar_expect_tx(&bars[q & 1], rbytes);
+            bulk_g2s(sring + (size_t)(q & 1) * SP * 3, cpos + (size_t)s * SP * 3, rbytes, &bars[q & 1]);
         }
-        if (ok) return tile_from_cells(c, tg);
     }
-    return tile_of_exact<SUP, PT>(pos, i, tg);
+    for (int s = 0; s < nround; s++) {
+        const int j0 = s * SP + 4 * (int)threadIdx.x;
+        const int nv = min(4, max(0, cn - j0));
+        PT x[4][3];
+        if (STAGED && s < nfull) {
+            const unsigned q = seq + s;
+            mbar_wait(&bars[q & 1], (q >> 1) & 1);
+            load_quad_smem(sring + (size_t)(q & 1) * SP * 3, x);
+        } else {
+            load_quad_gmem(cpos, j0, nv, aligned, x);
+        }
+        body(j0, nv, x);
+        if (STAGED && s < nfull) {
+            __syncthreads();                                   // every thread has read this ring slot
+            if (threadIdx.x == 0 && s + 2 < nfull) {
+                const unsigned q = seq + s + 2;
+                mbar_expect_tx(&bars[q & 1], rbytes);
+                bulk_g2s(sring + (size_t)(q & 1) * SP * 3, cpos + (size_t)(s + 2) * SP * 3, rbytes, &bars[q & 1]);
+            }
+        }
+    }
+    if (STAGED) seq += (unsigned)nfull;
 }
 
-// one atomic per distinct key per warp; returns this lane's rank within its key group and the group's base
-__device__ __forceinline__ unsigned warp_claim(unsigned *counter, int key, bool active) {
-    const int lane = threadIdx.x & 31;
-    // fast path: the whole warp is active and in one tile (spatially coherent catalogues)
-    int k0 = __shfl_sync(0xffffffffu, key, 0);
-    if (__all_sync(0xffffffffu, active && key == k0)) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(&counter[key], 32u);
-        return __shfl_sync(0xffffffffu, base, 0) + lane;
+// exact tile ids of a quad (fast float32 path, exact recomputation where it is not decisive)
+template <int SUP, typename PT>
+__device__ __forceinline__ void quad_tiles(const PT (&x)[4][3], int nv, const TileGeom &tg, const FastTile &ft, int (&t)[4]) {
+    bool redo = false;
+    bool okv[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        t[u] = tile_fast<SUP, PT>(x[u], tg, ft, okv[u]);
+        redo = redo || (!okv[u] && u < nv);
     }
-    unsigned mask = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
-    if (!active) return 0;
-    int leader = __ffs(mask) - 1;
-    unsigned rank = __popc(mask & ((1u << lane) - 1));
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(&counter[key], (unsigned)__popc(mask));
-    base = __shfl_sync(mask, base, leader);
-    return base + rank;
+    if (redo) {                                  // rare: near a cell boundary / outside the box / f8 positions
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (!okv[u] && u < nv) t[u] = tile_of_exact<SUP, PT>(x[u], tg);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) if (u >= nv) t[u] = -1;
 }
 
-template <int SUP, typename PT, typename MT>
-__global__ void __launch_bounds__(256)
-k_tile_count(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg, FastTile ft,
-             unsigned *__restrict__ counts, unsigned *__restrict__ absmax_bits, int *__restrict__ tile_ids) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+// window start of a chunk: 16 evenly spaced samples, the smallest plane of tiles among them minus one plane
+template <int SUP, typename PT>
+__device__ __forceinline__ int chunk_window_lo(const PT *__restrict__ cpos, int cn, const TileGeom &tg, int W, int *s_lo) {
+    if (W >= tg.ntiles) return 0;
+    if (threadIdx.x < 32) {
+        int t = 0x7fffffff;
+        if (threadIdx.x < 16 && cn > 0) {
+            int j = (int)((int64_t)threadIdx.x * (cn - 1) / 15);
+            PT x[3] = {cpos[3 * j], cpos[3 * j + 1], cpos[3 * j + 2]};
+            int tt = tile_of_exact<SUP, PT>(x, tg);
+            if (tt >= 0) t = tt;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = min(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (threadIdx.x == 0) {
+            const int plane = tg.nt[1] * tg.nt[2];
+            int lo = (t == 0x7fffffff) ? 0 : (t / plane - 1) * plane;
+            lo = max(0, min(lo, tg.ntiles - W));
+            *s_lo = lo;
+        }
+    }
+    __syncthreads();
+    return *s_lo;
+}
+
+template <int SUP, typename PT, bool STAGED>
+__global__ void __launch_bounds__(1024)
+k_bucket_count(const PT *__restrict__ pos, const void *__restrict__ mass, int mass_f4, int64_t n, TileGeom tg, FastTile ft,
+               unsigned *__restrict__ hdr, unsigned *__restrict__ cnt_w, unsigned *__restrict__ cnt_o,
+               unsigned *__restrict__ blk, int *__restrict__ win_lo, BucketPlan bp) {
+    if ((int)hdr[HDR_MODE] != bp.mode) return;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    unsigned *s_hist = reinterpret_cast<unsigned *>(s_raw);
+    PT *sring = reinterpret_cast<PT *>(s_raw + (((size_t)bp.W * sizeof(unsigned) + 127) & ~(size_t)127));
+    __shared__ uint64_t bars[2];
+    __shared__ int s_lo;
+    if (STAGED && threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+    unsigned seq = 0;
     float mx = 0.f;
-    int64_t nround = ((n + stride - 1) / stride) * stride;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        bool in = i < n;
-        PT x[3] = {0, 0, 0};
-        if (in) { x[0] = pos[3 * i]; x[1] = pos[3 * i + 1]; x[2] = pos[3 * i + 2]; }
-        int t = in ? tile_of<SUP, PT>(x, pos, i, tg, ft) : -1;
-        if (in) tile_ids[i] = t;          // the scatter pass reuses the id instead of recomputing it
-        warp_claim(counts, t, t >= 0);
-        if (mass && in && t >= 0) mx = fmaxf(mx, fabsf((float)mass[i]) * 1.0000001f);
+    for (int c = blockIdx.x; c < bp.nchunks; c += gridDim.x) {
+        const int64_t b = (int64_t)c * bp.chunk;
+        const int64_t e = (b + bp.chunk < n) ? b + bp.chunk : n;
+        const int cn = e > b ? (int)(e - b) : 0;
+        const PT *cpos = pos + 3 * b;
+        for (int i = threadIdx.x; i < bp.W; i += blockDim.x) s_hist[i] = 0;
+        __syncthreads();
+        const int lo = chunk_window_lo<SUP, PT>(cpos, cn, tg, bp.W, &s_lo);
+        if (threadIdx.x == 0) win_lo[c] = lo;
+        chunk_rounds<PT, STAGED>(cpos, cn, sring, bars, seq, aligned, [&](int j0, int nv, const PT (&x)[4][3]) {
+            int t[4], k[4];
+            quad_tiles<SUP, PT>(x, nv, tg, ft, t);
+            bool anyout = false;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const unsigned r = (unsigned)(t[u] - lo);
+                k[u] = (t[u] >= 0 && r < (unsigned)bp.W) ? (int)r : -1;
+                anyout = anyout || (t[u] >= 0 && k[u] < 0);
+            }
+            unsigned slot[4];
+            quad_claim(s_hist, k, slot);
+            if (__any_sync(0xffffffffu, anyout)) {
+#pragma unroll
+                for (int u = 0; u < 4; u++) warp_claim(cnt_o, t[u], t[u] >= 0 && k[u] < 0);
+            }
+            if (mass) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (t[u] >= 0) mx = fmaxf(mx, fabsf((float)load_mass(mass, mass_f4, b + j0 + u)) * 1.0000001f);
+            }
+        });
+        __syncthreads();
+        // reserve this chunk's share of every bucket: one global atomic per (chunk, tile)
+        unsigned *row = blk + (size_t)c * bp.W;
+        for (int i = threadIdx.x; i < bp.W; i += blockDim.x) {
+            const unsigned h = s_hist[i];
+            row[i] = h ? atomicAdd(&cnt_w[lo + i], h) : 0u;
+        }
+        __syncthreads();
     }
     if (mass) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(absmax_bits, __float_as_uint(mx));  // positive floats order as uints
+        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(&hdr[HDR_ABSMAX], __float_as_uint(mx));  // positive floats order as uints
     }
 }
 
-// single-CTA exclusive scan (4 counters per thread and round, warp shuffles + one shared hop); also clears the
-// cursors and the tile queue head
+// single-CTA exclusive scan of cnt_w + cnt_o (4 counters per thread and round, warp shuffles + one shared hop);
+// also clears the outlier cursors, the per-tile flags and the tile queue head
 __global__ void __launch_bounds__(1024)
-k_tile_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ offsets, unsigned *__restrict__ cursor,
-            unsigned *__restrict__ queue, int ntiles) {
+k_tile_scan(const unsigned *__restrict__ cnt_w, const unsigned *__restrict__ cnt_o, unsigned *__restrict__ offsets,
+            unsigned *__restrict__ cur_o, unsigned *__restrict__ flags, unsigned *__restrict__ hdr, int ntiles) {
     __shared__ unsigned warp_tot[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     unsigned carry = 0;
@@ -479,13 +720,13 @@ k_tile_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ offsets,
         const int i = base + threadIdx.x * 4;
         unsigned v[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = (i + j < ntiles) ? counts[i + j] : 0u;
+        for (int j = 0; j < 4; j++) v[j] = (i + j < ntiles) ? cnt_w[i + j] + cnt_o[i + j] : 0u;
         const unsigned s = v[0] + v[1] + v[2] + v[3];
         unsigned inc = s;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
+            unsigned nn = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += nn;
         }
         if (lane == 31) warp_tot[wid] = inc;
         __syncthreads();
@@ -493,8 +734,8 @@ k_tile_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ offsets,
             unsigned x = warp_tot[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                unsigned n = __shfl_up_sync(0xffffffffu, x, o);
-                if (lane >= o) x += n;
+                unsigned nn = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += nn;
             }
             warp_tot[lane] = x;
         }
@@ -502,239 +743,78 @@ k_tile_scan(const unsigned *__restrict__ counts, unsigned *__restrict__ offsets,
         unsigned run = carry + (wid ? warp_tot[wid - 1] : 0u) + inc - s;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            if (i + j < ntiles) { offsets[i + j] = run; cursor[i + j] = 0; }
+            if (i + j < ntiles) { offsets[i + j] = run; cur_o[i + j] = 0; flags[i + j] = 0; }
             run += v[j];
         }
         carry += warp_tot[31];
         __syncthreads();
     }
-    if (threadIdx.x == 0) { offsets[ntiles] = carry; queue[0] = 0; }
+    if (threadIdx.x == 0) { offsets[ntiles] = carry; hdr[HDR_QUEUE] = 0; }
 }
 
-template <int SUP, typename PT, typename MT>
-__global__ void __launch_bounds__(256)
-k_tile_scatter(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, TileGeom tg,
-               const unsigned *__restrict__ offsets, unsigned *__restrict__ cursor,
-               TileRec *__restrict__ recs, MT *__restrict__ smass, const int *__restrict__ tile_ids) {
-    int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    int64_t nround = ((n + stride - 1) / stride) * stride;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
-        bool in = i < n;
-        int t = in ? tile_ids[i] : -1;
-        TileRec r = make_uint4(0, 0, 0, 0);
-        if (t >= 0) {
-            PT x[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
-            t = make_record<SUP, PT>(x, pos, i, tg, r);
-        }
-        unsigned slot = warp_claim(cursor, t, t >= 0);
-        if (t >= 0) {
-            int64_t dst = (int64_t)offsets[t] + slot;
-            recs[dst] = r;                       // one 16-byte store per particle
-            if (mass) smass[dst] = mass[i];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// CTA-local bucketing (ntiles * 4 B fits in shared memory): CTA c owns the contiguous particle chunk
-// [c*chunk, (c+1)*chunk).  Pass A histograms its chunk in shared memory (native ATOMS.ADD.U32, no global
-// atomics) and stores the histogram as row c of blk[G][ntiles]; pass B turns every column into an exclusive
-// prefix over c and the column totals into tile offsets; pass C reloads row c as shared cursors and scatters the
-// same chunk.  Slot order inside a tile is arbitrary, the fixed-point accumulation makes the mesh independent of it.
-// ---------------------------------------------------------------------------------------------
-// Shared-memory counter claim.  Random catalogues: one native ATOMS per lane.  Spatially coherent catalogues put many
-// lanes of a warp on the same counter, which the atomic unit serialises; when neighbouring lanes agree often, the
-// warp aggregates equal keys first (one ATOMS per distinct key).  Must be called by all 32 lanes.
-__device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool active) {
-    const int lane = threadIdx.x & 31;
-    int kn = __shfl_xor_sync(0xffffffffu, key, 1);
-    unsigned same = __ballot_sync(0xffffffffu, active && kn == key);
-    if (__popc(same) < 8) return active ? atomicAdd(&hist[key], 1u) : 0u;
-    unsigned mask = __match_any_sync(0xffffffffu, active ? key : -1 - lane);
-    if (!active) return 0u;
-    int leader = __ffs(mask) - 1;
-    unsigned base = 0;
-    if (lane == leader) base = atomicAdd(&hist[key], (unsigned)__popc(mask));
-    return __shfl_sync(mask, base, leader) + __popc(mask & ((1u << lane) - 1));
-}
-
-// float32 fast path of tile_of without the fallback: ok == false means "recompute exactly"
-template <int SUP, typename PT>
-__device__ __forceinline__ int tile_fast(const PT *x, const TileGeom &tg, const FastTile &ft, bool &ok) {
-    ok = sizeof(PT) == 4;
-    int c[3] = {0, 0, 0};
-    if (sizeof(PT) == 4) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) {
-            float g = (float)x[d] * ft.sc[d];
-            if (WinOff<SUP>::A != 0.f) g += WinOff<SUP>::A;
-            float f = floorf(g);
-            ok = ok && (fabsf((g - f) - 0.5f) < ft.lim[d]);
-            c[d] = (int)f + WinOff<SUP>::B;
-            ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
-        }
-    }
-    return ok ? tile_from_cells(c, tg) : -1;
-}
-
-// Claim slots for the (up to) four particles of a thread's quad.  Coherent input: when every lane's quad lies in one
-// tile, the quad is claimed as a unit (then usually the whole warp as one ATOMS); otherwise particle by particle.
-// Returns the slot of the quad's first particle in `slot[0..3]`.  All 32 lanes must call.
-__device__ __forceinline__ void quad_claim(unsigned *hist, const int (&t)[4], unsigned (&slot)[4]) {
-    const bool uni = (t[0] == t[1]) && (t[1] == t[2]) && (t[2] == t[3]) && (t[0] >= 0);
-    if (__all_sync(0xffffffffu, uni)) {
-        const int lane = threadIdx.x & 31;
-        unsigned mask = __match_any_sync(0xffffffffu, t[0]);
-        int leader = __ffs(mask) - 1;
-        unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&hist[t[0]], 4u * (unsigned)__popc(mask));
-        base = __shfl_sync(mask, base, leader) + 4u * (unsigned)__popc(mask & ((1u << lane) - 1));
-#pragma unroll
-        for (int u = 0; u < 4; u++) slot[u] = base + u;
-        return;
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) slot[u] = smem_claim(hist, t[u], t[u] >= 0);
-}
-
-template <int SUP, typename PT, typename MT, bool HASM>
+template <int SUP, typename PT, bool STAGED>
 __global__ void __launch_bounds__(1024)
-k_tile_count_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
-                 FastTile ft, unsigned *__restrict__ blk, unsigned *__restrict__ absmax_bits, uint4 *__restrict__ zero1,
-                 uint4 *__restrict__ zero2, int64_t zero_n) {
-    extern __shared__ __align__(16) unsigned s_hist[];
-    for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) s_hist[t] = 0;
-    __syncthreads();
-    const int64_t b = (int64_t)blockIdx.x * chunk;
-    const int64_t e = (b + chunk < n) ? b + chunk : n;
-    const int cn = e > b ? (int)(e - b) : 0;           // particles of this CTA (chunk-relative 32-bit indices below)
-    const PT *cpos = pos + 3 * b;
-    const MT *cmass = HASM ? mass + b : nullptr;
-    float mx = 0.f;
-    // 4 consecutive particles per thread and round: the coordinate loads are issued before the first is consumed (the
-    // pass is bound by memory latency at 32 warps / SM) and, for aligned arrays, are 16-byte vectors
+k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int mass_f4, int64_t n, TileGeom tg,
+                 const unsigned *__restrict__ hdr, const unsigned *__restrict__ offsets,
+                 const unsigned *__restrict__ cnt_w, unsigned *__restrict__ cur_o, const unsigned *__restrict__ blk,
+                 const int *__restrict__ win_lo, unsigned *__restrict__ recs, void *__restrict__ smass, BucketPlan bp) {
+    if ((int)hdr[HDR_MODE] != bp.mode) return;
+    extern __shared__ __align__(128) unsigned char s_raw[];
+    unsigned *s_cur = reinterpret_cast<unsigned *>(s_raw);
+    PT *sring = reinterpret_cast<PT *>(s_raw + (((size_t)bp.W * sizeof(unsigned) + 127) & ~(size_t)127));
+    __shared__ uint64_t bars[2];
+    if (STAGED && threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
-    // hold=False: this pass also clears the mesh(es) -- zero_n 16-byte vectors each, a contiguous share per CTA, three
-    // stores per round riding in the shadow of the (latency-bound) particle loads; the tile pass runs later in-stream
-    const int64_t zper = zero1 ? (zero_n + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t zbeg = (int64_t)blockIdx.x * zper;
-    const int zcnt = zero1 ? (int)((zbeg + zper < zero_n ? zbeg + zper : zero_n) - zbeg) : 0;   // may be <= 0
-    uint4 *z1 = zero1 ? zero1 + zbeg : nullptr, *z2 = zero2 ? zero2 + zbeg : nullptr;
-    int zi = threadIdx.x;
-    const uint4 zz = make_uint4(0, 0, 0, 0);
-    for (int base = 0; base < cn; base += 4 * (int)blockDim.x) {     // uniform trip count (warp collectives)
-        const int j0 = base + 4 * (int)threadIdx.x;
-        const int nv = min(4, max(0, cn - j0));                       // valid particles of my quad
-        PT x[4][3];
-        MT mv[4];
-        load4(cpos, j0, nv, aligned, x);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            if (zi < zcnt) { z1[zi] = zz; if (z2) z2[zi] = zz; }
-            zi += blockDim.x;
-        }
-        if (HASM) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) mv[u] = (u < nv) ? cmass[j0 + u] : (MT)0;
-        }
-        int t[4];
-        bool redo = false;
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            bool ok;
-            t[u] = tile_fast<SUP, PT>(x[u], tg, ft, ok);
-            redo = redo || (!ok && u < nv);
-        }
-        if (redo) {                                  // rare: near a cell boundary / outside the box / f8 positions
+    unsigned seq = 0;
+    for (int c = blockIdx.x; c < bp.nchunks; c += gridDim.x) {
+        const int64_t b = (int64_t)c * bp.chunk;
+        const int64_t e = (b + bp.chunk < n) ? b + bp.chunk : n;
+        const int cn = e > b ? (int)(e - b) : 0;
+        const PT *cpos = pos + 3 * b;
+        const int lo = win_lo[c];
+        const unsigned *row = blk + (size_t)c * bp.W;
+        const int wn = min(bp.W, tg.ntiles - lo);
+        for (int i = threadIdx.x; i < wn; i += blockDim.x) s_cur[i] = offsets[lo + i] + row[i];
+        __syncthreads();
+        chunk_rounds<PT, STAGED>(cpos, cn, sring, bars, seq, aligned, [&](int j0, int nv, const PT (&x)[4][3]) {
+            unsigned r[4][3];
+            int t[4], k[4];
+            bool anyout = false;
 #pragma unroll
             for (int u = 0; u < 4; u++) {
-                bool ok;
-                tile_fast<SUP, PT>(x[u], tg, ft, ok);
-                if (!ok && u < nv) t[u] = tile_of_exact<SUP, PT>(cpos, j0 + u, tg);
+                r[u][0] = r[u][1] = r[u][2] = 0;
+                t[u] = (u < nv) ? make_record<SUP, PT>(x[u], tg, r[u]) : -1;
+                const unsigned rel = (unsigned)(t[u] - lo);
+                k[u] = (t[u] >= 0 && rel < (unsigned)bp.W) ? (int)rel : -1;
+                anyout = anyout || (t[u] >= 0 && k[u] < 0);
             }
-        }
+            unsigned slot[4];
+            quad_claim(s_cur, k, slot);
+            if (__any_sync(0xffffffffu, anyout)) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (u >= nv) t[u] = -1;
-        unsigned slot[4];
-        quad_claim(s_hist, t, slot);
-        if (HASM) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) if (t[u] >= 0) mx = fmaxf(mx, fabsf((float)mv[u]) * 1.0000001f);
-        }
-    }
-    for (; zi < zcnt; zi += blockDim.x) { z1[zi] = zz; if (z2) z2[zi] = zz; }
-    if (HASM) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(absmax_bits, __float_as_uint(mx));
-    }
-    __syncthreads();
-    unsigned *row = blk + (size_t)blockIdx.x * tg.ntiles;
-    for (int t = threadIdx.x; t < tg.ntiles; t += blockDim.x) row[t] = s_hist[t];
-}
-
-// column pass: blk[c][t] <- sum_{c' < c} blk[c'][t];  counts[t] <- column total.  16 independent loads in flight
-// per thread (the column is a chain of G dependent adds, not of G dependent memory round trips)
-__global__ void __launch_bounds__(128)
-k_tile_colscan(unsigned *__restrict__ blk, unsigned *__restrict__ counts, int ntiles, int G) {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= ntiles) return;
-    unsigned run = 0;
-    for (int c0 = 0; c0 < G; c0 += 16) {
-        unsigned v[16];
-#pragma unroll
-        for (int j = 0; j < 16; j++) v[j] = (c0 + j < G) ? blk[(size_t)(c0 + j) * ntiles + t] : 0u;
-#pragma unroll
-        for (int j = 0; j < 16; j++) {
-            if (c0 + j < G) blk[(size_t)(c0 + j) * ntiles + t] = run;
-            run += v[j];
-        }
-    }
-    counts[t] = run;
-}
-
-template <int SUP, typename PT, typename MT, bool HASM>
-__global__ void __launch_bounds__(1024)
-k_tile_scatter_blk(const PT *__restrict__ pos, const MT *__restrict__ mass, int64_t n, int64_t chunk, TileGeom tg,
-                   const unsigned *__restrict__ offsets, const unsigned *__restrict__ blk,
-                   TileRec *__restrict__ recs, MT *__restrict__ smass) {
-    extern __shared__ __align__(16) unsigned s_cur[];
-    const int ntiles = tg.ntiles;
-    const unsigned *row = blk + (size_t)blockIdx.x * ntiles;
-    for (int t = threadIdx.x; t < ntiles; t += blockDim.x) s_cur[t] = offsets[t] + row[t];
-    __syncthreads();
-    const int64_t b = (int64_t)blockIdx.x * chunk;
-    const int64_t e = (b + chunk < n) ? b + chunk : n;
-    const int cn = e > b ? (int)(e - b) : 0;
-    const PT *cpos = pos + 3 * b;
-    const MT *cmass = HASM ? mass + b : nullptr;
-    const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
-    for (int base = 0; base < cn; base += 4 * (int)blockDim.x) {     // see k_tile_count_blk
-        const int j0 = base + 4 * (int)threadIdx.x;
-        const int nv = min(4, max(0, cn - j0));
-        PT x[4][3];
-        MT mv[4];
-        load4(cpos, j0, nv, aligned, x);
-        if (HASM) {
-#pragma unroll
-            for (int u = 0; u < 4; u++) mv[u] = (u < nv) ? cmass[j0 + u] : (MT)0;
-        }
-        TileRec r[4];
-        int t[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            r[u] = make_uint4(0, 0, 0, 0);
-            t[u] = (u < nv) ? make_record<SUP, PT>(x[u], cpos, j0 + u, tg, r[u]) : -1;
-        }
-        unsigned slot[4];
-        quad_claim(s_cur, t, slot);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            if (t[u] >= 0) {
-                recs[slot[u]] = r[u];
-                if (HASM) smass[slot[u]] = mv[u];
+                for (int u = 0; u < 4; u++) {
+                    const bool out = t[u] >= 0 && k[u] < 0;
+                    unsigned so = warp_claim(cur_o, t[u], out);
+                    if (out) slot[u] = offsets[t[u]] + cnt_w[t[u]] + so;     // outliers follow the windowed shares
+                }
             }
-        }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (t[u] >= 0) {
+                    unsigned *dst = recs + 3 * (size_t)slot[u];
+                    dst[0] = r[u][0]; dst[1] = r[u][1]; dst[2] = r[u][2];
+                    if (mass) {
+                        if (mass_f4) ((float *)smass)[slot[u]] = ((const float *)mass)[b + j0 + u];
+                        else ((double *)smass)[slot[u]] = ((const double *)mass)[b + j0 + u];
+                    }
+                }
+            }
+        });
+        __syncthreads();
     }
 }
 
@@ -781,51 +861,76 @@ template <> struct WinD<4> { static constexpr double DMIN = 1.0;
         for (int r = 0; r < 4; r++) w[r] = pcs_kernel(d - (double)r);
     } };
 
-// FLUSH 0: per-cell read-add-store (exclusive cells) / REDG (halo)   1: TMA bulk reduce-add, one row per op
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// FLUSH 0: ordered write-back (first tile in queue order stores a cell, later ones add; no cleared mesh needed)
+// FLUSH 1: TMA bulk reduce-add, one row per op, into an existing mesh (hold=True)
 template <int SUP, typename MT, typename FT, bool SHIFTED, int FLUSH>
 __global__ void __launch_bounds__(256)
-k_tile_paint(const TileRec *__restrict__ recs, const MT *__restrict__ smass, TileGeom tg,
-             const unsigned *__restrict__ offsets, unsigned *__restrict__ queue,
-             const unsigned *__restrict__ absmax_bits, FT *__restrict__ mesh) {
+k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, TileGeom tg,
+             const unsigned *__restrict__ offsets, unsigned *__restrict__ hdr, unsigned *__restrict__ flags,
+             unsigned epoch, int spread, FT *__restrict__ mesh) {
     extern __shared__ __align__(16) unsigned s_acc[];
     constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0);   // == tg.R
     constexpr int RP = (R + 3) & ~3;                         // row pitch in cells: rows start 16-byte aligned
     constexpr int NC = R * R * RP;                           // multiple of 4
+    constexpr int H = R - TILE;   // cells with a local coordinate < H are also written by the preceding tile
     unsigned *s_lo = s_acc, *s_hi = s_acc + NC;
     __shared__ int s_tile;
     // scale 2^31 / M, M = power of two >= max |mass|
     double M = 1.0;
     if (smass) {
-        float mx = __uint_as_float(*absmax_bits);
+        float mx = __uint_as_float(hdr[HDR_ABSMAX]);
         int e;
         frexpf(mx, &e);
         M = mx > 0.f ? ldexp(1.0, e) : 1.0;
     }
     const double S = 2147483648.0 / M, invS = M / 2147483648.0;
-    constexpr int H = R - TILE;   // cells with a local coordinate < H may also be written by the preceding tile
     constexpr int PER = (NC + 255) / 256;
+    for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
     for (;;) {
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(queue, 1u);
-        __syncthreads();
-        int t = s_tile;
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);
+        __syncthreads();                                     // also: the accumulator is zero (start / end of last tile)
+        const int t = s_tile;
         if (t >= tg.ntiles) break;
-        unsigned b = offsets[t], e = offsets[t + 1];
-        if (b == e) { __syncthreads(); continue; }
-        for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
-        int tz = t % tg.nt[2], ty = (t / tg.nt[2]) % tg.nt[1], tx = t / (tg.nt[2] * tg.nt[1]);
-        int o[3] = {tx * TILE - tg.G, ty * TILE, tz * TILE};   // region origin (x: slab-local)
-        __syncthreads();
-        // the record (and mass) of the next round is requested before this round's deposits are issued
-        unsigned p = b + threadIdx.x;
-        TileRec rn = make_uint4(0, 0, 0, 0);
+        const unsigned b = offsets[t], e = offsets[t + 1];
+        if (FLUSH == 1 && b == e) { __syncthreads(); continue; }
+        const int tz = t % tg.nt[2], ty = (t / tg.nt[2]) % tg.nt[1], tx = t / (tg.nt[2] * tg.nt[1]);
+        const int o[3] = {tx * TILE - tg.G, ty * TILE, tz * TILE};   // region origin (x: slab-local)
+        // Particle -> thread map.  spread == 0: thread p takes records p, p + 256, ... (coalesced).  spread != 0: the
+        // lanes of a warp walk 32 separate segments of the bucket, so that the neighbouring (same-cell) particles of a
+        // spatially coherent catalogue do not meet in one ATOMS instruction.
+        const unsigned cnt = e - b;
+        const unsigned seg = (cnt + 31) / 32;               // records per lane segment (spread mode)
+        const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        unsigned idx = spread ? wid : threadIdx.x;          // spread: position within the lane's segment
+        const unsigned step = spread ? 8u : 256u;
+        const unsigned lim = spread ? min(seg, cnt > lane * seg ? cnt - lane * seg : 0u) : cnt;
+        const unsigned base = spread ? b + lane * seg : b;
+        unsigned rn[3] = {0, 0, 0};
         MT mn = (MT)1;
-        if (p < e) { rn = recs[p]; if (smass) mn = smass[p]; }
-        for (; p < e; p += blockDim.x) {
-            const TileRec r = rn;
+        if (idx < lim) {
+            const unsigned *rp = recs + 3 * (size_t)(base + idx);
+            rn[0] = rp[0]; rn[1] = rp[1]; rn[2] = rp[2];
+            if (smass) mn = smass[base + idx];
+        }
+        for (; idx < lim; idx += step) {
+            const unsigned r0 = rn[0], r1 = rn[1], r2 = rn[2];
             const MT mcur = mn;
-            if (p + blockDim.x < e) { rn = recs[p + blockDim.x]; if (smass) mn = smass[p + blockDim.x]; }
-            unsigned u[3] = {r.x, r.y, r.z};
-            int l[3] = {(int)(r.w & 255u), (int)((r.w >> 8) & 255u), (int)((r.w >> 16) & 255u)};
+            if (idx + step < lim) {                          // next round's record is requested before the deposits
+                const unsigned *rp = recs + 3 * (size_t)(base + idx + step);
+                rn[0] = rp[0]; rn[1] = rp[1]; rn[2] = rp[2];
+                if (smass) mn = smass[base + idx + step];
+            }
+            unsigned u[3] = {r0 << 4, r1 << 4, r2 << 4};
+            int l[3] = {(int)(r0 >> 28), (int)(r1 >> 28), (int)(r2 >> 28)};
             double w[3][SUP];
 #pragma unroll
             for (int d = 0; d < 3; d++) {
@@ -907,27 +1012,73 @@ k_tile_paint(const TileRec *__restrict__ recs, const MT *__restrict__ smass, Til
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused
+            __syncthreads();
+            for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
         } else {
-            // ---- per-cell flush: lanes run along z
-            for (int i = threadIdx.x; i < NC; i += blockDim.x) {
-                unsigned lo = s_lo[i], hi = s_hi[i];
-                if ((lo | hi) == 0u) continue;
-                int cz = i % RP, cy = (i / RP) % R, cx = i / (RP * R);
-                int gx = o[0] + cx + tg.gm.x_start;
-                if (gx < 0) gx += tg.gm.n[0];
-                if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
-                int ix = gx - tg.gm.x_start;
-                if (ix < 0 || ix >= tg.gm.x_n) continue;
-                int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
-                int iz = o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
-                double val = (double)(long long)(((unsigned long long)hi << 32) | lo) * invS;
-                FT *dst = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
-                bool exclusive = cx >= H && cx < TILE && cy >= H && cy < TILE && cz >= H && cz < TILE;
-                if (exclusive) *dst = (FT)((double)*dst + val);
-                else atomicAdd(dst, (FT)val);
+            // ---- ordered write-back.  Along every axis a region cell with local coordinate a is touched by this tile,
+            // by the preceding tile if a < H and by the following one if a >= TILE; queue order is lexicographic in
+            // (tx, ty, tz), so the first toucher of a cell is the per-axis minimum.  [flo, fhi) = cells this tile is
+            // first for along the axis: the preceding tile is earlier unless this is tile 0 (its periodic predecessor
+            // is the LAST tile); the following tile is later unless it wraps around to tile 0.
+            const int tc[3] = {tx, ty, tz};
+            int flo[3], fhi[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                const bool periodic = (d > 0) || tg.full;
+                flo[d] = (tc[d] > 0) ? H : 0;
+                fhi[d] = (periodic && tc[d] == tg.nt[d] - 1) ? TILE : R;
             }
+            // pass 1: plain stores of the cells this tile is first for (every mesh cell is stored exactly once)
+            // pass 2: after the earlier tiles have published their stores: add the rest
+#pragma unroll 1
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1) {
+                    __threadfence();
+                    __syncthreads();
+                    if (threadIdx.x == 0) st_release(&flags[t], epoch);
+                    // up to 26 earlier tiles: {this, preceding, wrapped-following} per axis
+                    if (threadIdx.x < 27) {
+                        int sel[3] = {(int)threadIdx.x % 3, ((int)threadIdx.x / 3) % 3, (int)threadIdx.x / 9};
+                        int nb[3];
+                        bool valid = threadIdx.x != 0;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) {
+                            if (sel[d] == 0) nb[d] = tc[d];
+                            else if (sel[d] == 1) { nb[d] = tc[d] - 1; valid = valid && flo[d] > 0; }
+                            else { nb[d] = 0; valid = valid && fhi[d] < R && tc[d] != 0; }
+                        }
+                        if (valid) {
+                            const unsigned *f = &flags[(nb[0] * tg.nt[1] + nb[1]) * tg.nt[2] + nb[2]];
+                            while (ld_acquire(f) < epoch) __nanosleep(64);
+                        }
+                    }
+                    __syncthreads();
+                }
+                for (int i = threadIdx.x; i < R * R * 32; i += blockDim.x) {
+                    const int row = i >> 5, cz = i & 31;                 // one warp-row per (cx, cy): lanes along z
+                    if (cz >= R) continue;
+                    const int cx = row / R, cy = row - cx * R;
+                    const bool first = cx >= flo[0] && cx < fhi[0] && cy >= flo[1] && cy < fhi[1] && cz >= flo[2] && cz < fhi[2];
+                    if (first != (pass == 0)) continue;
+                    const int si = row * RP + cz;
+                    const unsigned lo = s_lo[si], hi = s_hi[si];
+                    if (pass == 1 && (lo | hi) == 0u) continue;
+                    int gx = o[0] + cx + tg.gm.x_start;
+                    if (gx < 0) gx += tg.gm.n[0];
+                    if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
+                    const int ix = gx - tg.gm.x_start;
+                    if (ix < 0 || ix >= tg.gm.x_n) continue;             // not my plane (ghost semantics)
+                    int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
+                    int iz = o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
+                    const double val = (double)(long long)(((unsigned long long)hi << 32) | lo) * invS;
+                    FT *dst = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
+                    if (pass == 0) *dst = (FT)val;
+                    else atomicAdd(dst, (FT)val);
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
         }
-        __syncthreads();
     }
 }
 
@@ -960,17 +1111,46 @@ extern "C" int nbk_paint_tiled_supported(const int64_t *nmesh, int64_t x_n, int 
     return 1;
 }
 
+// the two bucketing configurations for a problem (only their sizes depend on it)
+static void make_plans(int64_t n, int ntiles, size_t pos_size, bool aligned, BucketPlan &coh, BucketPlan &sca,
+                       int &threads_coh, size_t &smem_coh, int &threads_sca, size_t &smem_sca) {
+    auto chunking = [&](BucketPlan &p, int maxchunks) {
+        int64_t nch = (n + 16383) / 16384;               // at least 16 Ki particles per chunk
+        if (nch < 1) nch = 1;
+        if (nch > maxchunks) nch = maxchunks;
+        p.chunk = (((n + nch - 1) / nch) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
+        if (p.chunk < 4) p.chunk = 4;
+        p.nchunks = (int)((n + p.chunk - 1) / p.chunk);
+        if (p.nchunks < 1) p.nchunks = 1;
+    };
+    coh.mode = 1;
+    coh.W = ntiles < NBK_WIN_COHERENT ? ntiles : NBK_WIN_COHERENT;
+    chunking(coh, NBK_CHUNKS_COHERENT);
+    threads_coh = 512;
+    size_t ring = (size_t)2 * 4 * threads_coh * 3 * pos_size;
+    coh.staged = aligned ? 1 : 0;
+    smem_coh = (((size_t)coh.W * 4 + 127) & ~(size_t)127) + (coh.staged ? ring : 0);
+    sca.mode = 0;
+    sca.W = ntiles < NBK_BLK_SMEM / 4 ? ntiles : NBK_BLK_SMEM / 4;
+    chunking(sca, NBK_CHUNKS_SCATTERED);
+    threads_sca = 1024;
+    ring = (size_t)2 * 4 * threads_sca * 3 * pos_size;
+    sca.staged = (aligned && (((size_t)sca.W * 4 + 127) & ~(size_t)127) + ring <= 224 * 1024) ? 1 : 0;
+    smem_sca = (((size_t)sca.W * 4 + 127) & ~(size_t)127) + (sca.staged ? ring : 0);
+}
+
 extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_dtype, const int64_t *nmesh,
                                              int64_t x_n) {
     int64_t G = 8;
     int64_t nt = ((x_n + G + TILE - 1) / TILE) * ((nmesh[1] + TILE - 1) / TILE) * ((nmesh[2] + TILE - 1) / TILE);
-    size_t bytes = 256;                                  // header: queue, absmax
-    bytes += 3 * align256(sizeof(unsigned) * (nt + 1));  // counts, offsets, cursor
     (void)pos_dtype;
-    bytes += align256((size_t)n * sizeof(TileRec));                      // 16-byte records
-    bytes += align256((size_t)n * sizeof(int));                          // tile id per particle
-    int64_t nh = nt < NBK_BLK_SMEM / 4 ? nt : NBK_BLK_SMEM / 4;
-    bytes += align256(sizeof(unsigned) * (size_t)nh * NBK_SM_COUNT);    // per-CTA tile histograms (CTA-local bucketing)
+    size_t bytes = 256;                                  // header: queue, absmax, mode
+    bytes += 5 * align256(sizeof(unsigned) * (nt + 1));  // cnt_w, cnt_o, offsets, cur_o, flags
+    bytes += align256(sizeof(int) * NBK_CHUNKS_COHERENT);                // window start per chunk
+    int64_t wc = nt < NBK_WIN_COHERENT ? nt : NBK_WIN_COHERENT, ws = nt < NBK_BLK_SMEM / 4 ? nt : NBK_BLK_SMEM / 4;
+    int64_t blk = wc * NBK_CHUNKS_COHERENT > ws * NBK_CHUNKS_SCATTERED ? wc * NBK_CHUNKS_COHERENT : ws * NBK_CHUNKS_SCATTERED;
+    bytes += align256(sizeof(unsigned) * (size_t)blk);                   // per-chunk bucket shares
+    bytes += align256((size_t)n * 12);                                   // 12-byte records
     if (mass_dtype) bytes += align256((size_t)n * (mass_dtype == NBK_F4 ? 4 : 8));
     return (int64_t)bytes;
 }
@@ -984,73 +1164,78 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     if (rc) return rc;
     const FastTile ft = make_fast_tile(tg);
     char *w = (char *)work;
-    unsigned *queue = (unsigned *)w;
-    unsigned *absmax = queue + 1;
+    unsigned *hdr = (unsigned *)w;
     w += 256;
     size_t tb = align256(sizeof(unsigned) * (tg.ntiles + 1));
-    unsigned *counts = (unsigned *)w; w += tb;
+    unsigned *cnt_w = (unsigned *)w; w += tb;
+    unsigned *cnt_o = (unsigned *)w; w += tb;
     unsigned *offsets = (unsigned *)w; w += tb;
-    unsigned *cursor = (unsigned *)w; w += tb;
-    TileRec *spos = (TileRec *)w; w += align256((size_t)n * sizeof(TileRec));
-    int *tile_ids = (int *)w; w += align256((size_t)n * sizeof(int));
-    MT *smass = mass ? (MT *)w : nullptr;
-    if (mass) w += align256((size_t)n * sizeof(MT));
+    unsigned *cur_o = (unsigned *)w; w += tb;
+    unsigned *flags = (unsigned *)w; w += tb;
+    int *win_lo = (int *)w; w += align256(sizeof(int) * NBK_CHUNKS_COHERENT);
+    BucketPlan coh, sca;
+    int th_c, th_s;
+    size_t sm_c, sm_s;
+    const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
+    make_plans(n, tg.ntiles, sizeof(PT), aligned, coh, sca, th_c, sm_c, th_s, sm_s);
     unsigned *blk = (unsigned *)w;
-    static int blk_mode = -1;
-    if (blk_mode < 0) {
-        const char *e = getenv("NBK_PAINT_BUCKET");
-        blk_mode = (e && e[0] == 'g') ? 0 : 1;          // NBK_PAINT_BUCKET=global forces the global-atomic passes
+    {
+        size_t a = (size_t)coh.W * NBK_CHUNKS_COHERENT, b = (size_t)sca.W * NBK_CHUNKS_SCATTERED;
+        w += align256(sizeof(unsigned) * (a > b ? a : b));
     }
-    const size_t hist_bytes = sizeof(unsigned) * (size_t)tg.ntiles;
-    const size_t mesh_bytes = (size_t)gm.x_n * gm.n[1] * gm.n[2] * sizeof(FT);   // multiple of 16 (tiled meshes)
-    const bool use_blk = blk_mode && hist_bytes <= NBK_BLK_SMEM && n >= 4 * (int64_t)tg.ntiles;
-    if (use_blk) {
-        const int G = NBK_SM_COUNT;
-        const int64_t chunk = (((n + G - 1) / G) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
-        NBK_CUDA(cudaMemsetAsync(work, 0, 256, s));        // header
-#define LAUNCH_BLK(HM)                                                                                               \
-        do {                                                                                                         \
-            NBK_CUDA(cudaFuncSetAttribute(k_tile_count_blk<SUP, PT, MT, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)hist_bytes));                                                         \
-            k_tile_count_blk<SUP, PT, MT, HM><<<G, 1024, hist_bytes, s>>>(                                             \
-                (const PT *)pos, (const MT *)mass, n, chunk, tg, ft, blk, absmax, clear ? (uint4 *)mesh : nullptr,   \
-                clear ? (uint4 *)mesh2 : nullptr, (int64_t)(mesh_bytes / 16));                                       \
-            NBK_LAUNCHED();                                                                                          \
-            k_tile_colscan<<<(tg.ntiles + 127) / 128, 128, 0, s>>>(blk, counts, tg.ntiles, G);                        \
-            NBK_LAUNCHED();                                                                                          \
-            k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);                                \
-            NBK_LAUNCHED();                                                                                          \
-            NBK_CUDA(cudaFuncSetAttribute(k_tile_scatter_blk<SUP, PT, MT, HM>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                          (int)hist_bytes));                                                         \
-            k_tile_scatter_blk<SUP, PT, MT, HM><<<G, 1024, hist_bytes, s>>>((const PT *)pos, (const MT *)mass, n, chunk, tg, \
-                                                                          offsets, blk, spos, smass);                \
-            NBK_LAUNCHED();                                                                                          \
-        } while (0)
-        if (mass) LAUNCH_BLK(true); else LAUNCH_BLK(false);
-#undef LAUNCH_BLK
+    unsigned *recs = (unsigned *)w; w += align256((size_t)n * 12);
+    MT *smass = mass ? (MT *)w : nullptr;
+    const int mass_f4 = sizeof(MT) == 4;
+    int force_mode;
+    {
+        const char *e = getenv("NBK_PAINT_BUCKET");      // "coherent" / "scattered" force a configuration (diagnosis)
+        force_mode = (e && e[0] == 'c') ? 1 : (e && e[0] == 's') ? 0 : -1;
+    }
+    NBK_CUDA(cudaMemsetAsync(work, 0, 256 + 2 * tb, s));   // header, cnt_w, cnt_o
+    if (force_mode >= 0) {
+        unsigned m = (unsigned)force_mode;
+        NBK_CUDA(cudaMemcpyAsync(&hdr[HDR_MODE], &m, sizeof(unsigned), cudaMemcpyHostToDevice, s));
     } else {
-        if (clear) {
-            NBK_CUDA(cudaMemsetAsync(mesh, 0, mesh_bytes, s));
-            if (mesh2) NBK_CUDA(cudaMemsetAsync(mesh2, 0, mesh_bytes, s));
-        }
-        NBK_CUDA(cudaMemsetAsync(work, 0, 256 + tb, s));   // header + counts
-        int g = nbk_grid_for(n, 256, 8);
-        k_tile_count<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, ft, counts, absmax, tile_ids);
-        NBK_LAUNCHED();
-        k_tile_scan<<<1, 1024, 0, s>>>(counts, offsets, cursor, queue, tg.ntiles);
-        NBK_LAUNCHED();
-        k_tile_scatter<SUP, PT, MT><<<g, 256, 0, s>>>((const PT *)pos, (const MT *)mass, n, tg, offsets, cursor, spos, smass,
-                                                      tile_ids);
+        k_bucket_probe<SUP, PT><<<1, 256, 0, s>>>((const PT *)pos, n, tg, hdr);
         NBK_LAUNCHED();
     }
-    // tile write-back: TMA bulk reduce-add rows (default) or per-cell stores/REDG (NBK_PAINT_FLUSH=st)
-    static int flush_mode = -1;
-    if (flush_mode < 0) {
-        const char *e = getenv("NBK_PAINT_FLUSH");
-        flush_mode = (e && e[0] == 's') ? 0 : 1;
+    const int grid_c = coh.nchunks < 2 * NBK_SM_COUNT ? coh.nchunks : 2 * NBK_SM_COUNT;
+    const int grid_s = sca.nchunks < NBK_SM_COUNT ? sca.nchunks : NBK_SM_COUNT;
+#define LAUNCH_BUCKET(KERN, ...)                                                                                      \
+    do {                                                                                                              \
+        if (coh.staged) {                                                                                             \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c)); \
+            KERN<SUP, PT, true><<<grid_c, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                         \
+        } else {                                                                                                      \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c)); \
+            KERN<SUP, PT, false><<<grid_c, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                        \
+        }                                                                                                             \
+        NBK_LAUNCHED();                                                                                               \
+        if (sca.staged) {                                                                                             \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                          (int)(sm_s > sm_c ? sm_s : sm_c)));                                         \
+            KERN<SUP, PT, true><<<grid_s, th_s, sm_s, s>>>(__VA_ARGS__, sca);                                         \
+        } else {                                                                                                      \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                          (int)(sm_s > sm_c ? sm_s : sm_c)));                                         \
+            KERN<SUP, PT, false><<<grid_s, th_s, sm_s, s>>>(__VA_ARGS__, sca);                                        \
+        }                                                                                                             \
+        NBK_LAUNCHED();                                                                                               \
+    } while (0)
+    // (the plan is the LAST kernel argument of both passes so that one macro serves them)
+    LAUNCH_BUCKET(k_bucket_count, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, cnt_w, cnt_o, blk, win_lo);
+    k_tile_scan<<<1, 1024, 0, s>>>(cnt_w, cnt_o, offsets, cur_o, flags, hdr, tg.ntiles);
+    NBK_LAUNCHED();
+    LAUNCH_BUCKET(k_bucket_scatter, (const PT *)pos, mass, mass_f4, n, tg, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
+                  (void *)smass);
+#undef LAUNCH_BUCKET
+    int spread_mode;
+    {
+        const char *e = getenv("NBK_PAINT_SPREAD");      // "0": thread p takes records p, p + 256, ... (diagnosis)
+        spread_mode = (e && e[0] == '0') ? 0 : 1;
     }
     // the region edge depends on the mesh being painted (one more cell for the half-cell shifted one); tile ids do not
-#define LAUNCH_TP(SH, FL, MESHP)                                                                                       \
+#define LAUNCH_TP(SH, FL, MESHP, EPOCH)                                                                                \
     do {                                                                                                              \
         const int Rr = TILE + SUP - 1 + ((SH) ? 1 : 0), RPr = (Rr + 3) & ~3;                                          \
         size_t smem = (size_t)2 * Rr * Rr * RPr * sizeof(unsigned);                                                   \
@@ -1061,15 +1246,15 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         if (grid > tg.ntiles) grid = tg.ntiles;                                                                       \
         NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                                    \
-        k_tile_paint<SUP, MT, FT, SH, FL><<<grid, 256, smem, s>>>(spos, smass, tg, offsets, queue, absmax,             \
-                                                                  (FT *)(MESHP));                                     \
+        k_tile_paint<SUP, MT, FT, SH, FL><<<grid, 256, smem, s>>>(recs, smass, tg, offsets, hdr, flags, EPOCH,         \
+                                                                  spread_mode, (FT *)(MESHP));                        \
         NBK_LAUNCHED();                                                                                               \
     } while (0)
-    if (shift != 0.0) { if (flush_mode) LAUNCH_TP(true, 1, mesh); else LAUNCH_TP(true, 0, mesh); }
-    else { if (flush_mode) LAUNCH_TP(false, 1, mesh); else LAUNCH_TP(false, 0, mesh); }
+    if (shift != 0.0) { if (clear) LAUNCH_TP(true, 0, mesh, 1u); else LAUNCH_TP(true, 1, mesh, 1u); }
+    else { if (clear) LAUNCH_TP(false, 0, mesh, 1u); else LAUNCH_TP(false, 1, mesh, 1u); }
     if (mesh2) {
-        NBK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned), s));
-        if (flush_mode) LAUNCH_TP(true, 1, mesh2); else LAUNCH_TP(true, 0, mesh2);
+        NBK_CUDA(cudaMemsetAsync(&hdr[HDR_QUEUE], 0, sizeof(unsigned), s));
+        if (clear) LAUNCH_TP(true, 0, mesh2, 2u); else LAUNCH_TP(true, 1, mesh2, 2u);
     }
 #undef LAUNCH_TP
     return NBK_OK;

@@ -231,20 +231,18 @@ def _legendre_coeffs(ell):
     return np.asarray(legendre(ell).coeffs, dtype="f8")
 
 
-def project_to_basis(y3d, x3d, edges, los=(0, 0, 1), poles=(), hermitian_symmetric=True):
-    """y3d: ndarray (N0,N1,N2c); x3d: 3 broadcastable coordinate arrays (their dtype is part of the
-    contract).  Returns exactly what the reference returns:
-    (xmean_2d, mumean_2d, y2d, N_2d), (xmean_1d, poles, N_1d) | None"""
+def project_sums(y3d, x3d, edges, los=(0, 0, 1), poles=(), hermitian_symmetric=True, planes=None):
+    """the raw per-bin sums of `project_to_basis` over the x-planes `planes` (default: all) -- what one MPI rank
+    of the reference accumulates before the allreduce (fftpower.py:605-672).  Returns (xsum, musum, ysum, Nsum)
+    shaped (Nx+2, Nmu+2) [ysum: (Nell, Nx+2, Nmu+2)]."""
     xedges, muedges = edges
     x2edges = np.asarray(xedges) ** 2
     Nx = len(xedges) - 1
     Nmu = len(muedges) - 1
     poles = list(poles)
-    do_poles = len(poles) > 0
     _poles = [0] + sorted(poles) if 0 not in poles else sorted(poles)
     if any(ell < 0 for ell in _poles):
         raise ValueError("in `project_to_basis`, multipole numbers must be non-negative integers")
-    ell_idx = [_poles.index(l) for l in poles]
     Nell = len(_poles)
 
     nbins = (Nx + 2) * (Nmu + 2)
@@ -255,7 +253,7 @@ def project_to_basis(y3d, x3d, edges, los=(0, 0, 1), poles=(), hermitian_symmetr
 
     # loop over x-planes to bound memory (the reference does the same, fftpower.py:605)
     x0, x1, x2 = x3d
-    for islab in range(y3d.shape[0]):
+    for islab in (range(y3d.shape[0]) if planes is None else planes):
         c0 = x0[islab].reshape(1, 1)
         c1 = x1[0]
         c2 = x2[0]
@@ -303,7 +301,20 @@ def project_to_basis(y3d, x3d, edges, los=(0, 0, 1), poles=(), hermitian_symmetr
     xsum = xsum.reshape(Nx + 2, Nmu + 2)
     Nsum = Nsum.reshape(Nx + 2, Nmu + 2)
     ysum = ysum.reshape(Nell, Nx + 2, Nmu + 2)
-    return finish_projection(xsum, musum, ysum, Nsum, do_poles, ell_idx)
+    return xsum, musum, ysum, Nsum
+
+
+def project_to_basis(y3d, x3d, edges, los=(0, 0, 1), poles=(), hermitian_symmetric=True):
+    """y3d: ndarray (N0,N1,N2c); x3d: 3 broadcastable coordinate arrays (their dtype is part of the
+    contract).  Returns exactly what the reference returns:
+    (xmean_2d, mumean_2d, y2d, N_2d), (xmean_1d, poles, N_1d) | None"""
+    poles = list(poles)
+    _poles = [0] + sorted(poles) if 0 not in poles else sorted(poles)
+    if any(ell < 0 for ell in _poles):
+        raise ValueError("in `project_to_basis`, multipole numbers must be non-negative integers")
+    ell_idx = [_poles.index(l) for l in poles]
+    xsum, musum, ysum, Nsum = project_sums(y3d, x3d, edges, los, poles, hermitian_symmetric)
+    return finish_projection(xsum, musum, ysum, Nsum, len(poles) > 0, ell_idx)
 
 
 def finish_projection(xsum, musum, ysum, Nsum, do_poles, ell_idx):

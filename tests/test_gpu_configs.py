@@ -1,0 +1,169 @@
+"""
+Parity on the configurations bench.py measures (BASELINE.json configs):
+
+  C2 exactly as benchmarked  LogNormal ~1e8 f4 particles -> 512^3 f8 CIC, FFTPower 1d, in the generator's cell order AND
+                             randomly permuted: painted mesh vs the C restatement of the pmesh scatter, mode counts
+                             bit-exact and P(k) <= 1e-5 vs the oracle flow (scipy r2c + the reference's compensation and
+                             project_to_basis code spread over host processes)
+  1024^3                     ~1e8 particles -> 1024^3 (more tiles than any shared-memory window holds): mesh, counts, P(k)
+  C3 / C4 / C5 at 256^3      TSC interlaced f4 1d; mode='2d' Nmu=5; FKP poles 0,2,4 -- against the oracle flow
+
+The same tests mirror /root/reference/nbodykit/algorithms/tests/test_fftpower.py:12-61 and
+source/mesh/tests/test_catalogmesh.py:12-82 in what they assert (spectra, modes, chunk / order invariance).
+Sized for the GPU box's host (the oracle legs need ~30 GB of RAM and all cores for a few seconds each).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import build_c, parallel as opar, pmesh_oracle as po
+
+RTOL = 1e-5
+
+
+def _lognormal(npart, box, gen, seed=42):
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.cosmology import NoWiggleEHPower
+    from nbodykit_b200.source.catalog.lognormal import LogNormalCatalog
+    cat = LogNormalCatalog(Plin=NoWiggleEHPower(), nbar=npart / box ** 3, BoxSize=box, Nmesh=gen, bias=2.0, seed=seed,
+                           comm=SelfComm())
+    return cat['Position'].compute()
+
+
+def _oracle_flow(pos_host, Nmesh, box, resampler="cic", mode="1d", Nmu=5, poles=()):
+    """paint_c -> normalise -> scipy r2c -> compensate + power + project_to_basis over host processes"""
+    N, L = [Nmesh] * 3, [box] * 3
+    mesh = build_c.paint(pos_host, None, N, L, resampler)
+    raw = mesh.copy()
+    mesh /= (len(pos_host) / float(np.prod(N)))
+    c = po.r2c(mesh)
+    del mesh
+    o = opar.power_from_complex(c, None, N, L, mode=mode, Nmu=Nmu, poles=poles,
+                                compensation=po.COMPENSATION[(False, resampler)])
+    return raw, o
+
+
+def _check_power(r, o, two_d=False):
+    assert np.array_equal(r.power['modes'], np.squeeze(o['modes']))
+    np.testing.assert_allclose(r.power['k'], np.squeeze(o['k']), rtol=RTOL, equal_nan=True)
+    P, Po = r.power['power'], np.squeeze(o['power'])
+    scale = np.nanmax(np.abs(Po))
+    assert np.array_equal(np.isnan(P.real), np.isnan(Po.real))
+    np.testing.assert_allclose(np.nan_to_num(P.real), np.nan_to_num(Po.real), rtol=RTOL, atol=RTOL * 1e-3 * scale)
+    if two_d:
+        np.testing.assert_allclose(r.power['mu'], o['mu'], rtol=RTOL, atol=1e-7, equal_nan=True)
+
+
+@pytest.fixture(scope="module")
+def c2_case(cuda):
+    """the C2 catalogue (bench.py --config c2) and its oracle results, computed once"""
+    pos = _lognormal(1.0e8, 1024.0, 256)
+    host = pos.cpu().numpy()
+    raw, o = _oracle_flow(host, 512, 1024.0)
+    return pos, raw, o
+
+
+@pytest.mark.parametrize("order", ["generator", "permuted"])
+def test_c2_as_benchmarked_vs_oracle(cuda, c2_case, order):
+    import torch
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.lab import ArrayCatalog, FFTPower
+    from nbodykit_b200.pmesh.pm import ParticleMesh
+    pos, raw, o = c2_case
+    if order == "permuted":
+        g = torch.Generator(device=pos.device)
+        g.manual_seed(45)
+        pos = pos[torch.randperm(pos.shape[0], device=pos.device, generator=g)].contiguous()
+    # the painted mesh, cell by cell (the tiled path: 2^-31 fixed point, 28-bit fractions -> 1e-7 of the largest cell)
+    pm = ParticleMesh(BoxSize=1024.0, Nmesh=512, dtype='f8', comm=SelfComm())
+    got = pm.paint(pos, resampler='cic').value.cpu().numpy()
+    assert abs(got.sum() - pos.shape[0]) < 1e-3
+    np.testing.assert_allclose(got, raw, rtol=0, atol=1e-7 * raw.max())
+    del got
+    # the whole call exactly as bench.py makes it
+    r = FFTPower(ArrayCatalog({'Position': pos}, comm=SelfComm(), BoxSize=1024.0), mode='1d', Nmesh=512)
+    assert r.attrs['N1'] == pos.shape[0]
+    _check_power(r, o)
+
+
+def test_1024_mesh_vs_oracle(cuda):
+    """~1e8 particles on a 1024^3 mesh: 262144 tiles, windowed bucketing; mesh, counts and P(k) against the oracle"""
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.lab import ArrayCatalog, FFTPower
+    from nbodykit_b200.pmesh.pm import ParticleMesh
+    pos = _lognormal(1.0e8, 2048.0, 256, seed=7)
+    raw, o = _oracle_flow(pos.cpu().numpy(), 1024, 2048.0)
+    pm = ParticleMesh(BoxSize=2048.0, Nmesh=1024, dtype='f8', comm=SelfComm())
+    got = pm.paint(pos, resampler='cic', method='tiled').value.cpu().numpy()
+    np.testing.assert_allclose(got, raw, rtol=0, atol=1e-7 * raw.max())
+    del got, raw
+    r = FFTPower(ArrayCatalog({'Position': pos}, comm=SelfComm(), BoxSize=2048.0), mode='1d', Nmesh=1024)
+    _check_power(r, o)
+
+
+def test_c3_tsc_interlaced_f4_256(cuda):
+    """BASELINE configs[2] at 256^3: to_mesh(resampler='tsc', interlaced=True, compensated=True) (f4 mesh), 1d"""
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.lab import ArrayCatalog, FFTPower
+    pos = _lognormal(1.0e7, 512.0, 128, seed=3)
+    cat = ArrayCatalog({'Position': pos}, comm=SelfComm(), BoxSize=512.0)
+    r = FFTPower(cat.to_mesh(Nmesh=256, resampler='tsc', interlaced=True, compensated=True, dtype='f4'), mode='1d')
+    o = po.fftpower(pos.cpu().numpy(), 256, 512.0, mode='1d', resampler='tsc', interlaced=True, compensated=True, dtype='f4')
+    assert np.array_equal(r.power['modes'], np.squeeze(o['modes']))
+    np.testing.assert_allclose(r.power['k'], np.squeeze(o['k']), rtol=RTOL)
+    P, Po = r.power['power'].real, np.squeeze(o['power']).real
+    # both pipelines carry float32 meshes through three FFTs; compare against the spectrum's own amplitude per bin
+    np.testing.assert_allclose(P, Po, rtol=2e-4, atol=1e-5 * np.nanmax(np.abs(Po)))
+    # and the same catalogue on an f8 mesh to the north-star tolerance
+    r8 = FFTPower(cat.to_mesh(Nmesh=256, resampler='tsc', interlaced=True, compensated=True, dtype='f8'), mode='1d')
+    o8 = po.fftpower(pos.cpu().numpy(), 256, 512.0, mode='1d', resampler='tsc', interlaced=True, compensated=True, dtype='f8')
+    _check_power(r8, o8)
+
+
+def test_c4_2d_nmu5_256(cuda):
+    """BASELINE configs[3] at 256^3: FFTPower(cat, mode='2d', Nmesh=N, Nmu=5) (f8 mesh, CIC)"""
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.lab import ArrayCatalog, FFTPower
+    pos = _lognormal(1.0e7, 512.0, 128, seed=4)
+    r = FFTPower(ArrayCatalog({'Position': pos}, comm=SelfComm(), BoxSize=512.0), mode='2d', Nmesh=256, Nmu=5)
+    _, o = _oracle_flow(pos.cpu().numpy(), 256, 512.0, mode='2d', Nmu=5)
+    assert r.power.shape == (128, 5)
+    assert np.array_equal(r.power['modes'], o['modes'])
+    np.testing.assert_allclose(r.power['k'], o['k'], rtol=RTOL, equal_nan=True)
+    np.testing.assert_allclose(r.power['mu'], o['mu'], rtol=RTOL, atol=1e-7, equal_nan=True)
+    scale = np.nanmax(np.abs(o['power']))
+    np.testing.assert_allclose(np.nan_to_num(r.power['power'].real), np.nan_to_num(o['power'].real), rtol=RTOL, atol=1e-8 * scale)
+
+
+def test_c5_fkp_poles024_256(cuda):
+    """BASELINE configs[4] at 256^3: FKPCatalog(data, randoms).to_mesh(dtype='f8') -> ConvolvedFFTPower poles 0,2,4"""
+    import torch
+    from oracle import convpower_oracle as co
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.lab import ArrayCatalog, ConvolvedFFTPower, FKPCatalog
+    box = 512.0
+    off = np.array([400.0, -150.0, 900.0])
+    dpos = (_lognormal(2.0e6, box, 128, seed=5).cpu().numpy().astype('f8') + off)
+    rng = np.random.RandomState(6)
+    rpos = rng.uniform(size=(4000000, 3)) * box + off
+    nbar = len(dpos) / box ** 3
+    d = ArrayCatalog({'Position': dpos}, comm=SelfComm())
+    r = ArrayCatalog({'Position': rpos}, comm=SelfComm())
+    for c in (d, r):
+        c['NZ'] = nbar * np.ones(c.size)
+    fkp = FKPCatalog(d, r, P0=1e4)
+    center = off + 0.5 * box
+    mesh = fkp.to_mesh(Nmesh=256, BoxSize=box, BoxCenter=center, dtype='f8')
+    res = ConvolvedFFTPower(mesh, poles=[0, 2, 4], dk=2 * np.pi / box, kmin=0.)
+    wf = 1.0 / (1.0 + 1e4 * nbar)
+    o = co.convpower(dpos, rpos, (np.ones(len(dpos)), wf * np.ones(len(dpos))), (np.ones(len(rpos)), wf * np.ones(len(rpos))),
+                     nbar * np.ones(len(dpos)), nbar * np.ones(len(rpos)), 256, [box] * 3, center, [0, 2, 4],
+                     dk=2 * np.pi / box)
+    np.testing.assert_allclose(res.attrs['alpha'], o['alpha'], rtol=1e-12)
+    assert np.array_equal(res.poles['modes'], o['modes'])
+    scale = np.nanmax(np.abs(o['power_0']))
+    for ell in (0, 2, 4):
+        got, want = res.poles['power_%d' % ell], o['power_%d' % ell]
+        np.testing.assert_allclose(np.nan_to_num(got.real), np.nan_to_num(want.real), rtol=1e-5, atol=2e-6 * scale)
+    torch.cuda.empty_cache()
