@@ -31,6 +31,11 @@ extern "C" {
 #define NBK_WINDOW_PCS 4
 
 /* compensation transfer functions (source/mesh/catalog.py:449-594) */
+/* layout bits of the `transposed` argument of the Fourier-space entry points */
+#define NBK_LAYOUT_TRANSPOSED 1  /* first stored axis is y: [y_n][Nx][Nzc] (what one slab transpose leaves behind) */
+#define NBK_LAYOUT_FULLZ 2       /* the last axis stores all Nz modes (complex-dtype meshes, ComplexField.compressed
+                                    == False, algorithms/fftpower.py:572) instead of the Hermitian half Nz/2+1 */
+
 #define NBK_COMP_NONE 0
 #define NBK_COMP_CIC 1           /* CompensateCIC            :513-535 */
 #define NBK_COMP_TSC 2           /* CompensateTSC            :449-473 */
@@ -204,6 +209,19 @@ int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double 
                   const double *los_host, const int *ells_host, int Nell, int hermitian, int comp1,
                   int comp2, int real_input, const double *coord_unit_host, int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
 
+/* nbk_power_bin with a third field: c2_mirror stands for c2 at the UNSTORED mirror mode -k of every mode with
+ * 0 < j_z < N_z/2, i.e. the mirror's share of the sum is conj(c1 conj(c2_mirror)) V instead of the (anti-)Hermitian
+ * fold of c1 conj(c2).  This is what a full complex ('c16') mesh gives the reference when c2 carries a factor that is
+ * not parity-symmetric on the Nyquist planes -- A_l = sum_m Y_lm(khat) FFT[F Y_lm] of ConvolvedFFTPower
+ * (algorithms/convpower/fkp.py:571-623; convpower/catalog.py:169-176): the mirror of index N/2 keeps the label -N/2
+ * (meshtools.py:150-153), so Y_lm(khat) at the mirror is not (-1)^l Y_lm(khat).  hermitian must be 1. */
+int nbk_power_bin2(const void *c1, const void *c2, const void *c2_mirror, int dtype, int is_p3d, double volume,
+                   int clear_zero, const int64_t *nmesh_host, const double *boxsize_host,
+                   int transposed, int64_t start, int64_t count, int coord_dtype,
+                   const double *k2edges_host, int Nx, const double *muedges_host, int Nmu,
+                   const double *los_host, const int *ells_host, int Nell, int hermitian, int comp1,
+                   int comp2, int real_input, const double *coord_unit_host, int64_t *nsum, double *xsum, double *musum, double *ysum, void *stream);
+
 /* out = c1 * conj(c2) * scale with element 0 cleared when clear_first != 0 (the k = 0 mode on the rank that owns
  * it): FFTBase._compute_3d_power (algorithms/fftpower.py:115-128), materialised only where the 3-D power itself
  * is needed (FFTCorr, algorithms/fftcorr.py:148-150).  c2 == NULL -> auto power.  out may alias c1. */
@@ -219,6 +237,35 @@ int nbk_ylm_mul_real(const void *in, void *out, int dtype, int l, int m, const i
 int nbk_ylm_mul_complex_acc(void *acc, const void *c, int dtype, int l, int m, const int64_t *nmesh_host,
                             const double *boxsize_host, int transposed, int64_t start, int64_t count,
                             void *stream);
+
+/* nbk_ylm_mul_complex_acc plus a second accumulator evaluated with the direction the mirror mode -k carries on a full
+ * complex mesh: every component flips sign except those at the Nyquist index (label stays -N/2) -- the c2_mirror of
+ * nbk_power_bin2. */
+int nbk_ylm_mul_complex_acc2(void *acc, void *acc_mirror, const void *c, int dtype, int l, int m,
+                             const int64_t *nmesh_host, const double *boxsize_host, int transposed, int64_t start,
+                             int64_t count, void *stream);
+
+/* Complex-dtype meshes (ParticleMesh(dtype='c16'/'c8'), base/mesh.py:50; convpower/catalog.py:151-176): pmesh keeps all
+ * N^3 modes of the c2c transform.  The configuration-space fields of this path are real-valued, so the full spectrum
+ * is the Hermitian completion of the r2c result: full[Nx][Ny][Nz] <- comp[Nx][Ny][Nz/2+1] (single GPU), and the
+ * stored half is cut back out before a c2r (rows = planes * Ny of this rank). */
+int nbk_hermitian_expand(const void *comp, void *full, int dtype, const int64_t *nmesh_host, void *stream);
+int nbk_hermitian_compress(const void *full, void *comp, int dtype, int64_t rows, int64_t Nz, void *stream);
+
+/* Slab transpose as a line pass into P contiguous local send blocks send[p][k % (N/P)][outer][inner] followed by one
+ * strided bulk copy per peer (cudaMemcpy2DAsync over NVLink, rows of n_outer * n_inner elements): the alternative to
+ * nbk_fft_lines_scatter's fine-grained remote stores for the pencil transpose of pfft (r2c / c2r, base/mesh.py:228,237).
+ * nbk_slab_push: block p of `send` -> rank p's field [rows_per_peer][n_outer * P][n_inner] at offset outer_start. */
+int nbk_fft_lines_pack(const void *src, void *send, int dtype, int64_t n_line, int64_t n_inner, int64_t n_outer, int P,
+                       int inverse, double scale, void *stream);
+int nbk_slab_push(const void *send, void *const *peer_ptrs_host, int dtype, int64_t rows_per_peer, int64_t n_outer,
+                  int64_t n_inner, int64_t outer_start, int P, int rank, void *stream);
+
+/* Fourier-space resampling to another mesh size: pmesh `Field.resample`, called by MeshSource.compute(Nmesh=...)
+ * (base/mesh.py:317-327).  Modes both meshes represent are copied (same integer frequency label per axis, Nyquist
+ * negative), everything else in dst is zero.  Hermitian-compressed single-GPU layouts [Nx][Ny][Nz/2+1]. */
+int nbk_resample_complex(const void *src, void *dst, int dtype, const int64_t *nmesh_src_host,
+                         const int64_t *nmesh_dst_host, void *stream);
 
 /* elementwise helpers behind RealField/ComplexField `[...] = v`, `*= a`, `+= other`
  * (source/mesh/catalog.py:203,354,396-398; fftpower.py:128).  n counts REAL scalars. */

@@ -231,32 +231,43 @@ class ConvolvedFFTPower(object):
         off_c = _lib.darr(offset)
         proj = None
         start = time.time()
+        # complex ('c16' / 'c8') meshes: the reference sums over ALL modes of a full mesh.  The field is real in
+        # configuration space, so the unstored half follows from the stored one -- except that Y_lm(khat) at the mirror
+        # of a mode with a Nyquist component is not (-1)^l Y_lm(khat) (the Nyquist label stays -N/2): Bell accumulates
+        # the A_l the mirror modes carry, and the binning kernel takes the mirror half from it (nbk_power_bin2)
+        full_mesh = bool(getattr(self.first, 'complex_mesh', False))
         if len(poles) > 1:
             Aell = ComplexField(pm)
+            Bell = ComplexField(pm) if full_mesh else None
             work_r = RealField(pm)
             work_c = ComplexField(pm)
         for ell in poles[1:]:
             Aell[...] = 0.
+            if full_mesh:
+                Bell[...] = 0.
             substart = time.time()
             for m in range(-ell, ell + 1):
                 # F(x) Y_lm(xhat) -> FFT -> accumulate Y_lm(khat) * FFT
                 check(lib().nbk_ylm_mul_real(_ptr(rfield2.value), _ptr(work_r.value), code, ell, m, pm._nmesh_c,
                                              pm._box_c, off_c, pm.x_start, pm.x_n, _stream()), "nbk_ylm_mul_real")
                 work_r.r2c(out=work_c)
-                check(lib().nbk_ylm_mul_complex_acc(_ptr(Aell.value), _ptr(work_c.value), code, ell, m, pm._nmesh_c,
-                                                    pm._box_c, tr, cstart, ccount, _stream()), "nbk_ylm_mul_complex_acc")
+                if full_mesh:
+                    check(lib().nbk_ylm_mul_complex_acc2(_ptr(Aell.value), _ptr(Bell.value), _ptr(work_c.value), code, ell, m,
+                                                         pm._nmesh_c, pm._box_c, tr, cstart, ccount, _stream()),
+                          "nbk_ylm_mul_complex_acc2")
+                else:
+                    check(lib().nbk_ylm_mul_complex_acc(_ptr(Aell.value), _ptr(work_c.value), code, ell, m, pm._nmesh_c,
+                                                        pm._box_c, tr, cstart, ccount, _stream()), "nbk_ylm_mul_complex_acc")
                 if rank == 0:
                     self.logger.debug("done term for Y(l=%d, m=%d) in %s" % (ell, m, timer(substart, time.time())))
             if rank == 0:
                 self.logger.info('ell = %d done; %s r2c completed' % (ell, 2 * ell + 1))
             # P_l = < norm * (V c1 / comp1) * conj(4 pi V Aell / comp2) >
-            # full complex ('c16') meshes give the reference the true sum over all modes; for odd ell the statistic is
-            # anti-Hermitian and the compressed half must be folded with that sign.  Hermitian ('f8'/'f4') meshes keep the
-            # reference's own (documented as incorrect for odd ell) Hermitian fold.
-            anti = bool(getattr(self.first, 'complex_mesh', False)) and (ell % 2 == 1)
+            # complex meshes: the true sum over all N^3 modes (mirror half from Bell); Hermitian ('f8'/'f4') meshes keep
+            # the reference's own Hermitian fold (documented there as incorrect for odd ell)
             proj, _ = project_to_basis_device(c1, edges, second=Aell, is_p3d=False,
                                               volume=norm * 4 * numpy.pi * volume * volume, compensation=comp,
-                                              clear_zero=False, antihermitian=anti)
+                                              clear_zero=False, mirror=Bell if full_mesh else None)
             result['power_%d' % ell][:] = numpy.squeeze(proj[2])
         if rank == 0:
             self.logger.info("higher order multipoles computed in elapsed time %s" % timer(start, time.time()))

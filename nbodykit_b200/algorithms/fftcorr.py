@@ -54,6 +54,15 @@ class FFTCorr(FFTBase):
         if comp2 and c2 is not c1:
             c2.compensate(comp2)
         pm = c1.pm
+        if c2 is not c1:
+            if tuple(c2.value.shape) != tuple(c1.value.shape):
+                raise ValueError("FFTCorr: mesh shape mismatch between the two sources")
+            if c2.pm.typestr != pm.typestr:      # NumPy promotion of c1 * conj(c2), as in the reference
+                if pm.typestr == 'f8':
+                    c2 = ComplexField(pm, c2.value.to(c1.value.dtype))
+                else:
+                    c1 = ComplexField(c2.pm, c1.value.to(c2.value.dtype))
+                    pm = c1.pm
         V = float(pm.BoxSize.prod())
         # 3-D power with the zero mode cleared; xi = c2r(P3d) / V
         p3d = ComplexField(pm)
@@ -76,6 +85,11 @@ class FFTCorr(FFTBase):
         coords = [rcenters, None]
         result, pole_result = project_to_basis_device(y3d, edges, poles=self.attrs['poles'], los=self.attrs['los'],
                                                       is_p3d=True)
+        # xi is a RealField: the reference bins it into sums of the field's real dtype (fftpower.py:583, 'corr' is f8)
+        result = list(result)
+        result[2] = numpy.ascontiguousarray(result[2].real)
+        if pole_result is not None:
+            pole_result = (pole_result[0], numpy.ascontiguousarray(pole_result[1].real), pole_result[2])
         if self.attrs['mode'] == "1d":
             cols, icols = ['r', 'corr', 'modes'], [0, 2, 3]
             edges, coords = edges[0:1], coords[0:1]

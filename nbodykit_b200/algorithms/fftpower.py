@@ -81,7 +81,7 @@ class FFTBase(object):
             # a CatalogMesh whose only action is its window compensation hands over the uncompensated field
             # and the name of the transfer function; the binning kernel applies it on the fly
             if hasattr(src, 'compute_complex_deferred'):
-                return src.compute_complex_deferred()
+                return src.compute_complex_deferred(Nmesh=self.attrs['Nmesh'])
             return src.compute(mode='complex', Nmesh=self.attrs['Nmesh']), None
         c1, comp1 = field_of(first)
         if first is second:
@@ -283,7 +283,7 @@ def _los_coord_mode(los, coord_dtype):
 
 
 def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4", is_p3d=True, second=None,
-                            volume=1.0, compensation=(None, None), clear_zero=True, antihermitian=False):
+                            volume=1.0, compensation=(None, None), clear_zero=True, antihermitian=False, mirror=None):
     """
     project_to_basis (fftpower.py:507-701) for a device ComplexField.
 
@@ -303,6 +303,20 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     if is_real and not is_p3d:
         raise ValueError("a RealField is binned as a 3-D statistic (is_p3d=True)")
     pm = y3d.pm
+    if second is not None and second is not y3d:
+        # the kernel reads both fields with ONE dtype code and ONE slab geometry: anything else must not reach it
+        if not isinstance(second, type(y3d)):
+            raise TypeError("project_to_basis_device: the two fields must be of the same kind (real / complex)")
+        if not numpy.array_equal(second.pm.Nmesh, pm.Nmesh) or tuple(second.value.shape) != tuple(y3d.value.shape):
+            raise ValueError("project_to_basis_device: mesh shape mismatch between the two fields (%s vs %s)"
+                             % (str(tuple(second.value.shape)), str(tuple(y3d.value.shape))))
+        if second.pm.typestr != pm.typestr:
+            # the reference multiplies c1 * conj(c2) under NumPy promotion: promote the narrower field (a copy)
+            if pm.typestr == 'f8':
+                second = type(second)(pm, second.value.to(y3d.value.dtype))
+            else:
+                y3d = type(y3d)(second.pm, y3d.value.to(second.value.dtype))
+                pm = y3d.pm
     # real-space statistics (FFTCorr) are binned in the wrapped separation x = index * L/N
     coord_unit = _lib.darr(pm.BoxSize / pm.Nmesh) if is_real else None
     comm = pm.comm
@@ -330,12 +344,17 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     ysum = facc[2 * nb:]
     tr, start, count = (0, pm.x_start, pm.x_n) if is_real else y3d._slab()
     los_f = [float(v) for v in los]
+    herm = 0 if (is_real or not y3d.compressed) else (2 if antihermitian else 1)
+    if mirror is not None and (herm != 1 or second is None or tuple(mirror.value.shape) != tuple(y3d.value.shape)):
+        raise ValueError("a mirror field needs a Hermitian-compressed pair of fields of the same shape")
     with stage("power_bin"):
-        check(lib().nbk_power_bin(
-            _ptr(y3d.value), _ptr(second.value) if second is not None else None, _CODE[pm.typestr],
+        fn = lib().nbk_power_bin if mirror is None else lib().nbk_power_bin2
+        extra = () if mirror is None else (_ptr(mirror.value),)
+        check(fn(
+            _ptr(y3d.value), _ptr(second.value) if second is not None else None, *extra, _CODE[pm.typestr],
             1 if is_p3d else 0, float(volume), 1 if clear_zero else 0, pm._nmesh_c, pm._box_c, tr, start, count,
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
-            _lib.i32arr(_poles), Nell, 0 if is_real else (2 if antihermitian else 1), _lib.COMP.get(compensation[0], 0),
+            _lib.i32arr(_poles), Nell, herm, _lib.COMP.get(compensation[0], 0),
             _lib.COMP.get(compensation[1], 0), 1 if is_real else 0, coord_unit,
             _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
     with stage("H:bin_reduce"):

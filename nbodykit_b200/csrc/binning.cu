@@ -8,6 +8,7 @@
 // (k_d = fl32(f32(j_d)*f32(2 pi/L_d)), k^2 = fl32(fl32(kx^2+ky^2)+kz^2), |k| = sqrt_rn, mu = div_rn)
 // is part of the bit-exact contract (pinned by nbodykit/tests/data/dataset_2d.json).
 #include "common.cuh"
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -32,7 +33,11 @@ static int make_slab(const int64_t *nmesh, int transposed, int64_t start, int64_
         NBK_CHECK_ARG(nmesh[d] > 0 && nmesh[d] < (1 << 24), "bad Nmesh[%d]=%lld", d, (long long)nmesh[d]);
         g.N[d] = (int)nmesh[d];
     }
-    g.Nzc = hermitian ? g.N[2] / 2 + 1 : g.N[2];
+    // `transposed` carries the layout bits: NBK_LAYOUT_TRANSPOSED (first stored axis is y) and NBK_LAYOUT_FULLZ (the
+    // last axis holds all Nz modes: complex-dtype meshes, real-space statistics)
+    const bool fullz = (transposed & NBK_LAYOUT_FULLZ) != 0;
+    transposed &= NBK_LAYOUT_TRANSPOSED;
+    g.Nzc = (hermitian && !fullz) ? g.N[2] / 2 + 1 : g.N[2];
     g.transposed = transposed ? 1 : 0;
     int D0 = transposed ? g.N[1] : g.N[0];
     g.D1 = transposed ? g.N[0] : g.N[1];
@@ -171,7 +176,7 @@ extern "C" int nbk_compensate(void *cplx, int dtype, int kind, const int64_t *nm
     int64_t rows = (int64_t)g.count * g.D1;
     int grid = (int)(rows < (int64_t)NBK_SM_COUNT * 16 ? rows : (int64_t)NBK_SM_COUNT * 16);
     int block = g.Nzc >= 256 ? 256 : 64;
-    const double *t0 = transposed ? ty : tx, *t1 = transposed ? tx : ty;
+    const double *t0 = g.transposed ? ty : tx, *t1 = g.transposed ? tx : ty;
     if (dtype == NBK_F4) k_compensate<float><<<grid, block, 0, s>>>((float *)cplx, g, t0, t1, tz);
     else k_compensate<double><<<grid, block, 0, s>>>((double *)cplx, g, t0, t1, tz);
     NBK_LAUNCHED();
@@ -303,6 +308,7 @@ struct BinParams {
     int ells[NBK_MAX_ELL];
     int hermitian, is_p3d, clear_zero, has_c2;
     int anti;         // the statistic obeys y(-k) = -conj y(k) (odd FKP multipoles): the fold of the mirror half flips
+    const void *c3;  // optional: the field that stands for c2 at the UNSTORED mirror mode -k (see nbk_power_bin2)
     int estride;     // 2: complex input (re, im interleaved)   1: real input (a RealField statistic, FFTCorr)
     double volume;
 };
@@ -478,7 +484,8 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                 wcnt = (nonsing ? 2u : 1u) * (unsigned)mult;
                 xs = knorm * wH;
                 ms = mu * wH;
-                double yre = 0.0, yim = 0.0;
+                double yre = 0.0, yim = 0.0, zre = 0.0, zim = 0.0;     // z: c1 * conj(c3), the statistic of the mirror mode
+                const bool mirror = nonsing && P.c3 != nullptr;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     if (q == 1 && !use1) continue;
@@ -491,12 +498,20 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                         if (P.has_c2) { const T *p2 = c2 + roff[q] + 2 * kz; c = (double)p2[0]; d = (double)p2[1]; }
                         yre += a * c + bb * d;      // c1 * conj(c2)
                         yim += bb * c - a * d;
+                        if (mirror) {
+                            const T *p3 = reinterpret_cast<const T *>(P.c3) + roff[q] + 2 * kz;
+                            const double c3r = (double)p3[0], c3i = (double)p3[1];
+                            zre += a * c3r + bb * c3i;
+                            zim += bb * c3r - a * c3i;
+                        }
                     }
                 }
                 if (!P.is_p3d) {
                     double vol = ct0 ? vol_row * ctz[kz] : vol_row;   // V [* window compensation of both fields]
                     yre *= vol;
                     yim *= vol;
+                    zre *= vol;
+                    zim *= vol;
                     if (P.clear_zero && jx == 0 && jy == 0 && jz == 0) { yre = 0; yim = 0; }
                 }
 #pragma unroll
@@ -504,7 +519,11 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     int ell = P.ells[l];
                     double f = legendre(ell, mu) * (2.0 * ell + 1.0);
                     double re = f * yre, im = f * yim;
-                    if (nonsing) {   // add the mirror mode: Leg(l)(-mu) * (+/-) conj(y)
+                    if (mirror) {    // add the mirror mode from its own statistic: Leg(l)(-mu) * (+/-) conj(z)
+                        const double sg = ((ell & 1) != P.anti) ? -1.0 : 1.0;
+                        re += sg * f * zre;
+                        im -= sg * f * zim;
+                    } else if (nonsing) {   // add the mirror mode: Leg(l)(-mu) * (+/-) conj(y)
                         if ((ell & 1) != P.anti) { re = 0.0; im *= 2.0; }
                         else { re *= 2.0; im = 0.0; }
                     }
@@ -601,11 +620,19 @@ static int get_edges(const double *host, int n, cudaStream_t s, double **out) {
     NBK_CUDA(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lock(g_edge_mutex);
     auto &vec = g_edges[dev];
-    for (auto &c : vec)
-        if ((int)c.host.size() == n && memcmp(c.host.data(), host, sizeof(double) * n) == 0) { *out = c.dev; return NBK_OK; }
-    if (vec.size() > 64) {  // bounded cache
-        for (auto &c : vec) cudaFree(c.dev);
-        vec.clear();
+    // LRU: a hit moves the entry to the back, a miss on a full cache evicts the FRONT entry only -- so an array handed
+    // out earlier in the same nbk_* call (the k edges, when the mu edges miss) is never the one freed.  cudaFree
+    // synchronises the device, so kernels still reading the evicted array have finished.
+    for (size_t i = 0; i < vec.size(); i++) {
+        if ((int)vec[i].host.size() == n && memcmp(vec[i].host.data(), host, sizeof(double) * n) == 0) {
+            if (i + 1 != vec.size()) std::rotate(vec.begin() + i, vec.begin() + i + 1, vec.end());
+            *out = vec.back().dev;
+            return NBK_OK;
+        }
+    }
+    if (vec.size() >= 64) {  // bounded cache
+        cudaFree(vec.front().dev);
+        vec.erase(vec.begin());
     }
     EdgeCache c;
     c.host.assign(host, host + n);
@@ -672,12 +699,12 @@ static int launch_bin_ell(const void *c1, const void *c2, const BinParams &P, co
     return NBK_ERR_UNSUPPORTED;
 }
 
-extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume, int clear_zero,
-                             const int64_t *nmesh, const double *box, int transposed, int64_t start, int64_t count,
-                             int coord_dtype, const double *k2edges, int Nx, const double *muedges, int Nmu,
-                             const double *los, const int *ells, int Nell, int hermitian, int comp1, int comp2,
-                             int real_input, const double *coord_unit, int64_t *nsum, double *xsum, double *musum,
-                             double *ysum, void *stream) {
+static int power_bin_impl(const void *c1, const void *c2, const void *c3, int dtype, int is_p3d, double volume, int clear_zero,
+                          const int64_t *nmesh, const double *box, int transposed, int64_t start, int64_t count,
+                          int coord_dtype, const double *k2edges, int Nx, const double *muedges, int Nmu,
+                          const double *los, const int *ells, int Nell, int hermitian, int comp1, int comp2,
+                          int real_input, const double *coord_unit, int64_t *nsum, double *xsum, double *musum,
+                          double *ysum, void *stream) {
     NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "power_bin: bad dtype %d", dtype);
     NBK_CHECK_ARG(coord_dtype == 4 || coord_dtype == 8 || coord_dtype == 48, "power_bin: bad coord_dtype %d", coord_dtype);
     NBK_CHECK_ARG(Nx >= 0 && Nmu >= 1, "power_bin: need Nx >= 0 and Nmu >= 1");
@@ -707,6 +734,7 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
     NBK_CHECK_ARG(!real_input || (is_p3d && !hermitian), "power_bin: a real input must be a full (non-Hermitian) 3-D statistic");
     P.clear_zero = clear_zero ? 1 : 0;
     P.has_c2 = (c2 != nullptr && c2 != c1) ? 1 : 0;
+    P.c3 = (c3 != nullptr && hermitian && !is_p3d && !real_input) ? c3 : nullptr;
     P.volume = volume;
     cudaStream_t s = (cudaStream_t)stream;
     double *d_k2, *d_mu;
@@ -721,8 +749,8 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
         double *t[3];
         for (int d = 0; d < 3; d++)
             if ((rc = get_comp_pair_table(comp1, comp2, P.g.N[d], s, &t[d]))) return rc;
-        ct0 = transposed ? t[1] : t[0];
-        ct1 = transposed ? t[0] : t[1];
+        ct0 = P.g.transposed ? t[1] : t[0];
+        ct1 = P.g.transposed ? t[0] : t[1];
         ctz = t[2];
     }
     // are the k edges uniformly spaced (numpy.arange)?  then bins start from a closed-form guess
@@ -738,4 +766,26 @@ extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p
     }
     if (dtype == NBK_F4) return launch_bin_ell<float>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
     return launch_bin_ell<double>(c1, c2, P, d_k2, d_mu, nsum, xsum, musum, ysum, kmin, inv_dk, uniform, ct0, ct1, ctz, s);
+}
+
+extern "C" int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume, int clear_zero,
+                             const int64_t *nmesh, const double *box, int transposed, int64_t start, int64_t count,
+                             int coord_dtype, const double *k2edges, int Nx, const double *muedges, int Nmu,
+                             const double *los, const int *ells, int Nell, int hermitian, int comp1, int comp2,
+                             int real_input, const double *coord_unit, int64_t *nsum, double *xsum, double *musum,
+                             double *ysum, void *stream) {
+    return power_bin_impl(c1, c2, nullptr, dtype, is_p3d, volume, clear_zero, nmesh, box, transposed, start, count, coord_dtype,
+                          k2edges, Nx, muedges, Nmu, los, ells, Nell, hermitian, comp1, comp2, real_input, coord_unit, nsum,
+                          xsum, musum, ysum, stream);
+}
+
+extern "C" int nbk_power_bin2(const void *c1, const void *c2, const void *c2_mirror, int dtype, int is_p3d, double volume,
+                              int clear_zero, const int64_t *nmesh, const double *box, int transposed, int64_t start,
+                              int64_t count, int coord_dtype, const double *k2edges, int Nx, const double *muedges, int Nmu,
+                              const double *los, const int *ells, int Nell, int hermitian, int comp1, int comp2,
+                              int real_input, const double *coord_unit, int64_t *nsum, double *xsum, double *musum,
+                              double *ysum, void *stream) {
+    return power_bin_impl(c1, c2, c2_mirror, dtype, is_p3d, volume, clear_zero, nmesh, box, transposed, start, count,
+                          coord_dtype, k2edges, Nx, muedges, Nmu, los, ells, Nell, hermitian, comp1, comp2, real_input,
+                          coord_unit, nsum, xsum, musum, ysum, stream);
 }

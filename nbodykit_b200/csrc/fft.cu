@@ -728,7 +728,7 @@ static bool use_reg_lines(int N) {
 template <typename T>
 static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, int P, int N, int64_t line_stride,
                            int64_t n_inner, int64_t n_outer, int64_t outer_stride, int64_t outer_start, int inverse,
-                           double scale, cudaStream_t s) {
+                           double scale, cudaStream_t s, int64_t d_total_override = 0) {
     typedef typename C2<T>::type C;
     int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
     void *tw;
@@ -770,7 +770,7 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
     PeerPtrs<C> peers;
     for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
     const int n_per = peer_host ? N / P : N;
-    const int64_t d_total = peer_host ? n_outer * P : 0;
+    const int64_t d_total = d_total_override ? d_total_override : (peer_host ? n_outer * P : 0);
 #define LAUNCH_RG(BB, NTT)                                                                                            \
     case BB:                                                                                                       \
         if (peer_host) {                                                                                           \
@@ -877,10 +877,11 @@ extern "C" int nbk_fft_lines_oop(const void *src, void *dst, int dtype, int64_t 
 
 template <typename T>
 static int launch_lines_scatter(const void *src, void *const *peer_host, int N, int64_t n_inner, int64_t n_outer,
-                                int64_t outer_start, int P, int inverse, double scale, cudaStream_t s) {
+                                int64_t outer_start, int P, int inverse, double scale, cudaStream_t s,
+                                int64_t d_total_override = 0) {
     if (use_reg_lines(N))
         return launch_lines_rg<T>(src, nullptr, peer_host, P, N, n_inner, n_inner, n_outer, (int64_t)N * n_inner, outer_start,
-                                  inverse, scale, s);
+                                  inverse, scale, s, d_total_override);
     typedef typename C2<T>::type C;
     int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
     void *tw;
@@ -901,7 +902,8 @@ static int launch_lines_scatter(const void *src, void *const *peer_host, int N, 
     case BB:                                                                                                         \
         NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_scatter<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_fft_lines_scatter<T, BB><<<(int)g, 256, smem, s>>>((const C *)src, peers, (const C *)tw, N, ilog2(N), n_inner, \
-                                                             tiles_inner, n_tiles, N / P, n_outer * P, outer_start,   \
+                                                             tiles_inner, n_tiles, N / P,                              \
+                                                             d_total_override ? d_total_override : n_outer * P, outer_start, \
                                                              inverse, (T)scale);                                     \
         break;
     switch (B) {
@@ -1129,4 +1131,159 @@ extern "C" int nbk_transpose_unpack_back(const void *src, void *dst, int dtype, 
     int64_t y_n = Ny / P;
     // dst (i0=x, i1=p, i2=yl): src row = (p*y_n + yl)*x_n + x
     return PERMUTE(dtype, src, dst, x_n, P, y_n, 1, y_n * x_n, x_n, (int)Nzc, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Complex-dtype meshes (ParticleMesh(dtype='c16'/'c8'): pmesh then runs c2c transforms and keeps all N^3 modes,
+// `ComplexField.compressed == False`, fftpower.py:572; convpower/catalog.py:151-176).  On this path the
+// configuration-space field is real-valued, so its full spectrum is the Hermitian completion of the r2c result:
+//   full[ix][iy][iz] = comp[ix][iy][iz]                                   iz <= Nz/2
+//                    = conj(comp[(-ix) % Nx][(-iy) % Ny][Nz - iz])        iz >  Nz/2
+// One read of the compressed field, one write of the full one (a c2c transform would move three times as much).
+// ---------------------------------------------------------------------------------------------
+template <typename C>
+__global__ void __launch_bounds__(256)
+k_hermitian_expand(const C *__restrict__ comp, C *__restrict__ full, int Nx, int Ny, int Nz) {
+    const int Nzc = Nz / 2 + 1;
+    const int64_t rows = (int64_t)Nx * Ny;
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = w0; row < rows; row += nw) {
+        const int ix = (int)(row / Ny), iy = (int)(row - (int64_t)ix * Ny);
+        const int mx = ix ? Nx - ix : 0, my = iy ? Ny - iy : 0;
+        const C *a = comp + row * Nzc;
+        const C *b = comp + ((int64_t)mx * Ny + my) * Nzc;
+        C *o = full + row * Nz;
+        for (int iz = lane; iz < Nz; iz += 32) {
+            C v;
+            if (iz < Nzc) v = a[iz];
+            else { v = b[Nz - iz]; v.y = -v.y; }
+            o[iz] = v;
+        }
+    }
+}
+
+template <typename C>
+__global__ void __launch_bounds__(256)
+k_hermitian_compress(const C *__restrict__ full, C *__restrict__ comp, int64_t rows, int Nz) {
+    const int Nzc = Nz / 2 + 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = w0; row < rows; row += nw)
+        for (int iz = lane; iz < Nzc; iz += 32) comp[row * Nzc + iz] = full[row * Nz + iz];
+}
+
+extern "C" int nbk_hermitian_expand(const void *comp, void *full, int dtype, const int64_t *nmesh, void *stream) {
+    int rc = check_dims("hermitian_expand", dtype, nmesh[0], nmesh[1], nmesh[2]);
+    if (rc) return rc;
+    NBK_CHECK_ARG(comp != nullptr && full != nullptr && comp != full, "hermitian_expand: needs two distinct buffers");
+    int64_t rows = nmesh[0] * nmesh[1];
+    int g = nbk_grid_for(rows * 32, 256, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4) k_hermitian_expand<float2><<<g, 256, 0, s>>>((const float2 *)comp, (float2 *)full, (int)nmesh[0], (int)nmesh[1], (int)nmesh[2]);
+    else k_hermitian_expand<double2><<<g, 256, 0, s>>>((const double2 *)comp, (double2 *)full, (int)nmesh[0], (int)nmesh[1], (int)nmesh[2]);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+// the stored half of a full spectrum (the inverse of nbk_hermitian_expand for Hermitian fields; rows = Nx * Ny of this rank)
+extern "C" int nbk_hermitian_compress(const void *full, void *comp, int dtype, int64_t rows, int64_t Nz, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "hermitian_compress: bad dtype %d", dtype);
+    NBK_CHECK_ARG(rows >= 0 && Nz >= 2 && comp != full, "hermitian_compress: bad arguments");
+    if (rows == 0) return NBK_OK;
+    int g = nbk_grid_for(rows * 32, 256, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4) k_hermitian_compress<float2><<<g, 256, 0, s>>>((const float2 *)full, (float2 *)comp, rows, (int)Nz);
+    else k_hermitian_compress<double2><<<g, 256, 0, s>>>((const double2 *)full, (double2 *)comp, rows, (int)Nz);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fourier-space resampling to another mesh size (pmesh `Field.resample`, called from base/mesh.py:317-327 when
+// compute(Nmesh=...) asks for a size other than the source's): the modes both meshes represent are copied, the rest
+// of the destination is zero (down-sampling = truncation, up-sampling = zero padding; the normalised transform keeps
+// amplitudes, so the mean is preserved).  Per axis a destination index maps to the source index with the same integer
+// frequency label, labels in [-Nmin/2, Nmin/2) (Nyquist negative, meshtools.py:150-153); along the Hermitian-compressed
+// axis indices 0 .. Nmin/2 map to themselves.  Single GPU, compressed layout [Nx][Ny][Nz/2+1].
+// ---------------------------------------------------------------------------------------------
+template <typename C>
+__global__ void __launch_bounds__(256)
+k_resample_complex(const C *__restrict__ src, C *__restrict__ dst, int sx, int sy, int sz, int dx, int dy, int dz) {
+    const int szc = sz / 2 + 1, dzc = dz / 2 + 1;
+    const int mzc = (sz < dz ? sz : dz) / 2 + 1;
+    const int64_t rows = (int64_t)dx * dy;
+    const int lane = threadIdx.x & 31;
+    const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t row = w0; row < rows; row += nw) {
+        const int ix = (int)(row / dy), iy = (int)(row - (int64_t)ix * dy);
+        const int jx = nbk_freq(ix, dx), jy = nbk_freq(iy, dy);
+        const int mx = sx < dx ? sx : dx, my = sy < dy ? sy : dy;
+        const bool ok = 2 * jx >= -mx && 2 * jx < mx && 2 * jy >= -my && 2 * jy < my;
+        const C *s = src + ((int64_t)(jx < 0 ? jx + sx : jx) * sy + (jy < 0 ? jy + sy : jy)) * szc;
+        C *d = dst + row * dzc;
+        for (int iz = lane; iz < dzc; iz += 32) d[iz] = (ok && iz < mzc) ? s[iz] : C{0, 0};
+    }
+}
+
+extern "C" int nbk_resample_complex(const void *src, void *dst, int dtype, const int64_t *nmesh_src,
+                                    const int64_t *nmesh_dst, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "resample_complex: bad dtype %d", dtype);
+    NBK_CHECK_ARG(src != nullptr && dst != nullptr && src != dst, "resample_complex: needs two distinct buffers");
+    for (int d = 0; d < 3; d++)
+        NBK_CHECK_ARG(nmesh_src[d] >= 2 && nmesh_dst[d] >= 2 && nmesh_src[d] < (1 << 24) && nmesh_dst[d] < (1 << 24) &&
+                      nmesh_src[d] % 2 == 0 && nmesh_dst[d] % 2 == 0, "resample_complex: mesh sides must be even");
+    int64_t rows = nmesh_dst[0] * nmesh_dst[1];
+    int g = nbk_grid_for(rows * 32, 256, 8);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4)
+        k_resample_complex<float2><<<g, 256, 0, s>>>((const float2 *)src, (float2 *)dst, (int)nmesh_src[0], (int)nmesh_src[1],
+                                                     (int)nmesh_src[2], (int)nmesh_dst[0], (int)nmesh_dst[1], (int)nmesh_dst[2]);
+    else
+        k_resample_complex<double2><<<g, 256, 0, s>>>((const double2 *)src, (double2 *)dst, (int)nmesh_src[0], (int)nmesh_src[1],
+                                                      (int)nmesh_src[2], (int)nmesh_dst[0], (int)nmesh_dst[1], (int)nmesh_dst[2]);
+    NBK_LAUNCHED();
+    return NBK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Slab transpose as "line pass into send blocks" + bulk peer copies (P > 1).  The line pass (y pass of r2c, inverse x
+// pass of c2r) stores its output rows directly in transposed order into P contiguous LOCAL blocks
+//     send[p][kl][outer][inner]      kl = k % (N/P) the line frequency inside rank p's share, outer < n_outer
+// and nbk_slab_push() moves block p into rank p's field [N/P][n_outer * P][n_inner] with one strided bulk copy per
+// peer: rows of n_outer * n_inner contiguous elements (1 MB at 1024^3 on 8 GPUs) travel over NVLink on the copy
+// engines at link rate, instead of the 128..256-byte remote stores of nbk_fft_lines_scatter.
+// ---------------------------------------------------------------------------------------------
+extern "C" int nbk_fft_lines_pack(const void *src, void *send, int dtype, int64_t n_line, int64_t n_inner, int64_t n_outer,
+                                  int P, int inverse, double scale, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "fft_lines_pack: bad dtype %d", dtype);
+    NBK_CHECK_ARG(is_pow2(n_line) && n_line >= 2 && n_line <= 8192, "fft_lines_pack: line length %lld unsupported", (long long)n_line);
+    NBK_CHECK_ARG(P >= 1 && P <= NBK_MAX_PEERS && n_line % P == 0, "fft_lines_pack: bad peer count %d", P);
+    if (n_inner <= 0 || n_outer <= 0) return NBK_OK;
+    const size_t cs = dtype == NBK_F4 ? 8 : 16;
+    const size_t block = (size_t)(n_line / P) * n_outer * n_inner * cs;
+    void *blocks[NBK_MAX_PEERS];
+    for (int p = 0; p < P; p++) blocks[p] = (char *)send + (size_t)p * block;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4)
+        return launch_lines_scatter<float>(src, blocks, (int)n_line, n_inner, n_outer, 0, P, inverse, scale, s, n_outer);
+    return launch_lines_scatter<double>(src, blocks, (int)n_line, n_inner, n_outer, 0, P, inverse, scale, s, n_outer);
+}
+
+extern "C" int nbk_slab_push(const void *send, void *const *peer_ptrs_host, int dtype, int64_t rows_per_peer,
+                             int64_t n_outer, int64_t n_inner, int64_t outer_start, int P, int rank, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "slab_push: bad dtype %d", dtype);
+    NBK_CHECK_ARG(P >= 1 && P <= NBK_MAX_PEERS && rank >= 0 && rank < P, "slab_push: bad peer count / rank");
+    if (rows_per_peer <= 0 || n_outer <= 0 || n_inner <= 0) return NBK_OK;
+    const size_t cs = dtype == NBK_F4 ? 8 : 16;
+    const size_t width = (size_t)n_outer * n_inner * cs;            // one kl row of my block
+    const size_t dpitch = width * P;                                // the same row of the destination field
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i = 0; i < P; i++) {
+        const int p = (rank + i) % P;                               // every rank starts with a different peer
+        const char *srcp = (const char *)send + (size_t)p * rows_per_peer * width;
+        char *dstp = (char *)peer_ptrs_host[p] + (size_t)outer_start * n_inner * cs;
+        NBK_CUDA(cudaMemcpy2DAsync(dstp, dpitch, srcp, width, width, (size_t)rows_per_peer, cudaMemcpyDeviceToDevice, s));
+    }
+    return NBK_OK;
 }

@@ -258,7 +258,7 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 #define TILE 16
 #define NBK_BLK_SMEM (200 * 1024)   // largest shared-memory tile window (scattered input)
 #define NBK_WIN_COHERENT 16384      // tile window of the coherent configuration (64 KB)
-#define NBK_CHUNKS_COHERENT (4 * NBK_SM_COUNT)
+#define NBK_CHUNKS_COHERENT (12 * NBK_SM_COUNT)
 #define NBK_CHUNKS_SCATTERED NBK_SM_COUNT
 
 // Tile-ordered particle record, 12 bytes for every position dtype: the scatter pass evaluates the grid coordinate
@@ -492,6 +492,7 @@ struct BucketPlan {          // one bucketing configuration (host side, by value
     int nchunks;             // particle chunks (CTAs loop over them)
     int64_t chunk;           // particles per chunk, multiple of 4
     int staged;              // particle coordinates staged by TMA bulk copies (needs a 16-byte aligned array)
+    int nst;                 // slots of the staging ring
 };
 
 // Is the catalogue spatially coherent in array order?  256 threads sample neighbouring pairs (i, i+1): coherent pairs
@@ -557,21 +558,21 @@ __device__ __forceinline__ double load_mass(const void *mass, int mass_f4, int64
 }
 
 // The chunk loop shared by the count and the scatter pass.  Rounds of 4 * blockDim particles: every thread owns one
-// aligned quad per round.  STAGED: thread 0 keeps two rounds in flight as TMA bulk copies into a shared-memory ring
-// (full rounds only; the ragged tail of the last chunk is read directly).  `body(j0, nv, x)` is called by ALL threads
-// (nv = 0 for idle ones) so that it may use warp collectives.
+// aligned quad per round.  STAGED: thread 0 keeps nst - 1 rounds in flight as TMA bulk copies into a shared-memory
+// ring of nst slots (full rounds only; the ragged tail of the last chunk is read directly).  `body(j0, nv, x)` is
+// called by ALL threads (nv = 0 for idle ones) so that it may use warp collectives.
 template <typename PT, bool STAGED, typename F>
-__device__ __forceinline__ void chunk_rounds(const PT *__restrict__ cpos, int cn, PT *sring, uint64_t *bars,
+__device__ __forceinline__ void chunk_rounds(const PT *__restrict__ cpos, int cn, PT *sring, uint64_t *bars, int nst,
                                              unsigned &seq, bool aligned, F body) {
     const int SP = 4 * (int)blockDim.x;                       // particles per round
     const int nround = (cn + SP - 1) / SP;
     const unsigned rbytes = (unsigned)(SP * 3 * sizeof(PT));
     const int nfull = STAGED ? cn / SP : 0;                   // rounds that are copied whole
     if (STAGED && threadIdx.x == 0) {
-        for (int s = 0; s < 2 && s < nfull; s++) {
-            const unsigned q = seq + s;
-            mbar_expect_tx(&bars[q & 1], rbytes);
-            bulk_g2s(sring + (size_t)(q & 1) * SP * 3, cpos + (size_t)s * SP * 3, rbytes, &bars[q & 1]);
+        for (int s = 0; s < nst && s < nfull; s++) {
+            const unsigned slot = (seq + s) % (unsigned)nst;
+            mbar_expect_tx(&bars[slot], rbytes);
+            bulk_g2s(sring + (size_t)slot * SP * 3, cpos + (size_t)s * SP * 3, rbytes, &bars[slot]);
         }
     }
     for (int s = 0; s < nround; s++) {
@@ -579,19 +580,19 @@ __device__ __forceinline__ void chunk_rounds(const PT *__restrict__ cpos, int cn
         const int nv = min(4, max(0, cn - j0));
         PT x[4][3];
         if (STAGED && s < nfull) {
-            const unsigned q = seq + s;
-            mbar_wait(&bars[q & 1], (q >> 1) & 1);
-            load_quad_smem(sring + (size_t)(q & 1) * SP * 3, x);
+            const unsigned q = seq + s, slot = q % (unsigned)nst;
+            mbar_wait(&bars[slot], (q / (unsigned)nst) & 1);
+            load_quad_smem(sring + (size_t)slot * SP * 3, x);
         } else {
             load_quad_gmem(cpos, j0, nv, aligned, x);
         }
         body(j0, nv, x);
         if (STAGED && s < nfull) {
             __syncthreads();                                   // every thread has read this ring slot
-            if (threadIdx.x == 0 && s + 2 < nfull) {
-                const unsigned q = seq + s + 2;
-                mbar_expect_tx(&bars[q & 1], rbytes);
-                bulk_g2s(sring + (size_t)(q & 1) * SP * 3, cpos + (size_t)(s + 2) * SP * 3, rbytes, &bars[q & 1]);
+            if (threadIdx.x == 0 && s + nst < nfull) {
+                const unsigned slot = (seq + s + nst) % (unsigned)nst;
+                mbar_expect_tx(&bars[slot], rbytes);
+                bulk_g2s(sring + (size_t)slot * SP * 3, cpos + (size_t)(s + nst) * SP * 3, rbytes, &bars[slot]);
             }
         }
     }
@@ -651,11 +652,10 @@ k_bucket_count(const PT *__restrict__ pos, const void *__restrict__ mass, int ma
     extern __shared__ __align__(128) unsigned char s_raw[];
     unsigned *s_hist = reinterpret_cast<unsigned *>(s_raw);
     PT *sring = reinterpret_cast<PT *>(s_raw + (((size_t)bp.W * sizeof(unsigned) + 127) & ~(size_t)127));
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[8];
     __shared__ int s_lo;
     if (STAGED && threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < 8; i++) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
@@ -670,7 +670,7 @@ k_bucket_count(const PT *__restrict__ pos, const void *__restrict__ mass, int ma
         __syncthreads();
         const int lo = chunk_window_lo<SUP, PT>(cpos, cn, tg, bp.W, &s_lo);
         if (threadIdx.x == 0) win_lo[c] = lo;
-        chunk_rounds<PT, STAGED>(cpos, cn, sring, bars, seq, aligned, [&](int j0, int nv, const PT (&x)[4][3]) {
+        chunk_rounds<PT, STAGED>(cpos, cn, sring, bars, bp.nst, seq, aligned, [&](int j0, int nv, const PT (&x)[4][3]) {
             int t[4], k[4];
             quad_tiles<SUP, PT>(x, nv, tg, ft, t);
             bool anyout = false;
@@ -762,10 +762,9 @@ k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int 
     extern __shared__ __align__(128) unsigned char s_raw[];
     unsigned *s_cur = reinterpret_cast<unsigned *>(s_raw);
     PT *sring = reinterpret_cast<PT *>(s_raw + (((size_t)bp.W * sizeof(unsigned) + 127) & ~(size_t)127));
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t bars[8];
     if (STAGED && threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < 8; i++) mbar_init(&bars[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
@@ -780,7 +779,7 @@ k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int 
         const int wn = min(bp.W, tg.ntiles - lo);
         for (int i = threadIdx.x; i < wn; i += blockDim.x) s_cur[i] = offsets[lo + i] + row[i];
         __syncthreads();
-        chunk_rounds<PT, STAGED>(cpos, cn, sring, bars, seq, aligned, [&](int j0, int nv, const PT (&x)[4][3]) {
+        chunk_rounds<PT, STAGED>(cpos, cn, sring, bars, bp.nst, seq, aligned, [&](int j0, int nv, const PT (&x)[4][3]) {
             unsigned r[4][3];
             int t[4], k[4];
             bool anyout = false;
@@ -870,20 +869,70 @@ __device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
-// FLUSH 0: ordered write-back (first tile in queue order stores a cell, later ones add; no cleared mesh needed)
+// Along every axis a region cell with local coordinate a is touched by this tile, by the preceding tile if a < H and
+// by the following one if a >= TILE.  Tiles are handed out in DESCENDING index order (lexicographic in (tx, ty, tz)),
+// so along each axis the tile with the larger coordinate is the earlier one and the first toucher of a cell is the
+// per-axis maximum: an interior tile is first for exactly its own 16^3 base block (rows of 16 cells = aligned
+// 128-byte runs of an f8 mesh) and adds its halo to the blocks of the tiles that came before it.  [flo, fhi) = the
+// local coordinates this tile is first for along the axis; the periodic seam is the exception: tile 0's predecessor
+// is the LAST tile (earlier), and the last tile's successor is tile 0 (later).
+struct TileBox {
+    int tc[3], o[3], flo[3], fhi[3];
+};
+template <int R, int H>
+__device__ __forceinline__ TileBox tile_box(int t, const TileGeom &tg) {
+    TileBox b;
+    b.tc[2] = t % tg.nt[2];
+    b.tc[1] = (t / tg.nt[2]) % tg.nt[1];
+    b.tc[0] = t / (tg.nt[2] * tg.nt[1]);
+    b.o[0] = b.tc[0] * TILE - tg.G;                  // region origin (x: slab-local)
+    b.o[1] = b.tc[1] * TILE;
+    b.o[2] = b.tc[2] * TILE;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const bool periodic = (d > 0) || tg.full;
+        b.flo[d] = (periodic && b.tc[d] == 0) ? H : 0;
+        b.fhi[d] = (b.tc[d] < tg.nt[d] - 1) ? TILE : R;
+    }
+    return b;
+}
+
+// exact (double)(hi:lo as a signed 64-bit integer) without conversion instructions (2^52 mantissa trick, one rounding)
+__device__ __forceinline__ double limbs_to_double(unsigned lo, unsigned hi) {
+    const double dlo = __hiloint2double(0x43300000, (int)lo) - 4503599627370496.0;
+    const double dhi = __hiloint2double(0x43300000, (int)(hi ^ 0x80000000u)) - 4503601774854144.0;   // 2^52 + 2^31
+    return __fma_rn(dhi, 4294967296.0, dlo);
+}
+
+// FLUSH 0: ordered write-back: of all tiles touching a cell the first in queue order stores it (plain coalesced
+//          stores), the later ones add (REDG, L2-resident) after the earlier tiles have published their stores; no
+//          cleared mesh needed, every cell is written exactly once.  Interior tiles (the common case) store their own
+//          16^3 base block as 16-byte pairs straight from the accumulator and park their halo -- the cells they must
+//          ADD to the blocks of earlier tiles -- in a small shared-memory stash, which is added one tile later, after
+//          the CTA has accumulated its next tile: by then the neighbours have long published, so the flag poll (per
+//          warp, no CTA barrier) is almost never a wait.  Two CTA barriers per tile.  Tiles on the mesh boundary take
+//          a generic per-cell path (and wait in place where their add set does not fit the stash).
 // FLUSH 1: TMA bulk reduce-add, one row per op, into an existing mesh (hold=True)
 template <int SUP, typename MT, typename FT, bool SHIFTED, int FLUSH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, FLUSH == 0 ? 4 : 1)
 k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, TileGeom tg,
              const unsigned *__restrict__ offsets, unsigned *__restrict__ hdr, unsigned *__restrict__ flags,
              unsigned epoch, int spread, FT *__restrict__ mesh) {
-    extern __shared__ __align__(16) unsigned s_acc[];
+    extern __shared__ __align__(16) unsigned s_all[];
     constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0);   // == tg.R
-    constexpr int RP = (R + 3) & ~3;                         // row pitch in cells: rows start 16-byte aligned
-    constexpr int NC = R * R * RP;                           // multiple of 4
+    // row pitch in cells: the TMA write-back needs rows that start 16-byte aligned, the ordered one 8-byte cell pairs
+    constexpr int RP = FLUSH == 0 ? ((R + 1) & ~1) : ((R + 3) & ~3);
+    constexpr int NC = R * R * RP;
+    constexpr int BUFW = (2 * NC + 3) & ~3;                  // words of the accumulator (lo | hi limbs)
     constexpr int H = R - TILE;   // cells with a local coordinate < H are also written by the preceding tile
-    unsigned *s_lo = s_acc, *s_hi = s_acc + NC;
+    constexpr int CAP = R * R * R - TILE * TILE * TILE;      // halo cells = what an interior tile adds
+    constexpr int NT = 256, NW = NT >> 5;
+    constexpr int HK = (CAP + NT - 1) / NT;                  // halo cells per thread
+    unsigned *s_lo = s_all, *s_hi = s_all + NC;
+    FT *s_sval = reinterpret_cast<FT *>(s_all + BUFW);                    // stash: value ...
+    unsigned *s_soff = reinterpret_cast<unsigned *>(s_sval + CAP);        // ... and mesh offset of a parked cell
     __shared__ int s_tile;
+    __shared__ unsigned s_nst[2];
     // scale 2^31 / M, M = power of two >= max |mass|
     double M = 1.0;
     if (smass) {
@@ -893,25 +942,20 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
         M = mx > 0.f ? ldexp(1.0, e) : 1.0;
     }
     const double S = 2147483648.0 / M, invS = M / 2147483648.0;
-    constexpr int PER = (NC + 255) / 256;
-    for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);
-        __syncthreads();                                     // also: the accumulator is zero (start / end of last tile)
-        const int t = s_tile;
-        if (t >= tg.ntiles) break;
-        const unsigned b = offsets[t], e = offsets[t + 1];
-        if (FLUSH == 1 && b == e) { __syncthreads(); continue; }
-        const int tz = t % tg.nt[2], ty = (t / tg.nt[2]) % tg.nt[1], tx = t / (tg.nt[2] * tg.nt[1]);
-        const int o[3] = {tx * TILE - tg.G, ty * TILE, tz * TILE};   // region origin (x: slab-local)
-        // Particle -> thread map.  spread == 0: thread p takes records p, p + 256, ... (coalesced).  spread != 0: the
+    for (int i = threadIdx.x; i < BUFW / 4; i += NT) reinterpret_cast<uint4 *>(s_all)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) { s_nst[0] = 0; s_nst[1] = 0; }
+    const bool small_mesh = (int64_t)tg.gm.x_n * tg.gm.n[1] * tg.gm.n[2] < (1ll << 32);   // 32-bit stash offsets
+    const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+
+    // deposits of the records [b, e) of one bucket into the accumulator
+    auto accumulate = [&](unsigned b, unsigned e) {
+        // Particle -> thread map.  spread == 0: thread p takes records p, p + NT, ... (coalesced).  spread != 0: the
         // lanes of a warp walk 32 separate segments of the bucket, so that the neighbouring (same-cell) particles of a
         // spatially coherent catalogue do not meet in one ATOMS instruction.
         const unsigned cnt = e - b;
         const unsigned seg = (cnt + 31) / 32;               // records per lane segment (spread mode)
-        const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
         unsigned idx = spread ? wid : threadIdx.x;          // spread: position within the lane's segment
-        const unsigned step = spread ? 8u : 256u;
+        const unsigned step = spread ? (unsigned)NW : (unsigned)NT;
         const unsigned lim = spread ? min(seg, cnt > lane * seg ? cnt - lane * seg : 0u) : cnt;
         const unsigned base = spread ? b + lane * seg : b;
         unsigned rn[3] = {0, 0, 0};
@@ -974,111 +1018,245 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                     }
             }
         }
-        __syncthreads();
-        if (FLUSH == 1) {
+    };
+
+    if (FLUSH == 1) {
+        for (;;) {
+            if (threadIdx.x == 0) s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);
+            __syncthreads();                                     // also: the accumulator is zero
+            const int t = s_tile;
+            if (t >= tg.ntiles) break;
+            const unsigned b = offsets[t], e = offsets[t + 1];
+            if (b == e) { __syncthreads(); continue; }
+            accumulate(b, e);
+            __syncthreads();
+            const TileBox bx = tile_box<R, H>(t, tg);
             // ---- convert the region to mesh dtype (through registers: the values overlay the limb arrays), then one
             // TMA bulk reduce-add per z row
+            constexpr int PER = (NC + NT - 1) / NT;
             FT v[PER];
 #pragma unroll
             for (int k = 0; k < PER; k++) {
-                int i = threadIdx.x + k * 256;
+                int i = threadIdx.x + k * NT;
                 v[k] = (FT)0;
-                if (i < NC) {
-                    unsigned lo = s_lo[i], hi = s_hi[i];
-                    v[k] = (FT)((double)(long long)(((unsigned long long)hi << 32) | lo) * invS);
-                }
+                if (i < NC) v[k] = (FT)(limbs_to_double(s_lo[i], s_hi[i]) * invS);
             }
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < PER; k++) {
-                int i = threadIdx.x + k * 256;
-                if (i < NC) reinterpret_cast<FT *>(s_acc)[i] = v[k];
+                int i = threadIdx.x + k * NT;
+                if (i < NC) reinterpret_cast<FT *>(s_all)[i] = v[k];
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
-            const int nz1 = min(RP, tg.gm.n[2] - o[2]);      // cells up to the end of the z row; the rest wraps to z = 0
-            for (int row = threadIdx.x; row < R * R; row += blockDim.x) {
+            const int nz1 = min(RP, tg.gm.n[2] - bx.o[2]);   // cells up to the end of the z row; the rest wraps to z = 0
+            for (int row = threadIdx.x; row < R * R; row += NT) {
                 int cx = row / R, cy = row - cx * R;
-                int gx = o[0] + cx + tg.gm.x_start;
+                int gx = bx.o[0] + cx + tg.gm.x_start;
                 if (gx < 0) gx += tg.gm.n[0];
                 if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
                 int ix = gx - tg.gm.x_start;
                 if (ix < 0 || ix >= tg.gm.x_n) continue;     // not my plane (ghost semantics)
-                int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
+                int iy = bx.o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
                 FT *grow = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2];
-                const FT *srow = reinterpret_cast<const FT *>(s_acc) + (size_t)row * RP;
-                tma_reduce_add(grow + o[2], srow, (unsigned)(nz1 * sizeof(FT)));
+                const FT *srow = reinterpret_cast<const FT *>(s_all) + (size_t)row * RP;
+                tma_reduce_add(grow + bx.o[2], srow, (unsigned)(nz1 * sizeof(FT)));
                 if (nz1 < RP) tma_reduce_add(grow, srow + nz1, (unsigned)((RP - nz1) * sizeof(FT)));
             }
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory may be reused
             __syncthreads();
-            for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
-        } else {
-            // ---- ordered write-back.  Along every axis a region cell with local coordinate a is touched by this tile,
-            // by the preceding tile if a < H and by the following one if a >= TILE; queue order is lexicographic in
-            // (tx, ty, tz), so the first toucher of a cell is the per-axis minimum.  [flo, fhi) = cells this tile is
-            // first for along the axis: the preceding tile is earlier unless this is tile 0 (its periodic predecessor
-            // is the LAST tile); the following tile is later unless it wraps around to tile 0.
-            const int tc[3] = {tx, ty, tz};
-            int flo[3], fhi[3];
+            for (int i = threadIdx.x; i < BUFW / 4; i += NT) reinterpret_cast<uint4 *>(s_all)[i] = make_uint4(0, 0, 0, 0);
+        }
+        return;
+    }
+
+    // ================= ordered write-back =================
+    // this thread's halo cells (tile independent): packed local coordinates, -1 = none
+    int hcell[HK > 0 ? HK : 1];
+    {
+        constexpr int N1 = H * R * R, N2 = TILE * H * R;
+        constexpr int HD = H > 0 ? H : 1;
+#pragma unroll
+        for (int k = 0; k < (HK > 0 ? HK : 1); k++) {
+            const int i = (int)threadIdx.x + k * NT;
+            int cx = 0, cy = 0, cz = 0;
+            if (i < N1) { cx = TILE + i / (R * R); const int r = i % (R * R); cy = r / R; cz = r - cy * R; }
+            else if (i < N1 + N2) { const int j = i - N1; cx = j / (HD * R); const int r = j - cx * (HD * R); cy = TILE + r / R; cz = r % R; }
+            else { const int j = i - N1 - N2; cx = j / (TILE * HD); const int r = j - cx * (TILE * HD); cy = r / HD; cz = TILE + r % HD; }
+            hcell[k] = (i < CAP) ? ((cx << 16) | (cy << 8) | cz) : -1;
+        }
+    }
+    // every warp polls the flags of the (up to 26) earlier tiles overlapping tile `bx` itself: no CTA barrier
+    auto poll_earlier = [&](const TileBox &bx) {
+        if (lane < 27) {              // {this, following, wrapped-preceding} per axis
+            int sel[3] = {(int)lane % 3, ((int)lane / 3) % 3, (int)lane / 9};
+            int nb[3];
+            bool valid = lane != 0;
 #pragma unroll
             for (int d = 0; d < 3; d++) {
-                const bool periodic = (d > 0) || tg.full;
-                flo[d] = (tc[d] > 0) ? H : 0;
-                fhi[d] = (periodic && tc[d] == tg.nt[d] - 1) ? TILE : R;
+                if (sel[d] == 0) nb[d] = bx.tc[d];
+                else if (sel[d] == 1) { nb[d] = bx.tc[d] + 1; valid = valid && bx.fhi[d] < R; }
+                else { nb[d] = tg.nt[d] - 1; valid = valid && bx.flo[d] > 0 && bx.tc[d] != tg.nt[d] - 1; }
             }
-            // pass 1: plain stores of the cells this tile is first for (every mesh cell is stored exactly once)
-            // pass 2: after the earlier tiles have published their stores: add the rest
-#pragma unroll 1
-            for (int pass = 0; pass < 2; pass++) {
-                if (pass == 1) {
-                    __threadfence();
-                    __syncthreads();
-                    if (threadIdx.x == 0) st_release(&flags[t], epoch);
-                    // up to 26 earlier tiles: {this, preceding, wrapped-following} per axis
-                    if (threadIdx.x < 27) {
-                        int sel[3] = {(int)threadIdx.x % 3, ((int)threadIdx.x / 3) % 3, (int)threadIdx.x / 9};
-                        int nb[3];
-                        bool valid = threadIdx.x != 0;
+            if (valid) {
+                const unsigned *f = &flags[(nb[0] * tg.nt[1] + nb[1]) * tg.nt[2] + nb[2]];
+                while (ld_acquire(f) < epoch) __nanosleep(32);
+            }
+        }
+        __syncwarp();
+    };
+    // warp-aggregated append of (mesh offset, value) to the stash
+    auto stash_push = [&](bool keep, unsigned off, FT val, unsigned *counter) {
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (mask) {
+            unsigned basep = 0;
+            const int leader = __ffs(mask) - 1;
+            if ((int)lane == leader) basep = atomicAdd(counter, (unsigned)__popc(mask));
+            basep = __shfl_sync(0xffffffffu, basep, leader);
+            if (keep) {
+                const unsigned pos = basep + __popc(mask & ((1u << lane) - 1u));
+                s_soff[pos] = off;
+                s_sval[pos] = val;
+            }
+        }
+    };
+
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);
+    __syncthreads();
+    int t = tg.ntiles - 1 - s_tile;            // tiles are handed out in descending order
+    bool pending = false;                      // the stash holds the add set of the previous tile (counter s_nst[pbuf])
+    int pbuf = 0;
+    TileBox pbox;
+    for (;;) {
+        // ---- (1) the parked add set of the previous tile
+        if (pending) {
+            poll_earlier(pbox);
+            const unsigned n = s_nst[pbuf];
+            for (unsigned i = threadIdx.x; i < n; i += NT) atomicAdd(mesh + s_soff[i], s_sval[i]);
+        }
+        if (t < 0) break;
+        // ---- (2) accumulate
+        accumulate(offsets[t], offsets[t + 1]);
+        __syncthreads();                                                 // barrier 1 of 2
+        const int cbuf = pbuf ^ 1;
+        if (threadIdx.x == 0) {
+            if (pending) s_nst[pbuf] = 0;                                // consumed above by everyone
+            s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);                // next tile, visible after barrier 2
+        }
+        pending = false;
+        // ---- (3) write-back
+        const TileBox bx = tile_box<R, H>(t, tg);
+        const bool interior = small_mesh && bx.flo[0] == 0 && bx.flo[1] == 0 && bx.flo[2] == 0 &&
+                              bx.fhi[0] == TILE && bx.fhi[1] == TILE && bx.fhi[2] == TILE;
+        if (interior) {
+            // base block: thread = (cy, z pair), 8 steps of two x planes; the accumulator is zeroed as it is read
+            {
+                const int row0 = (int)threadIdx.x >> 3, cz = ((int)threadIdx.x & 7) * 2;
+                const int cy = row0 & 15, cx0 = row0 >> 4;
+                int si = (cx0 * R + cy) * RP + cz;
+                int lx = bx.o[0] + cx0;                                   // slab-local x (full mesh: the global one)
+                int64_t o64 = ((int64_t)lx * tg.gm.n[1] + (bx.o[1] + cy)) * tg.gm.n[2] + (bx.o[2] + cz);
+                const int64_t ostep = 2 * (int64_t)tg.gm.n[1] * tg.gm.n[2];
+#pragma unroll 4
+                for (int j = 0; j < TILE / 2; j++) {
+                    const uint2 lo2 = *reinterpret_cast<const uint2 *>(s_lo + si);
+                    const uint2 hi2 = *reinterpret_cast<const uint2 *>(s_hi + si);
+                    *reinterpret_cast<uint2 *>(s_lo + si) = make_uint2(0u, 0u);
+                    *reinterpret_cast<uint2 *>(s_hi + si) = make_uint2(0u, 0u);
+                    if (lx >= 0 && lx < tg.gm.x_n) {                      // ghost planes of a slab are dropped
+                        const FT v0 = (FT)(limbs_to_double(lo2.x, hi2.x) * invS), v1 = (FT)(limbs_to_double(lo2.y, hi2.y) * invS);
+                        if (sizeof(FT) == 8) *reinterpret_cast<double2 *>(mesh + o64) = make_double2((double)v0, (double)v1);
+                        else *reinterpret_cast<float2 *>(mesh + o64) = make_float2((float)v0, (float)v1);
+                    }
+                    si += 2 * R * RP;
+                    lx += 2;
+                    o64 += ostep;
+                }
+            }
+            // halo: parked (read, zeroed, appended to the stash)
 #pragma unroll
-                        for (int d = 0; d < 3; d++) {
-                            if (sel[d] == 0) nb[d] = tc[d];
-                            else if (sel[d] == 1) { nb[d] = tc[d] - 1; valid = valid && flo[d] > 0; }
-                            else { nb[d] = 0; valid = valid && fhi[d] < R && tc[d] != 0; }
-                        }
-                        if (valid) {
-                            const unsigned *f = &flags[(nb[0] * tg.nt[1] + nb[1]) * tg.nt[2] + nb[2]];
-                            while (ld_acquire(f) < epoch) __nanosleep(64);
+            for (int k = 0; k < (HK > 0 ? HK : 1); k++) {
+                bool keep = false;
+                unsigned off = 0;
+                FT val = (FT)0;
+                if (HK > 0 && hcell[k] >= 0) {
+                    const int cx = hcell[k] >> 16, cy = (hcell[k] >> 8) & 255, cz = hcell[k] & 255;
+                    const int si = (cx * R + cy) * RP + cz;
+                    const unsigned lo = s_lo[si], hi = s_hi[si];
+                    if ((lo | hi) != 0u) {
+                        s_lo[si] = 0u;
+                        s_hi[si] = 0u;
+                        int lx = bx.o[0] + cx;
+                        if (tg.full && lx >= tg.gm.n[0]) lx -= tg.gm.n[0];
+                        if (lx >= 0 && lx < tg.gm.x_n) {
+                            int iy = bx.o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
+                            int iz = bx.o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
+                            off = (unsigned)(((int64_t)lx * tg.gm.n[1] + iy) * tg.gm.n[2] + iz);
+                            val = (FT)(limbs_to_double(lo, hi) * invS);
+                            keep = true;
                         }
                     }
-                    __syncthreads();
                 }
-                for (int i = threadIdx.x; i < R * R * 32; i += blockDim.x) {
-                    const int row = i >> 5, cz = i & 31;                 // one warp-row per (cx, cy): lanes along z
-                    if (cz >= R) continue;
-                    const int cx = row / R, cy = row - cx * R;
-                    const bool first = cx >= flo[0] && cx < fhi[0] && cy >= flo[1] && cy < fhi[1] && cz >= flo[2] && cz < fhi[2];
-                    if (first != (pass == 0)) continue;
-                    const int si = row * RP + cz;
-                    const unsigned lo = s_lo[si], hi = s_hi[si];
-                    if (pass == 1 && (lo | hi) == 0u) continue;
-                    int gx = o[0] + cx + tg.gm.x_start;
-                    if (gx < 0) gx += tg.gm.n[0];
-                    if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
-                    const int ix = gx - tg.gm.x_start;
-                    if (ix < 0 || ix >= tg.gm.x_n) continue;             // not my plane (ghost semantics)
-                    int iy = o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
-                    int iz = o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
-                    const double val = (double)(long long)(((unsigned long long)hi << 32) | lo) * invS;
-                    FT *dst = mesh + ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
-                    if (pass == 0) *dst = (FT)val;
-                    else atomicAdd(dst, (FT)val);
+                stash_push(keep, off, val, &s_nst[cbuf]);
+            }
+            pending = true;
+        } else {
+            // ---- mesh-boundary tiles: generic per-cell path
+            const bool park = small_mesh && bx.flo[0] == 0 && bx.flo[1] == 0 && bx.flo[2] == 0;
+            auto locate = [&](int cx, int cy, int cz, int64_t &o64) -> bool {
+                int gx = bx.o[0] + cx + tg.gm.x_start;
+                if (gx < 0) gx += tg.gm.n[0];
+                if (gx >= tg.gm.n[0]) gx -= tg.gm.n[0];
+                const int ix = gx - tg.gm.x_start;
+                if (ix < 0 || ix >= tg.gm.x_n) return false;
+                int iy = bx.o[1] + cy; if (iy >= tg.gm.n[1]) iy -= tg.gm.n[1];
+                int iz = bx.o[2] + cz; if (iz >= tg.gm.n[2]) iz -= tg.gm.n[2];
+                o64 = ((int64_t)ix * tg.gm.n[1] + iy) * tg.gm.n[2] + iz;
+                return true;
+            };
+            // pass 0: store if this tile is first for the cell, else park it (or leave it to pass 1);
+            // pass 1 (after the wait): add what was left
+            auto sweep = [&](int pass) {
+                for (int i0 = 0; i0 < R * R * R; i0 += NT) {
+                    const int i = i0 + (int)threadIdx.x;
+                    bool keep = false;
+                    FT val = (FT)0;
+                    unsigned off = 0;
+                    if (i < R * R * R) {
+                        const int cx = i / (R * R), r = i - cx * (R * R), cy = r / R, cz = r - cy * R;
+                        const bool first = cx >= bx.flo[0] && cx < bx.fhi[0] && cy >= bx.flo[1] && cy < bx.fhi[1] &&
+                                           cz >= bx.flo[2] && cz < bx.fhi[2];
+                        int64_t o64;
+                        if ((first == (pass == 0) || (pass == 0 && park)) && locate(cx, cy, cz, o64)) {
+                            const int si = (cx * R + cy) * RP + cz;
+                            const unsigned lo = s_lo[si], hi = s_hi[si];
+                            val = (FT)(limbs_to_double(lo, hi) * invS);
+                            if (first) mesh[o64] = val;
+                            else if ((lo | hi) != 0u) {
+                                if (pass == 1) atomicAdd(mesh + o64, val);
+                                else { keep = true; off = (unsigned)o64; }
+                            }
+                        }
+                    }
+                    if (pass == 0 && park) stash_push(keep, off, val, &s_nst[cbuf]);
                 }
+            };
+            sweep(0);
+            if (park) pending = true;
+            else {
+                __syncthreads();
+                if (threadIdx.x == 0) st_release(&flags[t], epoch);
+                poll_earlier(bx);
+                sweep(1);
             }
             __syncthreads();
-            for (int i = threadIdx.x; i < NC / 2; i += blockDim.x) reinterpret_cast<uint4 *>(s_acc)[i] = make_uint4(0, 0, 0, 0);
+            for (int i = threadIdx.x; i < BUFW / 4; i += NT) reinterpret_cast<uint4 *>(s_all)[i] = make_uint4(0, 0, 0, 0);
         }
+        __syncthreads();                                                 // barrier 2 of 2
+        if (threadIdx.x == 0) st_release(&flags[t], epoch);              // cumulative over the CTA's stores (bar.sync)
+        if (pending) { pbox = bx; pbuf = cbuf; }
+        t = tg.ntiles - 1 - s_tile;
     }
 }
 
@@ -1112,31 +1290,48 @@ extern "C" int nbk_paint_tiled_supported(const int64_t *nmesh, int64_t x_n, int 
 }
 
 // the two bucketing configurations for a problem (only their sizes depend on it)
-static void make_plans(int64_t n, int ntiles, size_t pos_size, bool aligned, BucketPlan &coh, BucketPlan &sca,
+static int env_int(const char *name, int dflt) {
+    const char *e = getenv(name);
+    return (e && e[0]) ? atoi(e) : dflt;
+}
+
+static void plan_chunks(BucketPlan &p, int64_t n, int maxchunks) {
+    int64_t nch = (n + 16383) / 16384;               // at least 16 Ki particles per chunk
+    if (nch < 1) nch = 1;
+    if (nch > maxchunks) nch = maxchunks;
+    p.chunk = (((n + nch - 1) / nch) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
+    if (p.chunk < 4) p.chunk = 4;
+    p.nchunks = (int)((n + p.chunk - 1) / p.chunk);
+    if (p.nchunks < 1) p.nchunks = 1;
+}
+
+static void make_plans(int64_t n, const int *nt, int ntiles, size_t pos_size, bool aligned, BucketPlan &coh, BucketPlan &sca,
                        int &threads_coh, size_t &smem_coh, int &threads_sca, size_t &smem_sca) {
-    auto chunking = [&](BucketPlan &p, int maxchunks) {
-        int64_t nch = (n + 16383) / 16384;               // at least 16 Ki particles per chunk
-        if (nch < 1) nch = 1;
-        if (nch > maxchunks) nch = maxchunks;
-        p.chunk = (((n + nch - 1) / nch) + 3) & ~(int64_t)3;   // multiple of 4: threads own aligned quads
-        if (p.chunk < 4) p.chunk = 4;
-        p.nchunks = (int)((n + p.chunk - 1) / p.chunk);
-        if (p.nchunks < 1) p.nchunks = 1;
-    };
+    auto align128 = [](size_t x) { return (x + 127) & ~(size_t)127; };
+    // coherent input: a chunk spans a couple of planes of tiles (+- the displacement blur): 4 planes, at least 4096
+    // tiles, at most NBK_WIN_COHERENT (64 KB)
     coh.mode = 1;
-    coh.W = ntiles < NBK_WIN_COHERENT ? ntiles : NBK_WIN_COHERENT;
-    chunking(coh, NBK_CHUNKS_COHERENT);
-    threads_coh = 512;
-    size_t ring = (size_t)2 * 4 * threads_coh * 3 * pos_size;
-    coh.staged = aligned ? 1 : 0;
-    smem_coh = (((size_t)coh.W * 4 + 127) & ~(size_t)127) + (coh.staged ? ring : 0);
+    int64_t w = 4 * (int64_t)nt[1] * nt[2];
+    if (w < 4096) w = 4096;
+    if (w > NBK_WIN_COHERENT) w = NBK_WIN_COHERENT;
+    w = env_int("NBK_PAINT_W", (int)w);
+    coh.W = ntiles < w ? ntiles : (int)w;
+    plan_chunks(coh, n, NBK_CHUNKS_COHERENT);        // refined by the caller once the occupancy is known
+    threads_coh = env_int("NBK_PAINT_THREADS", 512);
+    coh.nst = env_int("NBK_PAINT_NST", 2);
+    if (coh.nst < 2) coh.nst = 2;
+    if (coh.nst > 8) coh.nst = 8;
+    size_t ring = (size_t)coh.nst * 4 * threads_coh * 3 * pos_size;
+    coh.staged = (aligned && env_int("NBK_PAINT_STAGED", 0) && align128((size_t)coh.W * 4) + ring <= 224 * 1024) ? 1 : 0;
+    smem_coh = align128((size_t)coh.W * 4) + (coh.staged ? ring : 0);
     sca.mode = 0;
     sca.W = ntiles < NBK_BLK_SMEM / 4 ? ntiles : NBK_BLK_SMEM / 4;
-    chunking(sca, NBK_CHUNKS_SCATTERED);
+    plan_chunks(sca, n, NBK_CHUNKS_SCATTERED);
     threads_sca = 1024;
-    ring = (size_t)2 * 4 * threads_sca * 3 * pos_size;
-    sca.staged = (aligned && (((size_t)sca.W * 4 + 127) & ~(size_t)127) + ring <= 224 * 1024) ? 1 : 0;
-    smem_sca = (((size_t)sca.W * 4 + 127) & ~(size_t)127) + (sca.staged ? ring : 0);
+    sca.nst = 2;
+    ring = (size_t)sca.nst * 4 * threads_sca * 3 * pos_size;
+    sca.staged = (aligned && env_int("NBK_PAINT_STAGED", 0) && align128((size_t)sca.W * 4) + ring <= 224 * 1024) ? 1 : 0;
+    smem_sca = align128((size_t)sca.W * 4) + (sca.staged ? ring : 0);
 }
 
 extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_dtype, const int64_t *nmesh,
@@ -1177,7 +1372,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     int th_c, th_s;
     size_t sm_c, sm_s;
     const bool aligned = (reinterpret_cast<uintptr_t>(pos) & 15) == 0;
-    make_plans(n, tg.ntiles, sizeof(PT), aligned, coh, sca, th_c, sm_c, th_s, sm_s);
+    make_plans(n, tg.nt, tg.ntiles, sizeof(PT), aligned, coh, sca, th_c, sm_c, th_s, sm_s);
     unsigned *blk = (unsigned *)w;
     {
         size_t a = (size_t)coh.W * NBK_CHUNKS_COHERENT, b = (size_t)sca.W * NBK_CHUNKS_SCATTERED;
@@ -1199,16 +1394,41 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         k_bucket_probe<SUP, PT><<<1, 256, 0, s>>>((const PT *)pos, n, tg, hdr);
         NBK_LAUNCHED();
     }
-    const int grid_c = coh.nchunks < 2 * NBK_SM_COUNT ? coh.nchunks : 2 * NBK_SM_COUNT;
+    // Coherent plan: every resident CTA gets the same number of chunks in BOTH passes (their occupancies differ:
+    // the scatter pass needs more registers), else the last partial wave runs at a fraction of the machine.
+    int occ_c = 1, occ_s = 1;
+    if (coh.staged) {
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, true>, th_c, sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, true>, th_c, sm_c));
+    } else {
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, false>, th_c, sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, false>, th_c, sm_c));
+    }
+    if (occ_c < 1) occ_c = 1;
+    if (occ_s < 1) occ_s = 1;
+    if (occ_c > 4) occ_c = 4;
+    if (occ_s > 4) occ_s = 4;
+    {
+        int l = occ_c * occ_s, a = occ_c, b = occ_s;
+        while (b) { int r = a % b; a = b; b = r; }
+        l /= a;                                              // lcm <= 12
+        plan_chunks(coh, n, l * NBK_SM_COUNT);
+    }
+    const int grid_c = coh.nchunks < occ_c * NBK_SM_COUNT ? coh.nchunks : occ_c * NBK_SM_COUNT;
+    const int grid_cs = coh.nchunks < occ_s * NBK_SM_COUNT ? coh.nchunks : occ_s * NBK_SM_COUNT;
     const int grid_s = sca.nchunks < NBK_SM_COUNT ? sca.nchunks : NBK_SM_COUNT;
-#define LAUNCH_BUCKET(KERN, ...)                                                                                      \
+#define LAUNCH_BUCKET(KERN, GRIDC, ...)                                                                                      \
     do {                                                                                                              \
         if (coh.staged) {                                                                                             \
             NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c)); \
-            KERN<SUP, PT, true><<<grid_c, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                         \
+            KERN<SUP, PT, true><<<GRIDC, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                         \
         } else {                                                                                                      \
             NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c)); \
-            KERN<SUP, PT, false><<<grid_c, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                        \
+            KERN<SUP, PT, false><<<GRIDC, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                        \
         }                                                                                                             \
         NBK_LAUNCHED();                                                                                               \
         if (sca.staged) {                                                                                             \
@@ -1223,29 +1443,30 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         NBK_LAUNCHED();                                                                                               \
     } while (0)
     // (the plan is the LAST kernel argument of both passes so that one macro serves them)
-    LAUNCH_BUCKET(k_bucket_count, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, cnt_w, cnt_o, blk, win_lo);
+    LAUNCH_BUCKET(k_bucket_count, grid_c, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, cnt_w, cnt_o, blk, win_lo);
     k_tile_scan<<<1, 1024, 0, s>>>(cnt_w, cnt_o, offsets, cur_o, flags, hdr, tg.ntiles);
     NBK_LAUNCHED();
-    LAUNCH_BUCKET(k_bucket_scatter, (const PT *)pos, mass, mass_f4, n, tg, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
+    LAUNCH_BUCKET(k_bucket_scatter, grid_cs, (const PT *)pos, mass, mass_f4, n, tg, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
                   (void *)smass);
 #undef LAUNCH_BUCKET
     int spread_mode;
     {
-        const char *e = getenv("NBK_PAINT_SPREAD");      // "0": thread p takes records p, p + 256, ... (diagnosis)
-        spread_mode = (e && e[0] == '0') ? 0 : 1;
+        const char *e = getenv("NBK_PAINT_SPREAD");      // "1": the lanes of a warp walk separate segments of a bucket (diagnosis)
+        spread_mode = (e && e[0] == '1') ? 1 : 0;
     }
     // the region edge depends on the mesh being painted (one more cell for the half-cell shifted one); tile ids do not
 #define LAUNCH_TP(SH, FL, MESHP, EPOCH)                                                                                \
     do {                                                                                                              \
-        const int Rr = TILE + SUP - 1 + ((SH) ? 1 : 0), RPr = (Rr + 3) & ~3;                                          \
-        size_t smem = (size_t)2 * Rr * Rr * RPr * sizeof(unsigned);                                                   \
-        int per_sm = (int)((220 * 1024) / (smem + 2048));                                                             \
-        if (per_sm > 6) per_sm = 6;                                                                                   \
+        const int Rr = TILE + SUP - 1 + ((SH) ? 1 : 0), RPr = (FL) == 0 ? ((Rr + 1) & ~1) : ((Rr + 3) & ~3);                       \
+        size_t smem = (size_t)((2 * Rr * Rr * RPr + 3) & ~3) * sizeof(unsigned);                                      \
+        if ((FL) == 0) smem += (size_t)(Rr * Rr * Rr - TILE * TILE * TILE) * (sizeof(FT) + sizeof(unsigned));        \
+        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)smem));                                                                    \
+        int per_sm = 1;                                                                                               \
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tile_paint<SUP, MT, FT, SH, FL>, 256, smem)); \
         if (per_sm < 1) per_sm = 1;                                                                                   \
         int grid = NBK_SM_COUNT * per_sm;                                                                             \
         if (grid > tg.ntiles) grid = tg.ntiles;                                                                       \
-        NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
-                                      (int)smem));                                                                    \
         k_tile_paint<SUP, MT, FT, SH, FL><<<grid, 256, smem, s>>>(recs, smass, tg, offsets, hdr, flags, EPOCH,         \
                                                                   spread_mode, (FT *)(MESHP));                        \
         NBK_LAUNCHED();                                                                                               \

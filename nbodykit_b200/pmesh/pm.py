@@ -104,6 +104,15 @@ class Layout(object):
 _PEER_STAGE_CACHE = {}
 
 
+def _transpose_mode():
+    """how the slab transpose of a distributed FFT crosses NVLink: 'push' (line pass into send blocks + one strided bulk
+    copy per peer, default) or 'stores' (the line pass stores every 128..256-byte run straight into the peer's field);
+    NBK_FFT_TRANSPOSE_MODE selects"""
+    import os
+    m = os.environ.get("NBK_FFT_TRANSPOSE_MODE", "push")
+    return m if m in ("push", "stores") else "push"
+
+
 class SlabLayout(object):
     """device-side routing plan (nbk_route_count): compact list of the particles with REMOTE destination slabs
     (index | bitmask << 32).  Local particles are never moved -- `route()` returns only what arrives from other
@@ -186,11 +195,16 @@ class ParticleMesh(object):
         self.BoxSize[:] = BoxSize
         self.ndim = 3
         self._dtype_in = numpy.dtype(dtype)
-        if self._dtype_in.kind == "c":
+        # complex dtype ('c8'/'c16', pmesh then transforms c2c and keeps all N^3 modes: fftpower.py:572,
+        # convpower/catalog.py:151-176).  The configuration-space fields of this path are real-valued: they are
+        # STORED as real arrays, and the full spectrum is the Hermitian completion of the r2c result
+        # (nbk_hermitian_expand) -- identical values, a third of the memory traffic of a c2c transform.
+        self.cplx = self._dtype_in.kind == "c"
+        if self.cplx and self.comm.size > 1:
             raise NotImplementedError(
-                "complex-typed meshes (dtype='c8'/'c16', full c2c transforms) are not implemented; "
-                "use dtype='f4'/'f8' (Hermitian-compressed r2c), e.g. FKPCatalog.to_mesh(dtype='f8')")
-        self.dtype = numpy.dtype(_real_typestr(dtype))
+                "complex-typed meshes (dtype='c8'/'c16') are single-GPU here; on several GPUs use dtype='f4'/'f8' "
+                "(ConvolvedFFTPower reproduces the full-mesh result from the compressed field on any number of GPUs)")
+        self.dtype = self._dtype_in if self.cplx else numpy.dtype(_real_typestr(dtype))
         self.typestr = _real_typestr(dtype)
         self.resampler = _window.FindResampler(resampler)
         self.affine = Affine(3, self.Nmesh / self.BoxSize, 0.0, self.Nmesh.copy())
@@ -204,7 +218,7 @@ class ParticleMesh(object):
         self.x_start = self.comm.rank * self.x_n
         self.y_n = Ny // P
         self.y_start = self.comm.rank * self.y_n
-        self.Nzc = Nz // 2 + 1
+        self.Nzc = Nz if self.cplx else Nz // 2 + 1      # stored length of the last axis of a ComplexField
         self.transposed = P > 1
         self._nmesh_c = iarr(self.Nmesh)
         self._box_c = darr(self.BoxSize)
@@ -230,7 +244,7 @@ class ParticleMesh(object):
             dtype = self.dtype
         Nm = numpy.empty(3, dtype="i8")
         Nm[:] = Nmesh
-        if (Nm == self.Nmesh).all() and numpy.allclose(BoxSize, self.BoxSize) and numpy.dtype(dtype) == self.dtype:
+        if (Nm == self.Nmesh).all() and numpy.allclose(BoxSize, self.BoxSize) and numpy.dtype(dtype) == numpy.dtype(self.dtype):
             return self
         return ParticleMesh(BoxSize=BoxSize, Nmesh=Nm, dtype=dtype, comm=self.comm)
 
@@ -678,10 +692,12 @@ class Field(object):
                 and getattr(func, "__module__", "").startswith("nbodykit_b200"):
             target.compensate(name)
             return target
-        target._apply_host(func, kind)
+        if not target._apply_device(func, kind):
+            target._apply_host(func, kind)
         return target
 
-    def _apply_host(self, func, kind):
+    def _coords_for(self, kind):
+        """(coordinate arrays the callback gets for `kind`, physical dimension running along storage axis 0)"""
         pm = self.pm
         is_real = isinstance(self, RealField)
         coords, ind = pm.create_coords("real" if is_real else "complex", return_indices=True)
@@ -691,13 +707,60 @@ class Field(object):
         elif kind == "relative" and is_real:
             use = coords
         elif kind == "circular" and not is_real:
-            order = [0, 1, 2]
-            use = [(c.astype("f8") * (pm.BoxSize[d] / N[d])).astype(c.dtype) for d, c in zip(order, coords)]
+            use = [(c.astype("f8") * (pm.BoxSize[d] / N[d])).astype(c.dtype) for d, c in enumerate(coords)]
         elif kind in ("wavenumber", "relative"):
             use = coords
         else:
             raise ValueError("unknown kind %s" % kind)
-        ax0 = self.slabs._axis0()
+        return use, self.slabs._axis0()
+
+    APPLY_PLANES = 16
+
+    def _apply_device(self, func, kind):
+        """func(coords, values) evaluated ON THE DEVICE: the callback gets torch tensors (a batch of planes of the field
+        and broadcastable coordinate tensors), so callbacks written with arithmetic operators -- and the package's
+        own MeshFilters (filters.py) -- never move the field out of HBM.  Returns False, leaving the field untouched,
+        when the callback cannot work on device tensors (it calls NumPy functions): the host plane loop takes over."""
+        use, ax0 = self._coords_for(kind)
+        dev = self.value.device
+        tc = [torch.from_numpy(numpy.ascontiguousarray(c)).to(dev) for c in use]
+        n0 = int(self.value.shape[0])
+        step = max(1, min(n0, self.APPLY_PLANES))
+
+        def batch(i, values):
+            cs = [c[i:i + step] if d == ax0 else c for d, c in enumerate(tc)]
+            return func(cs, values)
+        if n0 == 0:
+            return True
+        try:     # dry run on a copy of the first batch
+            res = batch(0, self.value[0:step].clone())
+            if not isinstance(res, torch.Tensor) or tuple(res.shape) != tuple(self.value[0:step].shape):
+                return False
+        except Exception:    # noqa: BLE001  (numpy-only callbacks raise TypeError / RuntimeError on device tensors)
+            return False
+        for i in range(0, n0, step):
+            res = batch(i, self.value[i:i + step])
+            self.value[i:i + step] = res.to(self.value.dtype)
+        return True
+
+    def resample(self, out):
+        """the field on the mesh of `out` by Fourier-space resampling (pmesh `Field.resample`, base/mesh.py:317-327):
+        common modes are copied, the others are zero; real fields go through r2c / c2r.  Single GPU."""
+        pm, dst = self.pm, out.pm
+        if pm.comm.size > 1 or pm.cplx or dst.cplx:
+            raise NotImplementedError("Fourier-space resampling is implemented for one GPU and Hermitian-compressed meshes")
+        src_c = self if isinstance(self, BaseComplexField) else self.r2c()
+        dst_c = out if isinstance(out, BaseComplexField) else ComplexField(dst)
+        val = src_c.value if pm.typestr == dst.typestr else src_c.value.to(dst_c.value.dtype)
+        check(lib().nbk_resample_complex(_ptr(val), _ptr(dst_c.value), _CODE[dst.typestr], pm._nmesh_c, dst._nmesh_c, _stream()),
+              "nbk_resample_complex")
+        if isinstance(out, RealField):
+            dst_c.c2r(out=out)
+        out.attrs = dict(self.attrs)
+        return out
+
+    def _apply_host(self, func, kind):
+        use, ax0 = self._coords_for(kind)
         for i in range(self.value.shape[0]):
             plane = self.value[i].cpu().numpy()
             cs = [c[i:i + 1] if d == ax0 else c for d, c in enumerate(use)]
@@ -796,7 +859,13 @@ class RealField(Field):
         code = _CODE[pm.typestr]
         P = pm.comm.size
         Nx, Ny, Nz = [int(v) for v in pm.Nmesh]
-        if P == 1:
+        if pm.cplx:
+            half = torch.empty((Nx, Ny, Nz // 2 + 1), dtype=out.value.dtype, device=out.value.device)
+            with stage("r2c"):
+                check(lib().nbk_r2c(_ptr(self.value), _ptr(half), code, pm._nmesh_c, float(scale), _stream()), "nbk_r2c")
+                check(lib().nbk_hermitian_expand(_ptr(half), _ptr(out.value), code, pm._nmesh_c, _stream()),
+                      "nbk_hermitian_expand")
+        elif P == 1:
             with stage("r2c"):
                 check(lib().nbk_r2c(_ptr(self.value), _ptr(out.value), code, pm._nmesh_c, float(scale), _stream()), "nbk_r2c")
         else:
@@ -811,10 +880,21 @@ class RealField(Field):
                 from .._lib import lib as _L
                 with stage("fft_z"):
                     check(_L().nbk_fft_z_forward(_ptr(self.value), _ptr(work), code, pm.x_n * Ny, Nz, _stream()), "fft_z_forward")
-                hdl.barrier(channel=0)
-                with stage("fft_y_scatter"):
-                    check(_L().nbk_fft_lines_scatter(_ptr(work), ptrs, code, Ny, Nzc, pm.x_n, pm.x_start, P, 0, 1.0,
-                                                     _stream()), "fft_lines_scatter")
+                if _transpose_mode() == "push":
+                    # y pass into P contiguous send blocks, then one strided bulk copy per peer over NVLink
+                    send = torch.empty((P, pm.y_n, pm.x_n, Nzc), dtype=out.value.dtype, device=out.value.device)
+                    with stage("fft_y_pack"):
+                        check(_L().nbk_fft_lines_pack(_ptr(work), _ptr(send), code, Ny, Nzc, pm.x_n, P, 0, 1.0, _stream()),
+                              "fft_lines_pack")
+                    hdl.barrier(channel=0)
+                    with stage("fft_y_scatter"):
+                        check(_L().nbk_slab_push(_ptr(send), ptrs, code, pm.y_n, pm.x_n, Nzc, pm.x_start, P, pm.comm.rank,
+                                                 _stream()), "slab_push")
+                else:
+                    hdl.barrier(channel=0)
+                    with stage("fft_y_scatter"):
+                        check(_L().nbk_fft_lines_scatter(_ptr(work), ptrs, code, Ny, Nzc, pm.x_n, pm.x_start, P, 0, 1.0,
+                                                         _stream()), "fft_lines_scatter")
                 hdl.barrier(channel=1)
                 scale = float(scale) / (float(Nx) * Ny * Nz)
                 with stage("fft_x"):
@@ -844,7 +924,10 @@ class BaseComplexField(Field):
 
 
 class ComplexField(BaseComplexField):
-    compressed = True     # Hermitian-compressed last axis (fftpower.py:572)
+    @property
+    def compressed(self):
+        """Hermitian-compressed last axis (fftpower.py:572): False on complex-dtype meshes, which keep all N^3 modes"""
+        return not self.pm.cplx
 
     @staticmethod
     def _layout(pm):
@@ -859,8 +942,10 @@ class ComplexField(BaseComplexField):
         return self.pm.transposed
 
     def _slab(self):
+        """(layout bits, first owned index, count) as the Fourier-space kernels take them (NBK_LAYOUT_*)"""
         pm = self.pm
-        return (1, pm.y_start, pm.y_n) if pm.transposed else (0, 0, int(pm.Nmesh[0]))
+        full = 2 if pm.cplx else 0
+        return (1 | full, pm.y_start, pm.y_n) if pm.transposed else (full, 0, int(pm.Nmesh[0]))
 
     def c2r(self, out=None):
         """backward FFT, unnormalised.  The complex buffer is preserved."""
@@ -870,16 +955,35 @@ class ComplexField(BaseComplexField):
         code = _CODE[pm.typestr]
         P = pm.comm.size
         Nx, Ny, Nz = [int(v) for v in pm.Nmesh]
+        if pm.cplx:
+            # the field is the spectrum of a real array (this path never builds anything else): its stored half is
+            # all a c2r needs
+            half = torch.empty((Nx, Ny, Nz // 2 + 1), dtype=self.value.dtype, device=self.value.device)
+            check(lib().nbk_hermitian_compress(_ptr(self.value), _ptr(half), code, Nx * Ny, Nz, _stream()),
+                  "nbk_hermitian_compress")
+            check(lib().nbk_c2r(_ptr(half), _ptr(out.value), code, pm._nmesh_c, None, _stream()), "nbk_c2r")
+            out.attrs = dict(self.attrs)
+            return out
         st = pm._peer_stage() if P > 1 else None
         if st is not None:
             # inverse x pass scatters rows into the owners' staging buffers over NVLink (the input is only read);
             # inverse y pass + z c2r then run locally on the staging buffer
             view, ptrs, hdl = st
             Nzc = pm.Nzc
-            hdl.barrier(channel=0)
-            with stage("ifft_x_scatter"):
-                check(lib().nbk_fft_lines_scatter(_ptr(self.value), ptrs, code, Nx, Nzc, pm.y_n, pm.y_start, P, 1, 1.0,
-                                                  _stream()), "fft_lines_scatter(inverse)")
+            if _transpose_mode() == "push":
+                send = torch.empty((P, pm.x_n, pm.y_n, Nzc), dtype=self.value.dtype, device=self.value.device)
+                with stage("ifft_x_pack"):
+                    check(lib().nbk_fft_lines_pack(_ptr(self.value), _ptr(send), code, Nx, Nzc, pm.y_n, P, 1, 1.0, _stream()),
+                          "fft_lines_pack(inverse)")
+                hdl.barrier(channel=0)
+                with stage("ifft_x_scatter"):
+                    check(lib().nbk_slab_push(_ptr(send), ptrs, code, pm.x_n, pm.y_n, Nzc, pm.y_start, P, pm.comm.rank,
+                                              _stream()), "slab_push(inverse)")
+            else:
+                hdl.barrier(channel=0)
+                with stage("ifft_x_scatter"):
+                    check(lib().nbk_fft_lines_scatter(_ptr(self.value), ptrs, code, Nx, Nzc, pm.y_n, pm.y_start, P, 1, 1.0,
+                                                      _stream()), "fft_lines_scatter(inverse)")
             hdl.barrier(channel=1)
             with stage("ifft_zy"):
                 check(lib().nbk_fft_zy_backward(_ptr(view), _ptr(out.value), code, pm.x_n, Ny, Nz, _stream()), "fft_zy_backward")

@@ -1,28 +1,28 @@
 """
-LogNormalCatalog -- log-normal mock catalogue (API of nbodykit/source/catalog/lognormal.py:53-191,
-algorithm of nbodykit/mockmaker.py:7-359), generated ON THE DEVICE:
+LogNormalCatalog -- log-normal mock catalogue (API of nbodykit/source/catalog/lognormal.py:53-191), generated ON THE
+DEVICE by nbodykit_b200.mockmaker:
 
-  Gaussian delta(k) = white noise * sqrt(P(k)/V)            mockmaker.py:83-124
-  Zel'dovich displacement psi_i(k) = i k_i/k^2 delta(k)     :127-134   (3 c2r)
-  delta(x) = c2r(delta_k); 1+delta_LN = exp(b_L delta)/mean :213-243   (b_L = bias - 1)
-  N_cell ~ Poisson(nbar H^3 (1+delta_LN))                   :300-306
-  particles at cell node + uniform in-cell jitter, emitted in cell order  :312-354
-  pos += psi(cell) ; wrap                                   lognormal.py:172
+  Gaussian delta(k) = white noise * sqrt(P(k)/V), Zel'dovich psi_i(k) = i k_i/k^2 delta(k)     mockmaker.py:83-134
+  delta(x), psi(x) by four c2r (this package's CUDA FFT)
+  1 + delta_LN = exp(b_L delta)/mean, b_L = bias - 1                                            :213-243, 286
+  N_cell ~ Poisson(nbar H^3 (1 + delta_LN)); points at cell node + uniform in-cell offset, emitted in cell order  :300-354
+  Position += psi(cell) (periodic wrap), Velocity = f * psi                                     lognormal.py:160-187
 
-Columns `Position`, `Velocity` (= f * psi), `VelocityOffset`: float32 device tensors.  The c2r
-transforms are this package's CUDA FFT; random numbers come from torch's Philox generator, so the
-realisation is NOT bit-identical to the reference's (which depends on pmesh.generate_whitenoise and
-mpsort -- "parity unpinned" in SURVEY.md §2.1); its statistics are (tests/test_gpu_lognormal.py).
+Columns `Position`, `Velocity`, `VelocityOffset`: float32 device tensors.  P(k) is tabulated once on the host and
+interpolated on the device.  With several ranks every rank builds the same fields (same seed) and keeps the particles of
+its own x-slab of generator cells, which is what the reference's generator leaves on each rank: the catalogue does not
+depend on the number of ranks.  The realisation is NOT bit-identical to the reference's (pmesh.generate_whitenoise and
+mpsort are absent: "parity unpinned"); its statistics are tested (tests/test_gpu_lognormal.py).
 """
 import logging
 import numbers
 
 import numpy
-import torch
 
-from ... import CurrentMPIComm
+from ... import CurrentMPIComm, mockmaker
 from ...base.catalog import CatalogSource, column
-from ...pmesh.pm import ComplexField, ParticleMesh, RealField
+from ...comm import SelfComm
+from ...pmesh.pm import ParticleMesh
 
 
 class LogNormalCatalog(CatalogSource):
@@ -84,82 +84,25 @@ class LogNormalCatalog(CatalogSource):
 
     def _makesource(self):
         comm = self.comm
-        pm = ParticleMesh(BoxSize=self.attrs['BoxSize'], Nmesh=self.attrs['Nmesh'], dtype='f4', comm=comm)
-        if comm.size > 1:
-            raise NotImplementedError("multi-rank LogNormalCatalog generation: generate on one rank per slab "
-                                      "(see bench.py's per-rank generator) -- the Fourier-space fields here are "
-                                      "single-GPU")
-        dev = torch.device("cuda", torch.cuda.current_device())
-        N = [int(v) for v in pm.Nmesh]
-        L = pm.BoxSize
-        V = float(L.prod())
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(int(self.attrs['seed']))
-        # white noise with <|w_k|^2> = 1: r2c of unit normals carries 1/N^3 -> scale by sqrt(N^3)
-        white = RealField(pm)
-        white.value.normal_(generator=gen)
-        delta_k = white.r2c()
-        del white
-        delta_k *= float(numpy.sqrt(numpy.prod(N)))
-        if self.attrs['unitary_amplitude']:
-            a = delta_k.value.abs()
-            delta_k.value /= torch.where(a > 0, a, torch.ones_like(a))
-        if self.attrs['inverted_phase']:
-            delta_k *= -1.0
-        # amplitude sqrt(P(k)/V), evaluated on the host per x-plane with the user's callable
-        kx, ky, kz = [numpy.ravel(c).astype('f8') for c in pm.create_coords("complex")]
-        amp = torch.empty(delta_k.value.shape, dtype=torch.float32, device=dev)
-        kyz2 = ky[:, None] ** 2 + kz[None, :] ** 2
-        for i in range(N[0]):
-            k = numpy.sqrt(kx[i] ** 2 + kyz2)
-            k[k == 0] = 1.0
-            p = numpy.asarray(self.Plin(k.ravel())).reshape(k.shape)
-            amp[i] = torch.from_numpy(numpy.sqrt(p / V).astype('f4')).to(dev)
-        delta_k.value *= amp
-        del amp
-        delta_k.value[0, 0, 0] = 0
-        # Zel'dovich displacement per axis (nearest-grid-point read-out later)
-        kxt = torch.from_numpy(kx.astype('f4')).to(dev)[:, None, None]
-        kyt = torch.from_numpy(ky.astype('f4')).to(dev)[None, :, None]
-        kzt = torch.from_numpy(kz.astype('f4')).to(dev)[None, None, :]
-        k2 = kxt ** 2 + kyt ** 2 + kzt ** 2
-        k2[0, 0, 0] = 1.0
+        # the generator mesh lives on this GPU, whatever the size of the catalogue's communicator
+        pm = ParticleMesh(BoxSize=self.attrs['BoxSize'], Nmesh=self.attrs['Nmesh'], dtype='f4', comm=SelfComm())
+        delta_k, disp_k = mockmaker.gaussian_complex_fields(pm, self.Plin, int(self.attrs['seed']),
+                                                            unitary_amplitude=self.attrs['unitary_amplitude'],
+                                                            inverted_phase=self.attrs['inverted_phase'],
+                                                            compute_displacement=True)
         disp = []
-        for kd in (kxt, kyt, kzt):
-            d = ComplexField(pm, (1j * kd / k2) * delta_k.value)
-            d.value[0, 0, 0] = 0
-            disp.append(d.c2r().value)
-            del d
-        del k2
+        for d in range(3):
+            disp.append(disp_k[0].c2r())
+            del disp_k[0]
         delta = delta_k.c2r()
         del delta_k
-        # log-normal transform with the Lagrangian bias (mockmaker.py:213-243, 286)
-        bl = float(self.attrs['bias']) - 1.0
-        ln = torch.exp(delta.value.double() * bl)
-        ln /= ln.mean()
-        H3 = float((L / pm.Nmesh).prod())
-        lam = ln * (float(self.attrs['nbar']) * H3)
-        del ln, delta
-        counts = torch.poisson(lam, generator=gen).long().reshape(-1)
-        del lam
-        ntot = int(counts.sum().item())
-        cells = torch.repeat_interleave(torch.arange(counts.numel(), device=dev), counts)   # cell-sorted
-        del counts
-        iz = cells % N[2]
-        iy = (cells // N[2]) % N[1]
-        ix = cells // (N[2] * N[1])
-        H = [float(L[d] / N[d]) for d in range(3)]
-        pos = torch.empty((ntot, 3), dtype=torch.float32, device=dev)
-        dsp = torch.empty((ntot, 3), dtype=torch.float32, device=dev)
-        for d, idx in enumerate((ix, iy, iz)):
-            jitter = torch.rand(ntot, device=dev, dtype=torch.float64, generator=gen)
-            dd = disp[d].reshape(-1)[cells]
-            x = (idx.double() + jitter) * H[d] + dd.double()
-            pos[:, d] = torch.remainder(x, float(L[d])).float()
-            dsp[:, d] = dd
-        # float32 rounding can land exactly on L: fold it back
-        for d in range(3):
-            pos[:, d][pos[:, d] >= float(L[d])] = 0.0
+        # this rank's slab of generator cells (x planes), as the reference's domain decomposition leaves them
+        Nx = int(pm.Nmesh[0])
+        x0, x1 = (Nx * comm.rank) // comm.size, (Nx * (comm.rank + 1)) // comm.size
+        # the Poisson stream is seeded apart from the field's (mockmaker.py:300-306 draws a second seed)
+        pos, dsp = mockmaker.poisson_sample_to_points(delta, disp, pm, self.attrs['nbar'], bias=float(self.attrs['bias']) - 1.0,
+                                                      seed=(int(self.attrs['seed']) * 2654435761 + 12345) % (2 ** 63),
+                                                      x_range=(x0, x1) if comm.size > 1 else None)
         if comm.rank == 0:
-            self.logger.info("generated %d particles on a %s mesh" % (ntot, str(N)))
+            self.logger.info("generated %d particles on a %s mesh" % (int(pos.shape[0]), str([int(v) for v in pm.Nmesh])))
         return pos, dsp

@@ -329,13 +329,15 @@ class CatalogMesh(MeshSource):
             self.logger.info("painted %d objects to mesh" % N)
         return c
 
-    def compute_complex_deferred(self):
+    def compute_complex_deferred(self, Nmesh=None):
         """FFTPower fast path: (complex field WITHOUT the window compensation, name of the compensation the
         caller must still apply) when the compensation is the only action -- the power-binning kernel then
-        applies it on the fly.  Falls back to (compute('complex'), None)."""
+        applies it on the fly.  Falls back to (compute('complex', Nmesh=Nmesh), None) -- also whenever another
+        mesh size is asked for (the resampling of MeshSource.compute applies)."""
         own = self._get_compensation() if self.compensated else []
-        if list(MeshSource.actions.fget(self)) or not own:
-            return self.compute(mode='complex'), None
+        other_n = Nmesh is not None and any(numpy.ones(3, dtype='i8') * Nmesh != self.attrs['Nmesh'])
+        if list(MeshSource.actions.fget(self)) or not own or other_n:
+            return self.compute(mode='complex', Nmesh=Nmesh), None
         c = self.to_complex_field()
         c.attrs.update(self.attrs)
         return c, own[0][1].__name__

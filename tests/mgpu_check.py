@@ -35,7 +35,8 @@ def main():
     cases = [dict(resampler="cic", interlaced=False, dtype="f8", mode="1d", kw={}),
              dict(resampler="tsc", interlaced=True, dtype="f4", mode="2d", kw=dict(Nmu=4, poles=[0, 2])),
              dict(resampler="pcs", interlaced=False, dtype="f8", mode="1d", kw={})]
-    for c in cases:
+    for tmode, c in [(t, c) for t in ("push", "stores") for c in cases]:
+        os.environ["NBK_FFT_TRANSPOSE_MODE"] = tmode       # bulk peer copies | fine-grained remote stores
         cat = ArrayCatalog({"Position": torch.from_numpy(pos_all[mine]).cuda(), "Weight": torch.from_numpy(w_all[mine]).cuda()},
                            comm=comm, BoxSize=L)
         mesh = cat.to_mesh(Nmesh=N, resampler=c["resampler"], interlaced=c["interlaced"], compensated=True, dtype=c["dtype"])
@@ -63,9 +64,42 @@ def main():
                 ok &= np.allclose(np.nan_to_num(r.poles["power_2"].real), np.nan_to_num(r1.poles["power_2"].real),
                                   rtol=tol, atol=tol * np.nanmax(np.abs(r1.poles["power_0"])))
             bitexact = (not c["interlaced"]) and np.array_equal(full, real1)
-            print("case %s: %s (real field bit-identical to 1 GPU: %s)" % (c, "OK" if ok else "MISMATCH", bitexact), flush=True)
+            print("case %s [transpose=%s]: %s (real field bit-identical to 1 GPU: %s)" % (c, tmode, "OK" if ok else "MISMATCH", bitexact), flush=True)
             if not ok:
                 failures.append(c)
+    os.environ.pop("NBK_FFT_TRANSPOSE_MODE", None)
+    # ---- a dense catalogue on a 256^3 mesh: tiled paint on slabs (ghost tiles, ordered write-back), both orders
+    from nbodykit_b200.cosmology import NoWiggleEHPower
+    from nbodykit_b200.lab import LinearMesh, LogNormalCatalog
+    big = LogNormalCatalog(Plin=NoWiggleEHPower(), nbar=6e6 / 1000. ** 3, BoxSize=1000., Nmesh=128, bias=2.0, seed=5, comm=SelfComm())
+    pbig = big['Position'].compute()
+    for order in ("generator", "permuted"):
+        pp = pbig
+        if order == "permuted":
+            g = torch.Generator(device=pbig.device); g.manual_seed(9)
+            pp = pbig[torch.randperm(pbig.shape[0], device=pbig.device, generator=g)].contiguous()
+        lo, hi = rank * pp.shape[0] // world, (rank + 1) * pp.shape[0] // world
+        rd = FFTPower(ArrayCatalog({"Position": pp[lo:hi].contiguous()}, comm=comm, BoxSize=1000.), mode="1d", Nmesh=256)
+        if rank == 0:
+            r1 = FFTPower(ArrayCatalog({"Position": pp}, comm=SelfComm(), BoxSize=1000.), mode="1d", Nmesh=256)
+            ok = np.array_equal(rd.power["modes"], r1.power["modes"]) and np.allclose(
+                rd.power["power"].real, r1.power["power"].real, rtol=2e-8, atol=2e-8 * np.nanmax(np.abs(r1.power["power"])))
+            print("case 256^3 tiled slabs, %s order: %s" % (order, "OK" if ok else "MISMATCH"), flush=True)
+            if not ok:
+                failures.append("tiled-slabs-" + order)
+    # ---- generators: the shares of a P-rank LogNormalCatalog / LinearMesh are the slabs of the single-rank ones
+    lnc = LogNormalCatalog(Plin=NoWiggleEHPower(), nbar=2e-4, BoxSize=1000., Nmesh=64, bias=2.0, seed=5, comm=comm)
+    parts = comm.allgather(lnc['Position'].compute().cpu().numpy())
+    lin = LinearMesh(NoWiggleEHPower(), BoxSize=1000., Nmesh=64, seed=8, comm=comm)
+    plin = FFTPower(lin, mode="1d")
+    if rank == 0:
+        one = LogNormalCatalog(Plin=NoWiggleEHPower(), nbar=2e-4, BoxSize=1000., Nmesh=64, bias=2.0, seed=5, comm=SelfComm())
+        ok = np.array_equal(np.concatenate(parts), one['Position'].compute().cpu().numpy()) and lnc.csize == one.csize
+        p1 = FFTPower(LinearMesh(NoWiggleEHPower(), BoxSize=1000., Nmesh=64, seed=8, comm=SelfComm()), mode="1d")
+        ok &= np.allclose(plin.power["power"].real, p1.power["power"].real, rtol=1e-5, atol=0)
+        print("case generators (LogNormalCatalog shares, LinearMesh): %s" % ("OK" if ok else "MISMATCH"), flush=True)
+        if not ok:
+            failures.append("generators")
     # ---- FFTRecon (distributed paint + readout): the reconstructed mesh equals the single-GPU one
     from nbodykit_b200.lab import FFTRecon
     rng2 = np.random.RandomState(77)

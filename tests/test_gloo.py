@@ -145,5 +145,8 @@ def test_particle_mesh_slab_layout():
     np.testing.assert_allclose(k[1].ravel(), 2 * np.pi * np.array([-4, -3, -2, -1]), rtol=1e-6)
     with pytest.raises(ValueError):
         ParticleMesh(BoxSize=1., Nmesh=[30, 16, 8], dtype='f4', comm=Fake(0, 4))
+    # complex-dtype meshes keep all N^3 modes (single GPU; several GPUs -> dtype='f8')
+    cm = ParticleMesh(BoxSize=1., Nmesh=8, dtype='c16', comm=Fake(0, 1))
+    assert cm.cplx and cm.complex_shape == (8, 8, 8) and cm.real_shape == (8, 8, 8) and cm.typestr == 'f8'
     with pytest.raises(NotImplementedError):
-        ParticleMesh(BoxSize=1., Nmesh=8, dtype='c16', comm=Fake(0, 1))
+        ParticleMesh(BoxSize=1., Nmesh=8, dtype='c16', comm=Fake(0, 2))

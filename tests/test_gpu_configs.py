@@ -148,8 +148,9 @@ def test_c5_fkp_poles024_256(cuda):
     rng = np.random.RandomState(6)
     rpos = rng.uniform(size=(4000000, 3)) * box + off
     nbar = len(dpos) / box ** 3
-    d = ArrayCatalog({'Position': dpos}, comm=SelfComm())
-    r = ArrayCatalog({'Position': rpos}, comm=SelfComm())
+    comm = SelfComm()
+    d = ArrayCatalog({'Position': dpos}, comm=comm)
+    r = ArrayCatalog({'Position': rpos}, comm=comm)
     for c in (d, r):
         c['NZ'] = nbar * np.ones(c.size)
     fkp = FKPCatalog(d, r, P0=1e4)

@@ -132,9 +132,9 @@ def test_convolved_power_vs_oracle(cuda, resampler):
 
 
 def test_convolved_power_complex_mesh_odd_multipoles(cuda):
-    """dtype='c16' (the reference default): odd multipoles equal the sum over ALL modes of a full complex mesh
-    (oracle: fftn + project_to_basis(hermitian_symmetric=False)); even ones equal the Hermitian result; with an 'f8'
-    mesh the odd multipoles keep the reference's Hermitian fold (documented there as incorrect)"""
+    """dtype='c16' (the reference default): every multipole equals the sum over ALL modes of a full complex mesh
+    (oracle: fftn + project_to_basis(hermitian_symmetric=False)) in every bin; with an 'f8' mesh the odd multipoles
+    keep the reference's Hermitian fold (documented there as incorrect)"""
     from nbodykit_b200.lab import ConvolvedFFTPower
     fkp, d, r = _fkp()
     mesh = fkp.to_mesh(Nmesh=32)                       # default dtype, as in the reference
@@ -149,17 +149,16 @@ def test_convolved_power_complex_mesh_odd_multipoles(cuda):
     assert np.array_equal(res.poles['modes'], o['modes'])
     np.testing.assert_allclose(res.poles['k'], o['k'], rtol=1e-6, equal_nan=True)
     scale = np.nanmax(np.abs(o['power_0']))
-    # Every bin below the Nyquist shell.  The last bin holds modes with j_x or j_y = -N/2: on a full mesh their mirror
-    # partners carry the SAME label -N/2 (not +N/2), so Y_lm(khat) of the pair is not related by parity and the full
-    # sum cannot be folded from the compressed half; the two representations differ there (as the reference's own
-    # 'f8' and 'c16' results do).
+    # EVERY bin, including the Nyquist shell: modes with j_x or j_y = -N/2 have mirror partners that carry the SAME
+    # label -N/2 on a full mesh, so Y_lm(khat) of the pair is not related by parity; the mirror accumulator
+    # (nbk_ylm_mul_complex_acc2 -> nbk_power_bin2) reproduces exactly that
     for ell in (0, 1, 2, 3):
-        got, want = res.poles['power_%d' % ell][:-1], o['power_%d' % ell][:-1]
+        got, want = res.poles['power_%d' % ell], o['power_%d' % ell]
         np.testing.assert_allclose(np.nan_to_num(got.real), np.nan_to_num(want.real), rtol=1e-5, atol=2e-6 * scale)
         np.testing.assert_allclose(np.nan_to_num(got.imag), np.nan_to_num(want.imag), rtol=1e-5, atol=2e-6 * scale)
     # the odd multipoles of a survey-like geometry are imaginary and do not vanish
-    assert np.nanmax(np.abs(res.poles['power_1'].imag[:-1])) > 1e-3 * scale
-    assert np.nanmax(np.abs(res.poles['power_1'].real[:-1])) < 1e-5 * scale
+    assert np.nanmax(np.abs(res.poles['power_1'].imag)) > 1e-3 * scale
+    assert np.nanmax(np.abs(res.poles['power_1'].real[:-1])) < 1e-5 * scale    # (the Nyquist-shell bin is not purely imaginary)
     # Hermitian mesh: the reference's own (Hermitian) fold -> the restatement with hermitian_symmetric=True
     res8 = ConvolvedFFTPower(fkp.to_mesh(Nmesh=32, dtype='f8'), poles=[1], dk=0.02)
     o8 = co.convpower(*args[:-1], [1], dk=0.02)

@@ -93,10 +93,9 @@ def test_preview_and_attrs(cuda):
     np.testing.assert_allclose(real.cmean(), 1.0, rtol=1e-12)
     with pytest.raises(ValueError):
         mesh.compute(mode='nope')
-    with pytest.raises(NotImplementedError):
-        mesh.save("x")
-    with pytest.raises(NotImplementedError):
-        cat.to_mesh(Nmesh=16, dtype='c16')
+    # complex-dtype meshes keep all N^3 modes
+    cm = cat.to_mesh(Nmesh=16, dtype='c16')
+    assert not cm.compute(mode='complex').compressed and cm.compute(mode='complex').value.shape == (16, 16, 16)
 
 
 def test_dk0_unique_bins(cuda):
@@ -184,3 +183,148 @@ def test_fftcorr_unique_and_padding(cuda):
     np.testing.assert_allclose(p.coords['r'], p['r'], rtol=1e-6)
     r = FFTCorr(source, mode='1d', BoxSize=1024, Nmesh=32)
     assert r.attrs['N1'] != 0 and r.attrs['N2'] != 0
+
+
+def test_complex_dtype_mesh_full_spectrum(cuda):
+    """ParticleMesh(dtype='c16'): pmesh runs c2c transforms and keeps all N^3 modes, ComplexField.compressed is False
+    (fftpower.py:572; convpower/catalog.py:169-176).  r2c == numpy fftn / N^3, c2r brings the field back, and FFTPower
+    on such a mesh equals the reference's project_to_basis(hermitian_symmetric=False) over the full mesh."""
+    import torch
+    from nbodykit_b200.comm import SelfComm
+    from nbodykit_b200.lab import ArrayCatalog, FFTPower
+    from nbodykit_b200.pmesh.pm import ParticleMesh, RealField
+    from oracle import pmesh_oracle as po
+    N, L = [16, 32, 8], [100., 200., 50.]
+    pm = ParticleMesh(BoxSize=L, Nmesh=N, dtype='c16', comm=SelfComm())
+    rng = np.random.RandomState(3)
+    x = rng.normal(size=N)
+    r = RealField(pm)
+    r[...] = x
+    c = r.r2c()
+    assert not c.compressed and c.value.shape == tuple(N)
+    np.testing.assert_allclose(c.value.cpu().numpy(), np.fft.fftn(x) / x.size, rtol=0, atol=1e-13)
+    np.testing.assert_allclose(c.c2r().value.cpu().numpy(), x, rtol=0, atol=1e-12)
+    # the power spectrum of a catalogue painted on a complex mesh: all modes, weight 1 each
+    pos = rng.uniform(size=(20000, 3)) * np.array(L)
+    cat = ArrayCatalog({'Position': pos}, comm=SelfComm(), BoxSize=L)
+    res = FFTPower(cat.to_mesh(Nmesh=N, dtype='c16', compensated=True), mode='2d', Nmu=4, poles=[0, 1, 2], dk=0.05)
+    real, attrs = po.paint_field(pos, N, L, "cic")
+    cf = np.fft.fftn(real) / real.size
+    w = []
+    for d in range(3):
+        j = po.freq_index(N[d]).astype('f4') * np.float32(2 * np.pi / N[d])
+        sh = [1, 1, 1]; sh[d] = N[d]
+        w.append(j.reshape(sh))
+    cf = po.compensate("CompensateCICShotnoise", w, cf)
+    p3d = cf * np.conj(cf)
+    p3d[0, 0, 0] = 0
+    p3d = p3d * np.prod(L)
+    k3 = []
+    for d in range(3):
+        j = po.freq_index(N[d]).astype('f4') * np.float32(2 * np.pi / L[d])
+        sh = [1, 1, 1]; sh[d] = N[d]
+        k3.append(j.reshape(sh))
+    kedges = np.arange(0., np.pi * min(N) / max(L) + 0.025, 0.05)
+    (kk, mu, P, modes), (pk, poles, pmodes) = po.project_to_basis(p3d, k3, [kedges, np.linspace(-1, 1, 5)], poles=[0, 1, 2],
+                                                                 hermitian_symmetric=False)
+    assert np.array_equal(res.power['modes'], modes)
+    assert res.power['modes'].sum() <= np.prod(N)
+    scale = np.nanmax(np.abs(P))
+    np.testing.assert_allclose(np.nan_to_num(res.power['power'].real), np.nan_to_num(P.real), rtol=1e-5, atol=1e-8 * scale)
+    for i, ell in enumerate([0, 1, 2]):
+        np.testing.assert_allclose(np.nan_to_num(res.poles['power_%d' % ell]), np.nan_to_num(poles[i]), rtol=1e-5, atol=1e-8 * scale)
+
+
+def test_device_callbacks_filters_and_fallback(cuda):
+    """Field.apply evaluates callbacks on DEVICE tensors (the package's TopHat / Gaussian filters, operator-only user
+    callbacks); a callback that calls NumPy functions falls back to the host plane loop -- same result either way"""
+    import torch
+    from nbodykit_b200.filters import Gaussian, TopHat
+    from nbodykit_b200.lab import ArrayMesh
+    from nbodykit_b200.pmesh.pm import Field
+    rng = np.random.RandomState(5)
+    N, L = [16, 8, 32], [50., 20., 100.]
+    arr = rng.standard_normal(N)
+    mesh = ArrayMesh(arr, BoxSize=L)
+    k = po.k_coords(N, L, 'f4')
+    kk = np.sqrt(k[0] ** 2 + k[1] ** 2 + k[2] ** 2)
+    c = po.r2c(arr)
+    calls = {"device": 0, "host": 0}
+    dev0, host0 = Field._apply_device, Field._apply_host
+
+    def spy_dev(self, func, kind):
+        ok = dev0(self, func, kind)
+        calls["device"] += int(ok)
+        return ok
+
+    def spy_host(self, func, kind):
+        calls["host"] += 1
+        return host0(self, func, kind)
+    Field._apply_device, Field._apply_host = spy_dev, spy_host
+    try:
+        out = mesh.apply(Gaussian(4.0)).compute(mode='complex').numpy()
+        np.testing.assert_allclose(out, c * np.exp(-0.5 * kk ** 2 * 16.0), rtol=2e-6, atol=1e-12)
+        assert calls == {"device": 1, "host": 0}
+        out = mesh.apply(TopHat(6.0)).compute(mode='complex').numpy()
+        kr = kk * 6.0
+        with np.errstate(invalid='ignore', divide='ignore'):
+            w = 3 * (np.sin(kr) / kr ** 3 - np.cos(kr) / kr ** 2)
+        w[kk == 0] = 1.0
+        np.testing.assert_allclose(out, c * w, rtol=1e-4, atol=1e-9)       # float32 coordinates through kr^-3
+        assert calls == {"device": 2, "host": 0}
+
+        def numpy_only(kv, v):            # NumPy ufuncs reject device tensors -> host loop
+            return v * np.exp(-sum(ki ** 2 for ki in kv))
+        out = mesh.apply(numpy_only, kind='wavenumber', mode='complex').compute(mode='complex').numpy()
+        np.testing.assert_allclose(out, c * np.exp(-kk ** 2), rtol=2e-6, atol=1e-12)
+        assert calls["host"] == 1
+
+        def masking(x, v):                # in-place, index-kind, real space: runs on the device
+            v[(x[0] % 2 == 0) & (x[2] < 4)] = 0
+            return v
+        out = mesh.apply(masking, kind='index', mode='real').compute(mode='real').numpy()
+        want = arr.copy()
+        want[::2, :, :4] = 0
+        np.testing.assert_allclose(out, want, rtol=1e-14)
+        assert calls["device"] == 3
+    finally:
+        Field._apply_device, Field._apply_host = dev0, host0
+
+
+def test_compute_at_another_nmesh_resamples_in_fourier_space(cuda):
+    """MeshSource.compute(Nmesh=...) (base/mesh.py:317-327): a band-limited field is reproduced exactly on a finer and
+    on a coarser mesh; the mean is preserved"""
+    from nbodykit_b200.lab import ArrayMesh
+    N, L = 32, 64.
+    x = np.arange(N) * (L / N)
+    X, Y, Z = np.meshgrid(x, x, x, indexing='ij')
+
+    def f(X, Y, Z):
+        q = 2 * np.pi / L
+        return 1.5 + np.cos(2 * q * X) * np.sin(3 * q * Y + 0.3) + 0.25 * np.cos(q * (X - 2 * Y + 4 * Z))
+    mesh = ArrayMesh(f(X, Y, Z), BoxSize=L)
+    for M in (64, 16):                     # 16: Nyquist index 8 > every frequency in f
+        xm = np.arange(M) * (L / M)
+        Xm, Ym, Zm = np.meshgrid(xm, xm, xm, indexing='ij')
+        got = mesh.compute(mode='real', Nmesh=M)
+        assert got.value.shape == (M, M, M) and np.array_equal(got.attrs['Nmesh'], [N, N, N])
+        np.testing.assert_allclose(got.numpy(), f(Xm, Ym, Zm), rtol=0, atol=1e-12)
+        c = mesh.compute(mode='complex', Nmesh=M)
+        assert c.value.shape == (M, M, M // 2 + 1)
+        np.testing.assert_allclose(c.value[0, 0, 0].item().real, 1.5, rtol=1e-13)
+
+
+def test_mesh_save_and_filemesh_roundtrip(cuda, tmp_path):
+    """MeshSource.save + FileMesh (the roles of base/mesh.py:367-412 and source/mesh/bigfile.py)"""
+    from nbodykit_b200.lab import ArrayMesh, FFTPower, FileMesh
+    rng = np.random.RandomState(6)
+    N, L = [16, 8, 8], [10., 5., 5.]
+    arr = rng.standard_normal(N) + 1.0
+    mesh = ArrayMesh(arr, BoxSize=L, note="hello")
+    for mode in ('real', 'complex'):
+        path = mesh.save(str(tmp_path / mode), dataset='Field', mode=mode)
+        back = FileMesh(str(tmp_path / mode), 'Field')
+        assert np.array_equal(back.attrs['Nmesh'], N) and back.attrs['note'] == "hello"
+        np.testing.assert_allclose(back.compute(mode='real').numpy(), arr, rtol=0, atol=1e-13)
+        a, b = FFTPower(mesh, mode='1d'), FFTPower(back, mode='1d')
+        np.testing.assert_allclose(a.power['power'].real, b.power['power'].real, rtol=1e-10)
