@@ -114,6 +114,23 @@ class ClockSampler(object):
         return out
 
 
+def bind_to_gpu_numa(local):
+    """pin this process (and so the pinned host buffers it first-touches) to the CPU cores next to its GPU: with one
+    rank per GPU the H2D copies of the e2e leg then never cross the socket interconnect"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1 and 64 * i + b < ncpu]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
+
+
 def generate(cfg, seed=42):
     """the config's particles on the current GPU (device float32 positions in the generator's cell order)"""
     from nbodykit_b200.comm import SelfComm
@@ -195,6 +212,8 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    if world > 1:
+        bind_to_gpu_numa(local)
     # keep stdout clean for the ONE JSON line: libraries (e.g. the NCCL version banner) write to fd 1 directly
     real_stdout = os.dup(1)
     os.dup2(2, 1)

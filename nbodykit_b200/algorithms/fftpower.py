@@ -321,9 +321,11 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
     coord_unit = _lib.darr(pm.BoxSize / pm.Nmesh) if is_real else None
     comm = pm.comm
     xedges, muedges = edges
+    # edges**2 is formed in the dtype the edges come in (fftpower.py:583 `x2edges = xedges**2`: float32 for the
+    # dk = 0 edges, which are built from float32 coordinates) and only then widened -- the widening is exact
+    x2edges = (numpy.asarray(xedges) ** 2).astype('f8')
     xedges = numpy.asarray(xedges, dtype='f8')
     muedges = numpy.asarray(muedges, dtype='f8')
-    x2edges = xedges ** 2
     Nx = len(xedges) - 1
     Nmu = len(muedges) - 1
     poles = list(poles)
@@ -430,18 +432,33 @@ def _find_unique_edges(pm, xmax, real=False):
         j[j >= (N[d] + 1) // 2] -= N[d]
         full.append(j.astype(ct) * ct(x0[d]))
     binning = (x0.min() * 0.05) ** 2
-    xy = (0 + full[0][:, None] ** 2) + full[1][None, :] ** 2      # same association order as sum(xi**2)
-    best = {}
-    # process plane by plane in x (the reference's ravel order: x, y, z) keeping the first occurrence
+    # Device pass over the planes in the reference's ravel order (x, y, z), keeping the first occurrence of every
+    # quantised value: per plane a sort of ~N^2/2 keys, merged into the running set by a stable sort (earlier planes
+    # first).  Planes whose x coordinate squares to a value already seen add nothing and are skipped.  The set has
+    # ~3 (N/2)^2 members at most, so the whole pass takes well under a second at 1024^3.
+    # (coordinate bookkeeping, not field data: it runs wherever torch runs, so the host-logic tests can pin it)
+    dev = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+    fx_t = [torch.from_numpy(numpy.ascontiguousarray(f)).to(dev) for f in full]
+    best_k = torch.empty(0, dtype=torch.int64, device=dev)
+    best_v = torch.empty(0, dtype=torch.float32, device=dev)
+    seen = set()
     for ix in range(len(full[0])):
-        fx2 = (xy[ix][:, None] + full[2][None, :] ** 2).ravel()
-        ix2 = numpy.int64(fx2 / binning + 0.5)
-        u, ind = numpy.unique(ix2, return_index=True)
-        for key, val in zip(u.tolist(), fx2[ind].tolist()):
-            if key not in best:
-                best[key] = val
-    keys = sorted(best)
-    fx = numpy.array([best[k] for k in keys], dtype=xy.dtype) ** 0.5
+        x2 = float(full[0][ix] * full[0][ix])
+        if x2 in seen:
+            continue
+        seen.add(x2)
+        # (0 + x^2 + y^2) + z^2 in float32, as the reference's sum(xi ** 2) associates it
+        fx2 = ((0 + fx_t[0][ix] ** 2) + fx_t[1][:, None] ** 2 + fx_t[2][None, :] ** 2).reshape(-1)
+        key = (fx2.double() / binning + 0.5).to(torch.int64)
+        allk = torch.cat([best_k, key])
+        allv = torch.cat([best_v, fx2])
+        order = torch.sort(allk, stable=True).indices
+        sk = allk[order]
+        first = torch.ones_like(sk, dtype=torch.bool)
+        first[1:] = sk[1:] != sk[:-1]
+        best_k = sk[first]
+        best_v = allv[order][first]
+    fx = best_v.cpu().numpy() ** 0.5
     fx = fx[fx < xmax]
     # second pass of the reference (re-bin after allgather with bin size minx0*1e-5)
     ix = numpy.int64(fx / (x0.min() * 1e-5) + 0.5)

@@ -14,6 +14,7 @@
 #include <tuple>
 #include <vector>
 #include <math.h>
+#include <stdlib.h>
 
 #define NBK_MAX_ELL 8
 
@@ -308,6 +309,7 @@ struct BinParams {
     int ells[NBK_MAX_ELL];
     int hermitian, is_p3d, clear_zero, has_c2;
     int anti;         // the statistic obeys y(-k) = -conj y(k) (odd FKP multipoles): the fold of the mirror half flips
+    int stage_edges; // the k edges fit in shared memory
     const void *c3;  // optional: the field that stands for c2 at the UNSTORED mirror mode -k (see nbk_power_bin2)
     int estride;     // 2: complex input (re, im interleaved)   1: real input (a RealField statistic, FFTCorr)
     double volume;
@@ -360,13 +362,17 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
     // stored axis, z); null when no compensation is fused
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // shared layout: k2edges[Nx+1] | muedges[Nmu+1] | (if SMEM_ACC) xsum[nb] musum[nb] ysum[NELL][nb][2] nsum[nb](u32)
-    double *s_k2 = reinterpret_cast<double *>(smem_raw);
-    double *s_mu = s_k2 + (P.Nx + 1);
+    // the k edges are staged in shared memory when they fit; with very many edges (dk = 0: one bin per distinct |k|,
+    // ~N^2 of them) they stay in global memory (L2-resident) and the accumulators are global too
+    const bool stage = P.stage_edges != 0;
+    double *s_k2s = reinterpret_cast<double *>(smem_raw);
+    double *s_mu = s_k2s + (stage ? P.Nx + 1 : 0);
+    const double *s_k2 = stage ? s_k2s : k2edges;
     double *s_x = s_mu + (P.Nmu + 1);
     double *s_m = s_x + (SMEM_ACC ? P.nb : 0);
     double *s_y = s_m + (SMEM_ACC ? P.nb : 0);
     unsigned *s_n = reinterpret_cast<unsigned *>(s_y + (SMEM_ACC ? (size_t)NELL * P.nb * 2 : 0));
-    for (int i = threadIdx.x; i <= P.Nx; i += blockDim.x) s_k2[i] = k2edges[i];
+    if (stage) for (int i = threadIdx.x; i <= P.Nx; i += blockDim.x) s_k2s[i] = k2edges[i];
     for (int i = threadIdx.x; i <= P.Nmu; i += blockDim.x) s_mu[i] = muedges[i];
     if (SMEM_ACC) {
         int nd = P.nb * (2 + 2 * NELL);
@@ -651,8 +657,12 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
     size_t edge_bytes = sizeof(double) * (P.Nx + 1 + P.Nmu + 1);
     size_t acc_bytes = (size_t)P.nb * (sizeof(double) * (2 + 2 * NELL) + sizeof(unsigned));
     bool smem_acc = edge_bytes + acc_bytes <= 200 * 1024;
+    const bool stage = edge_bytes <= 200 * 1024 && getenv("NBK_BIN_EDGES_GLOBAL") == nullptr;   // (env: force the global path)
+    if (!stage) edge_bytes = sizeof(double) * (P.Nmu + 1);      // k edges read from global memory
     size_t smem = edge_bytes + (smem_acc ? acc_bytes : 0);
-    NBK_CHECK_ARG(smem <= 227 * 1024, "power_bin: too many bin edges for shared memory");
+    NBK_CHECK_ARG(smem <= 227 * 1024, "power_bin: too many mu edges for shared memory");
+    BinParams Pk = P;
+    Pk.stage_edges = stage ? 1 : 0;
     int64_t rows = (int64_t)P.g.count * P.g.D1;
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 8) per_sm = 8;
@@ -670,7 +680,7 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
         NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_power_bin<T, NELL, ACC, SYMV>, 256, smem));    \
         if (occ < 1) occ = 1;                                                                                        \
         if ((int64_t)grid > (int64_t)NBK_SM_COUNT * occ) grid = NBK_SM_COUNT * occ;                                   \
-        k_power_bin<T, NELL, ACC, SYMV><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, P, d_k2, d_mu,          \
+        k_power_bin<T, NELL, ACC, SYMV><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, Pk, d_k2, d_mu,         \
                                                                 (unsigned long long *)nsum, xsum, musum, ysum, kmin, \
                                                                 inv_dk, uniform, ct0, ct1, ctz);                      \
     } while (0)

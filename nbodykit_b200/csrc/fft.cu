@@ -423,6 +423,135 @@ k_fft_lines_rg(const typename C2<T>::type *src, typename C2<T>::type *dst, PeerP
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-I/O line pass with the NEXT tile's first-stage loads in flight during the last stage of the current one
+// (ITER first-stage butterflies per thread, Q1 * B == ITER * NT).  With one 512-thread CTA per SM (lines of 1024
+// complex doubles) nothing else hides the global-load latency: the loads of tile i+1 are issued before the last stage
+// of tile i reads shared memory and streams its outputs out, so the memory system stays busy through the butterflies.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int B, bool PEER, int NT, int ITER>
+__global__ void __launch_bounds__(NT, 512 / NT)
+k_fft_lines_rgp(const typename C2<T>::type *src, typename C2<T>::type *dst, PeerPtrs<typename C2<T>::type> peers,
+                const typename C2<T>::type *__restrict__ tw, int N, int log2n, int64_t line_stride, int64_t n_inner,
+                int64_t tiles_inner, int64_t n_tiles, int64_t outer_stride, int n_per, int64_t d_total,
+                int64_t outer_start, int inverse, T scale) {
+    typedef typename C2<T>::type C;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C *sm = reinterpret_cast<C *>(smem_raw);
+    constexpr int pitch = B + 1;
+    tw = stage_twiddles<C>(sm + (size_t)N * pitch, tw, N);
+    const int n8 = log2n / 3, rrem = log2n - 3 * n8;
+    const int Q1 = N >> 3;
+    const T sgn = inverse ? (T)-1 : (T)1;
+    C pre[ITER][8];
+    auto issue_loads = [&](int64_t tile) {
+        const int64_t outer = tile / tiles_inner;
+        const int64_t inner0 = (tile - outer * tiles_inner) * B;
+        const C *ibase = src + outer * outer_stride + inner0;
+        const int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+#pragma unroll
+        for (int it = 0; it < ITER; it++) {
+            const int w = (int)threadIdx.x + it * NT;
+            const int b = w % B, q = w / B;
+            if (b < bvalid) {
+                const C *g = ibase + (int64_t)q * line_stride + b;
+#pragma unroll
+                for (int j = 0; j < 8; j++) pre[it][j] = g[(int64_t)j * Q1 * line_stride];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) pre[it][j] = C{0, 0};
+            }
+        }
+    };
+    int64_t tile = blockIdx.x;
+    if (tile < n_tiles) issue_loads(tile);
+    for (; tile < n_tiles; tile += gridDim.x) {
+        const int64_t outer = tile / tiles_inner;
+        const int64_t inner0 = (tile - outer * tiles_inner) * B;
+        const int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+        // ---- first stage: registers -> shared
+#pragma unroll
+        for (int it = 0; it < ITER; it++) {
+            const int w = (int)threadIdx.x + it * NT;
+            const int b = w % B, q = w / B;
+            C a[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { a[j] = pre[it][j]; a[j].y *= sgn; }
+            radix8(a);
+            C *o = sm + q * pitch + b;
+            o[0] = a[0];
+#pragma unroll
+            for (int m = 1; m < 8; m++) o[m * Q1 * pitch] = cmul(a[m], tw[m * q]);
+        }
+        __syncthreads();
+        // ---- middle stages, in place in shared memory
+        {
+            const int last8 = rrem ? n8 : n8 - 1;
+            int Ns = Q1, lq = log2n - 3;
+            for (int s = 1; s < last8; s++) {
+                const int Q = Ns >> 3;
+                lq -= 3;
+                const int tws = N / Ns;
+                for (int w = threadIdx.x; w < Q1 * B; w += NT) {
+                    int b = w % B, t = w / B;
+                    int blk = t >> lq, q = t & (Q - 1);
+                    C *p = sm + (blk * Ns + q) * pitch + b;
+                    C a[8];
+#pragma unroll
+                    for (int j = 0; j < 8; j++) a[j] = p[j * Q * pitch];
+                    radix8(a);
+                    int ti = q * tws;
+                    p[0] = a[0];
+#pragma unroll
+                    for (int m = 1; m < 8; m++) p[m * Q * pitch] = cmul(a[m], tw[m * ti]);
+                }
+                __syncthreads();
+                Ns = Q;
+            }
+        }
+        // ---- the next tile's inputs start travelling now
+        if (tile + gridDim.x < n_tiles) issue_loads(tile + gridDim.x);
+        // ---- last stage: shared -> registers -> global (frequency rows)
+        const int R = rrem == 0 ? 8 : (rrem == 2 ? 4 : 2);
+        const int NR = N / R;
+        const int ndig = rrem == 0 ? n8 - 1 : n8;
+        for (int w = threadIdx.x; w < NR * B; w += NT) {
+            int b = w % B, t = w / B;
+            const C *p = sm + (t * R) * pitch + b;
+            C a[8];
+            if (R == 8) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = p[j * pitch];
+                radix8(a);
+            } else if (R == 4) {
+                a[0] = p[0]; a[1] = p[pitch]; a[2] = p[2 * pitch]; a[3] = p[3 * pitch];
+                dft4(a[0], a[1], a[2], a[3]);
+            } else {
+                C x0 = p[0], x1 = p[pitch];
+                a[0] = cadd(x0, x1);
+                a[1] = csub(x0, x1);
+            }
+            if (b < bvalid) {
+                int k0 = rev8(t, ndig);
+#pragma unroll
+                for (int m = 0; m < 8; m++) {
+                    if (m < R) {
+                        int k = k0 + m * NR;
+                        C v = C{a[m].x * scale, a[m].y * sgn * scale};
+                        if (PEER) {
+                            int pr = k / n_per, kl = k - pr * n_per;
+                            peers.p[pr][((int64_t)kl * d_total + outer_start + outer) * n_inner + inner0 + b] = v;
+                        } else {
+                            dst[outer * outer_stride + inner0 + (int64_t)k * line_stride + b] = v;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();      // the next tile's first stage overwrites the buffer
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // z pass forward: real rows [rows][Nz] -> complex rows [rows][Nz/2+1]
 // packed trick: z[n] = x[2n] + i x[2n+1], Z = FFT_M(z), M = Nz/2,
 //   X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k]) ],  k = 0..M  (Z[M] := Z[0])
@@ -771,6 +900,34 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
     for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
     const int n_per = peer_host ? N / P : N;
     const int64_t d_total = d_total_override ? d_total_override : (peer_host ? n_outer * P : 0);
+    static int prefetch = -1;
+    if (prefetch < 0) {
+        const char *e = getenv("NBK_FFT_PREFETCH");
+        prefetch = (e && e[0] == '0') ? 0 : 1;
+    }
+    const int first_per_thread = (int)(((int64_t)(N >> 3) * B) / nthreads);
+    const bool exact = ((int64_t)(N >> 3) * B) % nthreads == 0;
+#define LAUNCH_RGP(BB, NTT, IT)                                                                                       \
+        if (peer_host) {                                                                                           \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rgp<T, BB, true, NTT, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_lines_rgp<T, BB, true, NTT, IT><<<(int)g, NTT, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
+                ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
+        } else {                                                                                                   \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_rgp<T, BB, false, NTT, IT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_lines_rgp<T, BB, false, NTT, IT><<<(int)g, NTT, smem, s>>>((const C *)src, (C *)dst, peers, (const C *)tw, N, \
+                ilog2(N), line_stride, n_inner, tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale); \
+        }
+    // the common shapes: two first-stage butterflies per thread (512^3: B=8/16, 256 threads; 1024^3: B=8, 512 threads)
+    if (prefetch && exact && first_per_thread == 2) {
+        bool done = true;
+        if (nthreads == 512 && B == 8) { LAUNCH_RGP(8, 512, 2) }
+        else if (nthreads == 512 && B == 16) { LAUNCH_RGP(16, 512, 2) }
+        else if (nthreads == 256 && B == 8) { LAUNCH_RGP(8, 256, 2) }
+        else if (nthreads == 256 && B == 16) { LAUNCH_RGP(16, 256, 2) }
+        else done = false;
+        if (done) { NBK_LAUNCHED(); return NBK_OK; }
+    }
+#undef LAUNCH_RGP
 #define LAUNCH_RG(BB, NTT)                                                                                            \
     case BB:                                                                                                       \
         if (peer_host) {                                                                                           \
@@ -951,10 +1108,14 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
         if (per_sm > 4) per_sm = 4;
         int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
 #define LAUNCH_ZRG(BB)                                                                                            \
-    case BB:                                                                                                      \
+    case BB: {                                                                                                    \
         NBK_CUDA(cudaFuncSetAttribute(k_fft_z_r2c_rg<T, BB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int occ = 1;   /* persistent tile loop: exactly one wave of resident CTAs (registers, not shared memory, limit it) */ \
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_fft_z_r2c_rg<T, BB>, 256, smem));           \
+        if (occ < 1) occ = 1;                                                                                     \
+        if (g > (int64_t)NBK_SM_COUNT * occ) g = (int64_t)NBK_SM_COUNT * occ;                                      \
         k_fft_z_r2c_rg<T, BB><<<(int)g, 256, smem, s>>>((const T *)in, (C *)out, (const C *)twN, Nz, ilog2(M), rows, (T)scale); \
-        break;
+        break; }
         switch (B) {
             LAUNCH_ZRG(1) LAUNCH_ZRG(2) LAUNCH_ZRG(4) LAUNCH_ZRG(8) LAUNCH_ZRG(16)
             default: nbk_set_error("fft z pass: internal tile width %d", B); return NBK_ERR_ARG;

@@ -376,6 +376,7 @@ __device__ __forceinline__ int make_record(const PT *x, const TileGeom &tg, unsi
 struct FastTile {
     float sc[3];    // float32 scale N/L
     float lim[3];   // accept when |frac(g) - 0.5| < lim  (frac at least eps away from both cell boundaries)
+    int pow2;       // N/L is a power of two on every axis: x * scale is exact in float32 (see make_record_pow2)
 };
 
 static FastTile make_fast_tile(const TileGeom &tg) {      // host side: passed to the kernels by value
@@ -385,7 +386,44 @@ static FastTile make_fast_tile(const TileGeom &tg) {      // host side: passed t
         // |g32 - g_exact| <= 2 float32 roundings of a value below n+2 -> 3e-7 (n+2) + 1e-6 is a safe margin
         f.lim[d] = 0.5f - (3e-7f * (float)(tg.gm.n[d] + 2) + 1e-6f);
     }
+    f.pow2 = 1;
+    for (int d = 0; d < 3; d++) {
+        int e;
+        if (frexp(tg.gm.scale[d], &e) != 0.5 || e < -60 || e > 60) f.pow2 = 0;
+    }
     return f;
+}
+
+// float32 positions on a mesh whose N/L is a power of two (every benchmark box: L = 2 N): g = x * scale is EXACT in
+// float32, so the leftmost cell and the 28-bit truncated fraction follow from float32 / integer arithmetic alone and
+// are bit-identical to the f8 path (same real number, same truncation): ~8 instructions per axis instead of ~25.
+// frac(g + 1/2) (TSC, NNB) is formed in fixed point: + 2^27 with the carry moving to the cell.
+template <int SUP>
+__device__ __forceinline__ int make_record_pow2(const float *x, const TileGeom &tg, const FastTile &ft, unsigned *rec, bool &ok) {
+    unsigned u[3];
+    int c[3];
+    ok = true;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const float g = x[d] * ft.sc[d];                       // exact
+        ok = ok && (fabsf(g) < 4194304.0f);                    // false for NaN / inf as well; far outside: slow path
+        const float f = floorf(g);
+        unsigned u28 = (unsigned)((g - f) * 268435456.0f);     // (g - f) exact; cvt truncates: floor(frac * 2^28)
+        int ci = (int)f;
+        if (WinOff<SUP>::A != 0.f) {
+            u28 += 1u << 27;
+            if (u28 >= (1u << 28)) { u28 -= 1u << 28; ci += 1; }
+        }
+        int cc = ci + WinOff<SUP>::B;
+        if (cc < 0) cc += tg.gm.n[d];
+        else if (cc >= tg.gm.n[d]) cc -= tg.gm.n[d];
+        ok = ok && ((unsigned)cc < (unsigned)tg.gm.n[d]);
+        c[d] = cc;
+        u[d] = u28 << 4;
+    }
+    if (!ok) return -1;
+    pack_record(u, c, tg, rec);
+    return tile_from_cells(c, tg);
 }
 
 // Tile id of a particle.  float32 in-box positions take a float32 fast path: unless the fraction of
@@ -440,23 +478,35 @@ __device__ __forceinline__ unsigned smem_claim(unsigned *hist, int key, bool act
 }
 
 // Claim slots for the (up to) four particles of a thread's quad (k[u] = window-relative tile, -1 = none).
-// Coherent input: when every lane's quad lies in one tile, the quad is claimed as a unit (then usually the whole warp
-// as one ATOMS); otherwise particle by particle.  All 32 lanes must call.
+// Lanes run in array order, so for a spatially coherent catalogue the lanes whose whole quad lies in one tile form
+// contiguous RUNS of equal keys: run heads come from one shuffle + ballot, the run's leader claims 4 * length slots
+// with one native ATOMS and the members take consecutive groups of four (no MATCH.ANY).  The particles of quads that
+// straddle tiles (and everything of a scattered catalogue) claim one slot each.  All 32 lanes must call.
 __device__ __forceinline__ void quad_claim(unsigned *hist, const int (&k)[4], unsigned (&slot)[4]) {
+    const unsigned lane = threadIdx.x & 31;
     const bool uni = (k[0] == k[1]) && (k[1] == k[2]) && (k[2] == k[3]) && (k[0] >= 0);
-    if (__all_sync(0xffffffffu, uni)) {
-        const int lane = threadIdx.x & 31;
-        unsigned mask = __match_any_sync(0xffffffffu, k[0]);
-        int leader = __ffs(mask) - 1;
+    const unsigned unis = __ballot_sync(0xffffffffu, uni);
+    if (unis) {
+        const int key = uni ? k[0] : -2 - (int)lane;                   // non-uniform lanes never join a run
+        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const unsigned heads = __ballot_sync(0xffffffffu, lane == 0 || prev != key);
+        const unsigned below = heads & ((2u << lane) - 1u);            // heads at or below me (lane 31: all)
+        const int start = 31 - __clz(lane == 31 ? heads : below);
+        const unsigned above = lane == 31 ? 0u : (heads & ~((2u << lane) - 1u));
+        const int end = above ? (__ffs(above) - 1) : 32;
         unsigned base = 0;
-        if (lane == leader) base = atomicAdd(&hist[k[0]], 4u * (unsigned)__popc(mask));
-        base = __shfl_sync(mask, base, leader) + 4u * (unsigned)__popc(mask & ((1u << lane) - 1));
+        if (uni && (int)lane == start) base = atomicAdd(&hist[key], 4u * (unsigned)(end - start));
+        base = __shfl_sync(0xffffffffu, base, start);
+        if (uni) {
+            const unsigned s0 = base + 4u * (lane - (unsigned)start);
 #pragma unroll
-        for (int u = 0; u < 4; u++) slot[u] = base + u;
-        return;
+            for (int u = 0; u < 4; u++) slot[u] = s0 + u;
+        }
     }
+    if (!uni) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) slot[u] = smem_claim(hist, k[u], k[u] >= 0);
+        for (int u = 0; u < 4; u++) slot[u] = (k[u] >= 0) ? atomicAdd(&hist[k[u]], 1u) : 0u;
+    }
 }
 
 // ---- TMA bulk copy global -> shared with an mbarrier (1-D: no tensor map needed)
@@ -754,7 +804,7 @@ k_tile_scan(const unsigned *__restrict__ cnt_w, const unsigned *__restrict__ cnt
 
 template <int SUP, typename PT, bool STAGED>
 __global__ void __launch_bounds__(1024)
-k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int mass_f4, int64_t n, TileGeom tg,
+k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int mass_f4, int64_t n, TileGeom tg, FastTile ft,
                  const unsigned *__restrict__ hdr, const unsigned *__restrict__ offsets,
                  const unsigned *__restrict__ cnt_w, unsigned *__restrict__ cur_o, const unsigned *__restrict__ blk,
                  const int *__restrict__ win_lo, unsigned *__restrict__ recs, void *__restrict__ smass, BucketPlan bp) {
@@ -786,7 +836,12 @@ k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int 
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 r[u][0] = r[u][1] = r[u][2] = 0;
-                t[u] = (u < nv) ? make_record<SUP, PT>(x[u], tg, r[u]) : -1;
+                t[u] = -1;
+                if (u < nv) {
+                    bool okp = false;
+                    if (sizeof(PT) == 4 && ft.pow2) t[u] = make_record_pow2<SUP>(reinterpret_cast<const float *>(x[u]), tg, ft, r[u], okp);
+                    if (!okp) t[u] = make_record<SUP, PT>(x[u], tg, r[u]);
+                }
                 const unsigned rel = (unsigned)(t[u] - lo);
                 k[u] = (t[u] >= 0 && rel < (unsigned)bp.W) ? (int)rel : -1;
                 anyout = anyout || (t[u] >= 0 && k[u] < 0);
@@ -804,6 +859,8 @@ k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int 
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (t[u] >= 0) {
+                    // 12-byte records, three 4-byte stores: a 16-byte record (one vector store / load) makes THIS pass
+                    // 10 % faster but the tile pass 25 % slower -- it is the DRAM bytes that count (profiles/r02_paint.md)
                     unsigned *dst = recs + 3 * (size_t)slot[u];
                     dst[0] = r[u][0]; dst[1] = r[u][1]; dst[2] = r[u][2];
                     if (mass) {
@@ -1129,21 +1186,18 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
     int pbuf = 0;
     TileBox pbox;
     for (;;) {
-        // ---- (1) the parked add set of the previous tile
+        // ---- (1) accumulate this tile, THEN add the parked set of the previous one: its neighbours had a whole
+        // accumulation phase to publish, so the flag poll is almost never a wait
+        if (t >= 0) accumulate(offsets[t], offsets[t + 1]);
         if (pending) {
             poll_earlier(pbox);
             const unsigned n = s_nst[pbuf];
             for (unsigned i = threadIdx.x; i < n; i += NT) atomicAdd(mesh + s_soff[i], s_sval[i]);
         }
         if (t < 0) break;
-        // ---- (2) accumulate
-        accumulate(offsets[t], offsets[t + 1]);
         __syncthreads();                                                 // barrier 1 of 2
         const int cbuf = pbuf ^ 1;
-        if (threadIdx.x == 0) {
-            if (pending) s_nst[pbuf] = 0;                                // consumed above by everyone
-            s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);                // next tile, visible after barrier 2
-        }
+        if (threadIdx.x == 0 && pending) s_nst[pbuf] = 0;                // consumed above by everyone
         pending = false;
         // ---- (3) write-back
         const TileBox bx = tile_box<R, H>(t, tg);
@@ -1253,6 +1307,9 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
             __syncthreads();
             for (int i = threadIdx.x; i < BUFW / 4; i += NT) reinterpret_cast<uint4 *>(s_all)[i] = make_uint4(0, 0, 0, 0);
         }
+        // the next tile is taken only now: a tile that is handed out is also published one tile-time later, which is
+        // what the tiles waiting on it count on
+        if (threadIdx.x == 0) s_tile = (int)atomicAdd(&hdr[HDR_QUEUE], 1u);
         __syncthreads();                                                 // barrier 2 of 2
         if (threadIdx.x == 0) st_release(&flags[t], epoch);              // cumulative over the CTA's stores (bar.sync)
         if (pending) { pbox = bx; pbuf = cbuf; }
@@ -1446,7 +1503,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     LAUNCH_BUCKET(k_bucket_count, grid_c, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, cnt_w, cnt_o, blk, win_lo);
     k_tile_scan<<<1, 1024, 0, s>>>(cnt_w, cnt_o, offsets, cur_o, flags, hdr, tg.ntiles);
     NBK_LAUNCHED();
-    LAUNCH_BUCKET(k_bucket_scatter, grid_cs, (const PT *)pos, mass, mass_f4, n, tg, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
+    LAUNCH_BUCKET(k_bucket_scatter, grid_cs, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
                   (void *)smass);
 #undef LAUNCH_BUCKET
     int spread_mode;

@@ -1,25 +1,29 @@
-"""FieldMesh -- a MeshSource wrapping an in-memory (device) Field (API of nbodykit/source/mesh/field.py)."""
+"""
+FieldMesh -- a MeshSource around a device field that already exists (API of nbodykit/source/mesh/field.py:7-40).
+
+The source shares the field's ParticleMesh (its slab decomposition and dtype) and answers only for the representation
+the field is in; MeshSource.compute converts (one FFT) when the other one is asked for.  The wrapped field is never
+modified: what leaves the source is a device-side copy.
+"""
 from ...base.mesh import MeshSource
-from ...pmesh.pm import ComplexField, RealField
+from ...pmesh.pm import BaseComplexField, RealField
 
 
 class FieldMesh(MeshSource):
-    """the wrapped field is never modified: every conversion hands out a copy"""
-
     def __repr__(self):
         return "FieldMesh()"
 
     def __init__(self, field):
-        MeshSource.__init__(self, field.pm.comm, field.Nmesh, field.BoxSize, field.pm.dtype)
-        self.pm = field.pm      # share the decomposition of the wrapped field
+        pm = field.pm
+        MeshSource.__init__(self, pm.comm, pm.Nmesh, pm.BoxSize, pm.dtype)
+        self.pm = pm
         self.field = field
 
-    def to_complex_field(self):
-        if isinstance(self.field, ComplexField):
-            return self.field.copy()
-        return NotImplemented
+    def _copy_if(self, kind):
+        return self.field.copy() if isinstance(self.field, kind) else NotImplemented
 
     def to_real_field(self):
-        if isinstance(self.field, RealField):
-            return self.field.copy()
-        return NotImplemented
+        return self._copy_if(RealField)
+
+    def to_complex_field(self):
+        return self._copy_if(BaseComplexField)

@@ -48,11 +48,12 @@ def main():
     del perm
     ref = None
     cases = (("sorted", pos),) if "--only-sorted" in sys.argv else (("sorted", pos), ("permuted", pp))
-    spreads = ("1", "0") if "--spread-both" in sys.argv else (os.environ.get("NBK_PAINT_SPREAD", "1"),)
+    spreads = ("1", "0") if "--spread-both" in sys.argv else (os.environ.get("NBK_PAINT_SPREAD", ""),)
     tag = " ".join("%s=%s" % (k[10:], v) for k, v in sorted(os.environ.items()) if k.startswith("NBK_PAINT_"))
     for label, p in cases:
         for spread in spreads:
-            os.environ["NBK_PAINT_SPREAD"] = spread
+            if spread:
+                os.environ["NBK_PAINT_SPREAD"] = spread
             t = timeit(lambda: pm.paint(p, resampler=res, hold=False, out=real, method='tiled'))
             print("%s %d^3 %s n=%d %-8s spread=%s [%s]: %.3f ms (median %.3f) -> %.3e part/s, %.0f GB/s algorithmic" % (
                 res, Nmesh, dtype, n, label, spread, tag, t[0], t[1], n / t[0] * 1e3, alg / t[0] / 1e6), flush=True)

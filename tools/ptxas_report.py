@@ -6,7 +6,7 @@ extra = sys.argv[sys.argv.index("--") + 1:] if "--" in sys.argv else []
 cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xptxas", "-v", "-c", src, "-o", "/tmp/_ptxas_report.o"] + extra
 out = subprocess.run(cmd, capture_output=True, text=True).stderr
 names = re.findall(r"Compiling entry function '(\S+)'", out)
-dem = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines()
+dem = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines() if names else []
 blocks = out.split("Compiling entry function")[1:]
 for n, d, b in zip(names, dem, blocks):
     if not re.search(pat, d):
