@@ -14,6 +14,7 @@
 // k_fft_z_c2r) stage whole tiles and serve short lines, the backward z pass and NBK_FFT_LINES=smem.
 // Twiddles: f8-accurate table built on the device with sincospi, staged in shared memory.  Sizes: 2^k.
 #include "common.cuh"
+#include <cuda.h>      // CUtensorMap types only: the encoder comes from cudaGetDriverEntryPoint (no -lcuda)
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -552,6 +553,225 @@ k_fft_lines_rgp(const typename C2<T>::type *src, typename C2<T>::type *dst, Peer
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA-pipelined line pass (N = 64 R, R in {4, 8, 16}: lines of 256 / 512 / 1024).  Decimation in TIME over the first
+// factor: the line x[n], n = j + R i, splits into R "row groups" j (rows j, j + R, ...: 64 rows of B adjacent columns =
+// one 8 KB box of a 4-D tensor map {inner, j, i, outer}), each an independent 64-point FFT, followed by ONE radix-R
+// combine  X[k + 64 m] = sum_j W_R^{jm} (W_N^{jk} Y_j[k]).
+//   * one elected thread streams the groups of this CTA's tiles through a ring of NS = R + P shared-memory slots with
+//     `cp.async.bulk.tensor` (SASS UTMALDG) + one mbarrier per slot: P groups of the NEXT tile are already in flight
+//     while this tile is combined, the rest follow as soon as its slots are free -- the copy engine, not the warps'
+//     registers, hides the HBM latency, and the warps only run butterflies;
+//   * warp w owns group w of the tile: it waits for its own mbarrier and runs the 64-point FFT (8 x 8, two radix-8
+//     stages in place, __syncwarp between) while later groups are still landing;
+//   * after one CTA barrier every thread combines R values (radix-R in registers, natural output order) and stores the
+//     frequency rows k + 64 m straight to global memory (128-byte runs); a second CTA barrier frees the R slots.
+// Slots are dense [64][B] with B * sizeof(complex) = 128 bytes, lanes run along the columns first, so every quarter
+// warp touches one full 128-byte row: conflict-free without padding.  In place (dst == src) is safe: a tile's stores
+// only touch its own rows / columns, which were read completely before its combine.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned fm_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fm_mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(fm_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fm_mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(fm_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void fm_mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "NBK_FM_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra NBK_FM_DONE;\n"
+        "bra NBK_FM_WAIT;\n"
+        "NBK_FM_DONE:\n"
+        "}\n" :: "r"(fm_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fm_tma_load_4d(void *sdst, const CUtensorMap *tmap, int c0, int c1, int c2, int c3, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 :: "r"(fm_smem_u32(sdst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(fm_smem_u32(bar)) : "memory");
+}
+
+template <typename C> struct W16c;      // cos(pi/8), sin(pi/8)
+template <> struct W16c<float2> { static __device__ __forceinline__ float c() { return 0.92387953251128675613f; }
+                                  static __device__ __forceinline__ float s() { return 0.38268343236508977173f; } };
+template <> struct W16c<double2> { static __device__ __forceinline__ double c() { return 0.92387953251128675613; }
+                                   static __device__ __forceinline__ double s() { return 0.38268343236508977173; } };
+
+// 16-point forward DFT in registers, natural order in and out (4 x 4: n = 4 n1 + n2, k = k1 + 4 k2)
+template <typename C>
+__device__ __forceinline__ void dft16(C (&a)[16]) {
+    const auto h = Sqrt1_2<C>::v();
+    const auto c8 = W16c<C>::c(), s8 = W16c<C>::s();
+    C y[4][4];                                   // y[n2][k1]
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) {
+        C b0 = a[n2], b1 = a[4 + n2], b2 = a[8 + n2], b3 = a[12 + n2];
+        dft4(b0, b1, b2, b3);
+        y[n2][0] = b0; y[n2][1] = b1; y[n2][2] = b2; y[n2][3] = b3;
+    }
+    // twiddles W_16^{n2 k1}
+    y[1][1] = cmul(y[1][1], C{c8, -s8});                                   // W^1
+    y[1][2] = C{(y[1][2].x + y[1][2].y) * h, (y[1][2].y - y[1][2].x) * h};  // W^2 = (1 - i)/sqrt2
+    y[1][3] = cmul(y[1][3], C{s8, -c8});                                   // W^3
+    y[2][1] = C{(y[2][1].x + y[2][1].y) * h, (y[2][1].y - y[2][1].x) * h};  // W^2
+    y[2][2] = cmuli_neg(y[2][2]);                                          // W^4 = -i
+    y[2][3] = C{(y[2][3].y - y[2][3].x) * h, -(y[2][3].x + y[2][3].y) * h}; // W^6 = (-1 - i)/sqrt2
+    y[3][1] = cmul(y[3][1], C{s8, -c8});                                   // W^3
+    y[3][2] = C{(y[3][2].y - y[3][2].x) * h, -(y[3][2].x + y[3][2].y) * h}; // W^6
+    y[3][3] = cmul(y[3][3], C{-c8, s8});                                   // W^9 = -W^1
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+        C b0 = y[0][k1], b1 = y[1][k1], b2 = y[2][k1], b3 = y[3][k1];
+        dft4(b0, b1, b2, b3);
+        a[k1] = b0; a[k1 + 4] = b1; a[k1 + 8] = b2; a[k1 + 12] = b3;
+    }
+}
+template <int R, typename C> __device__ __forceinline__ void dftR(C (&a)[R]) {
+    if constexpr (R == 16) dft16(a);
+    else if constexpr (R == 8) radix8(a);
+    else { static_assert(R == 4, "combine radix"); dft4(a[0], a[1], a[2], a[3]); }
+}
+
+template <typename T, int R, bool PEER>
+__global__ void __launch_bounds__(32 * R)
+k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *dst, PeerPtrs<typename C2<T>::type> peers,
+                const typename C2<T>::type *__restrict__ twg, int64_t line_stride, int64_t n_inner, int64_t tiles_inner,
+                int64_t n_tiles, int64_t outer_stride, int n_per, int64_t d_total, int64_t outer_start, int inverse, T scale,
+                int NS) {
+    typedef typename C2<T>::type C;
+    constexpr int B = 128 / (int)sizeof(C);      // side-by-side lines: 8 (c16) / 16 (c8) = 128-byte rows
+    constexpr int S = 64, N = S * R, NT = 32 * R, SLOT = S * B;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    C *ring = reinterpret_cast<C *>(smem_raw);                 // [NS][64][B]
+    C *twN = ring + (size_t)NS * SLOT;                         // W_N^i, i < N
+    C *tw64 = twN + N;                                         // W_64^i, i < 64
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tw64 + S);   // [NS]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < NS; i++) fm_mbar_init(&bars[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < N; i += NT) twN[i] = twg[i];
+    for (int i = tid; i < S; i += NT) tw64[i] = twg[i * R];
+    __syncthreads();
+    const int64_t first = blockIdx.x;
+    const int my_tiles = first < n_tiles ? (int)((n_tiles - first + gridDim.x - 1) / gridDim.x) : 0;
+    const int G = my_tiles * R;                                // row groups this CTA streams
+    const T sgn = inverse ? (T)-1 : (T)1;
+    int issued = 0;
+    auto issue = [&](int g) {
+        const int it = g / R, j = g - it * R;
+        const int64_t tile = first + (int64_t)it * gridDim.x;
+        const int64_t outer = tile / tiles_inner;
+        const int64_t inner0 = (tile - outer * tiles_inner) * B;
+        const int slot = g % NS;
+        fm_mbar_expect_tx(&bars[slot], (unsigned)(SLOT * sizeof(C)));
+        fm_tma_load_4d(ring + (size_t)slot * SLOT, &tmap, (int)(2 * inner0), j, 0, (int)outer, &bars[slot]);
+    };
+    if (tid == 0) {
+        const int upto = G < NS ? G : NS;
+        for (; issued < upto; issued++) issue(issued);
+    }
+    for (int it = 0; it < my_tiles; it++) {
+        const int64_t tile = first + (int64_t)it * gridDim.x;
+        const int64_t outer = tile / tiles_inner;
+        const int64_t inner0 = (tile - outer * tiles_inner) * B;
+        const int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
+        // ---- 64-point FFT of my row group (warp-local: two radix-8 stages in place)
+        {
+            const int g = it * R + warp, slot = g % NS;
+            fm_mbar_wait(&bars[slot], (unsigned)((g / NS) & 1));
+            C *sl = ring + (size_t)slot * SLOT;
+            constexpr int IT = (8 * B) / 32;
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                const int w = lane + 32 * i, b = w % B, q = w / B;
+                C *p = sl + q * B + b;
+                C a[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) { a[j] = p[j * 8 * B]; a[j].y *= sgn; }
+                radix8(a);
+                p[0] = a[0];
+#pragma unroll
+                for (int m = 1; m < 8; m++) p[m * 8 * B] = cmul(a[m], tw64[m * q]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < IT; i++) {
+                const int w = lane + 32 * i, b = w % B, t = w / B;
+                C *p = sl + t * 8 * B + b;
+                C a[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = p[j * B];
+                radix8(a);
+#pragma unroll
+                for (int m = 0; m < 8; m++) p[m * B] = a[m];       // position 8 t + m holds frequency t + 8 m
+            }
+        }
+        __syncthreads();
+        // ---- radix-R combine across the groups, registers -> global frequency rows k + 64 m
+        {
+            const int base = (it * R) % NS;
+            for (int w = tid; w < S * B; w += NT) {
+                const int b = w % B, k = w / B;
+                const int pos = ((k & 7) << 3) | (k >> 3);
+                C a[R];
+#pragma unroll
+                for (int j = 0; j < R; j++) {
+                    int sj = base + j;
+                    if (sj >= NS) sj -= NS;
+                    C v = ring[(size_t)sj * SLOT + pos * B + b];
+                    a[j] = j ? cmul(v, twN[j * k]) : v;
+                }
+                dftR<R, C>(a);
+                if (b < bvalid) {
+#pragma unroll
+                    for (int m = 0; m < R; m++) {
+                        const int K = k + S * m;
+                        const C v = C{a[m].x * scale, a[m].y * sgn * scale};
+                        if (PEER) {
+                            const int pr = K / n_per, kl = K - pr * n_per;
+                            peers.p[pr][((int64_t)kl * d_total + outer_start + outer) * n_inner + inner0 + b] = v;
+                        } else {
+                            dst[outer * outer_stride + inner0 + (int64_t)K * line_stride + b] = v;
+                        }
+                    }
+                }
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic accesses to the slots before the next TMA writes
+        __syncthreads();
+        if (tid == 0) {
+            int upto = (it + 1) * R + NS;
+            if (upto > G) upto = G;
+            for (; issued < upto; issued++) issue(issued);
+        }
+    }
+}
+
+typedef CUresult (*nbk_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                        const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static nbk_encode_tiled_fn get_tensor_map_encoder() {
+    static std::mutex m;
+    static bool tried = false;
+    static nbk_encode_tiled_fn fn = nullptr;
+    std::lock_guard<std::mutex> lock(m);
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (nbk_encode_tiled_fn)p;
+        else
+            (void)cudaGetLastError();
+    }
+    return fn;
+}
+
+// ---------------------------------------------------------------------------------------------
 // z pass forward: real rows [rows][Nz] -> complex rows [rows][Nz/2+1]
 // packed trick: z[n] = x[2n] + i x[2n+1], Z = FFT_M(z), M = Nz/2,
 //   X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k]) ],  k = 0..M  (Z[M] := Z[0])
@@ -848,9 +1068,85 @@ static bool use_reg_lines(int N) {
     static int mode = -1;
     if (mode < 0) {
         const char *e = getenv("NBK_FFT_LINES");
-        mode = (e && strcmp(e, "smem") == 0) ? 0 : 1;
+        mode = (e && strcmp(e, "smem") == 0) ? 0 : 1;      // "rg" / default: register-I/O family (the TMA pass is tried first)
     }
     return mode == 1 && N >= 64;
+}
+
+// TMA-pipelined line pass (k_fft_lines_tma) where it applies: N in {256, 512, 1024}, 16-byte aligned rows (always true
+// for c16 fields; c8 fields with an odd row length -- the y pass over Nz/2+1 columns -- keep the register-I/O kernel).
+// NBK_FFT_LINES=rg|smem selects the older kernels.  *done = false: not applicable, the caller falls back.
+static int lines_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char *e = getenv("NBK_FFT_LINES");
+        mode = (e && strcmp(e, "smem") == 0) ? 0 : (e && strcmp(e, "rg") == 0) ? 1 : 2;
+    }
+    return mode;
+}
+template <typename T>
+static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, int P, int N, int64_t line_stride,
+                            int64_t n_inner, int64_t n_outer, int64_t outer_stride, int64_t outer_start, int inverse,
+                            double scale, cudaStream_t s, int64_t d_total_override, bool *done) {
+    typedef typename C2<T>::type C;
+    *done = false;
+    if (lines_mode() != 2 || (N != 256 && N != 512 && N != 1024)) return NBK_OK;
+    const size_t cs = sizeof(C);
+    if (n_outer > 1 && outer_stride == 0) return NBK_OK;
+    const int64_t ostride = n_outer > 1 ? outer_stride : (int64_t)N * line_stride;
+    if ((reinterpret_cast<uintptr_t>(src) & 15) || ((size_t)line_stride * cs) % 16 || ((size_t)ostride * cs) % 16) return NBK_OK;
+    if (2 * n_inner >= (1ll << 31) || n_outer >= (1ll << 31) || (size_t)ostride * cs >= ((size_t)1 << 40) ||
+        (size_t)(N / 64) * line_stride * cs >= ((size_t)1 << 40)) return NBK_OK;
+    nbk_encode_tiled_fn enc = get_tensor_map_encoder();
+    if (!enc) return NBK_OK;
+    const int R = N / 64;
+    constexpr int B = 128 / (int)sizeof(C);
+    CUtensorMap tmap;
+    const cuuint64_t gdim[4] = {(cuuint64_t)(2 * n_inner), (cuuint64_t)R, 64, (cuuint64_t)n_outer};
+    const cuuint64_t gstr[3] = {(cuuint64_t)line_stride * cs, (cuuint64_t)R * line_stride * cs, (cuuint64_t)ostride * cs};
+    const cuuint32_t box[4] = {(cuuint32_t)(2 * B), 1, 64, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult cr = enc(&tmap, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4,
+                      const_cast<void *>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return NBK_OK;                     // shape the encoder refuses: older kernels
+    int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
+    void *tw;
+    int rc = get_twiddle(N, dtype, s, &tw);
+    if (rc) return rc;
+    // ring: R slots of the tile being transformed + P prefetch slots; 1 CTA / SM at N = 1024, 2 at 512, 3 at 256
+    static int knob_ns = -1;
+    if (knob_ns < 0) { const char *e = getenv("NBK_FFT_TMA_NS"); knob_ns = e ? atoi(e) : 0; }
+    int NS = R == 16 ? 24 : R == 8 ? 12 : 8;
+    if (knob_ns >= R + 1 && knob_ns <= 26) NS = knob_ns;
+    const size_t slot = (size_t)64 * B * cs;                   // 8 KB
+    const size_t smem = (size_t)NS * slot + (size_t)(N + 64) * cs + (size_t)NS * 8 + 64;
+    NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: ring of %d slots does not fit in shared memory", NS);
+    int per_sm = (int)((227 * 1024) / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 3) per_sm = 3;
+    const int64_t tiles_inner = (n_inner + B - 1) / B;
+    const int64_t n_tiles = tiles_inner * n_outer;
+    const int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
+    PeerPtrs<C> peers;
+    for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
+    const int n_per = peer_host ? N / P : N;
+    const int64_t d_total = d_total_override ? d_total_override : (peer_host ? n_outer * P : 0);
+#define LAUNCH_TMA(RR, PEERF)                                                                                          \
+    do {                                                                                                               \
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_tma<T, RR, PEERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_fft_lines_tma<T, RR, PEERF><<<(int)g, 32 * RR, smem, s>>>(tmap, (C *)dst, peers, (const C *)tw, line_stride, n_inner, \
+            tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale, NS);                  \
+    } while (0)
+    if (peer_host) {
+        if (R == 16) LAUNCH_TMA(16, true); else if (R == 8) LAUNCH_TMA(8, true); else LAUNCH_TMA(4, true);
+    } else {
+        if (R == 16) LAUNCH_TMA(16, false); else if (R == 8) LAUNCH_TMA(8, false); else LAUNCH_TMA(4, false);
+    }
+#undef LAUNCH_TMA
+    NBK_LAUNCHED();
+    *done = true;
+    return NBK_OK;
 }
 
 // register-I/O line pass; peer_host != nullptr selects the peer-memory scatter store
@@ -859,6 +1155,12 @@ static int launch_lines_rg(const void *src, void *dst, void *const *peer_host, i
                            int64_t n_inner, int64_t n_outer, int64_t outer_stride, int64_t outer_start, int inverse,
                            double scale, cudaStream_t s, int64_t d_total_override = 0) {
     typedef typename C2<T>::type C;
+    {
+        bool done = false;
+        int rct = launch_lines_tma<T>(src, dst, peer_host, P, N, line_stride, n_inner, n_outer, outer_stride, outer_start,
+                                      inverse, scale, s, d_total_override, &done);
+        if (rct || done) return rct;
+    }
     int dtype = sizeof(T) == 4 ? NBK_F4 : NBK_F8;
     void *tw;
     int rc = get_twiddle(N, dtype, s, &tw);

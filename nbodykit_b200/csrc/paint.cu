@@ -301,8 +301,10 @@ __device__ __forceinline__ int tile_from_cells(const int *c, const TileGeom &tg)
 }
 
 // exact (f8) tile id of the particle at x[0..2]: the arithmetic of the scatter itself
+// (coordinates by value: a pointer argument of a non-inlined function would force the callers' arrays into local memory)
 template <int SUP, typename PT>
-__device__ __noinline__ int tile_of_exact(const PT *x, const TileGeom &tg) {
+__device__ __noinline__ int tile_of_exact3(PT x0, PT x1, PT x2, const TileGeom &tg) {
+    const PT x[3] = {x0, x1, x2};
     int c[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
@@ -315,6 +317,8 @@ __device__ __noinline__ int tile_of_exact(const PT *x, const TileGeom &tg) {
     }
     return tile_from_cells(c, tg);
 }
+template <int SUP, typename PT>
+__device__ __forceinline__ int tile_of_exact(const PT *x, const TileGeom &tg) { return tile_of_exact3<SUP, PT>(x[0], x[1], x[2], tg); }
 
 __device__ __forceinline__ void pack_record(const unsigned *u, const int *c, const TileGeom &tg, unsigned *rec) {
     int lx = (tg.full ? c[0] : slab_local(c[0], tg) + tg.G) & (TILE - 1);
@@ -325,21 +329,33 @@ __device__ __forceinline__ void pack_record(const unsigned *u, const int *c, con
 
 // exact leftmost cell + fixed-point fraction (the arithmetic of Window<SUP>::eval on the unshifted g).
 // Slow path: any magnitude, 64-bit cell arithmetic.
+struct RecTile { unsigned r[3]; int tile; };
 template <int SUP, typename PT>
-__device__ __noinline__ int make_record_slow(const PT *x, const TileGeom &tg, unsigned *rec) {
+__device__ __noinline__ RecTile make_record_slow3(PT x0, PT x1, PT x2, const TileGeom &tg) {
+    const PT x[3] = {x0, x1, x2};
+    RecTile o;
+    o.r[0] = o.r[1] = o.r[2] = 0;
+    o.tile = -1;
     unsigned u[3];
     int c[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         double g = (double)x[d] * tg.gm.scale[d];
-        if (!isfinite(g)) return -1;
+        if (!isfinite(g)) return o;
         double a = g + (double)WinOff<SUP>::A;
         double f = floor(a);
         u[d] = __double2uint_rz((a - f) * 4294967296.0);
         c[d] = wrap((long long)f + WinOff<SUP>::B, tg.gm.n[d]);
     }
-    pack_record(u, c, tg, rec);
-    return tile_from_cells(c, tg);
+    pack_record(u, c, tg, o.r);
+    o.tile = tile_from_cells(c, tg);
+    return o;
+}
+template <int SUP, typename PT>
+__device__ __forceinline__ int make_record_slow(const PT *x, const TileGeom &tg, unsigned *rec) {
+    const RecTile o = make_record_slow3<SUP, PT>(x[0], x[1], x[2], tg);
+    rec[0] = o.r[0]; rec[1] = o.r[1]; rec[2] = o.r[2];
+    return o.tile;
 }
 
 // Fast path for |g| < 2^31 without any float<->int conversion instruction (they issue at a fraction of the FP64
@@ -922,6 +938,14 @@ __device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// polling load: gpu-scope relaxed (no L1 invalidation per iteration, unlike ld.acquire = LDG.STRONG + CCTL.IVALL);
+// the acquire is one fence after the loop
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(unsigned *p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
@@ -974,8 +998,10 @@ template <int SUP, typename MT, typename FT, bool SHIFTED, int FLUSH>
 __global__ void __launch_bounds__(256, FLUSH == 0 ? 4 : 1)
 k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, TileGeom tg,
              const unsigned *__restrict__ offsets, unsigned *__restrict__ hdr, unsigned *__restrict__ flags,
-             unsigned epoch, int spread, FT *__restrict__ mesh) {
+             unsigned epoch, int knobs, FT *__restrict__ mesh) {
     extern __shared__ __align__(16) unsigned s_all[];
+    const int spread = knobs & 1;                  // diagnosis knobs: bit 0 = spread lanes, bit 1 = acquire-load polling
+    const bool poll_relaxed = !(knobs & 2);
     constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0);   // == tg.R
     // row pitch in cells: the TMA write-back needs rows that start 16-byte aligned, the ordered one 8-byte cell pairs
     constexpr int RP = FLUSH == 0 ? ((R + 1) & ~1) : ((R + 3) & ~3);
@@ -1158,10 +1184,12 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
             }
             if (valid) {
                 const unsigned *f = &flags[(nb[0] * tg.nt[1] + nb[1]) * tg.nt[2] + nb[2]];
-                while (ld_acquire(f) < epoch) __nanosleep(32);
+                if (poll_relaxed) { while (ld_relaxed(f) < epoch) __nanosleep(32); }
+                else { while (ld_acquire(f) < epoch) __nanosleep(32); }
             }
         }
         __syncwarp();
+        if (poll_relaxed) fence_acq_rel_gpu();
     };
     // warp-aggregated append of (mesh offset, value) to the stash
     auto stash_push = [&](bool keep, unsigned off, FT val, unsigned *counter) {
@@ -1510,6 +1538,8 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     {
         const char *e = getenv("NBK_PAINT_SPREAD");      // "1": the lanes of a warp walk separate segments of a bucket (diagnosis)
         spread_mode = (e && e[0] == '1') ? 1 : 0;
+        e = getenv("NBK_PAINT_POLL");                    // "acquire": ld.acquire in the flag poll loop (round-2 baseline)
+        if (e && e[0] == 'a') spread_mode |= 2;
     }
     // the region edge depends on the mesh being painted (one more cell for the half-cell shifted one); tile ids do not
 #define LAUNCH_TP(SH, FL, MESHP, EPOCH)                                                                                \

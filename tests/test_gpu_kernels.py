@@ -111,7 +111,9 @@ def test_paint_interlaced_pair(cuda):
 
 
 @pytest.mark.parametrize("N", [[8, 8, 8], [16, 32, 64], [64, 16, 4], [128, 128, 128], [2, 4, 8], [256, 64, 32], [512, 128, 16],
-                               [1024, 8, 16], [2048, 4, 8]])
+                               [1024, 8, 16], [2048, 4, 8],
+                               # y / x lines of 256, 512, 1024: the TMA-pipelined line pass (ragged last column tile included)
+                               [4, 256, 16], [2, 512, 8], [2, 1024, 8], [256, 256, 16], [512, 4, 16]])
 @pytest.mark.parametrize("dtype,tol", [("f8", 1e-13), ("f4", 2e-6)])
 def test_r2c_c2r(cuda, N, dtype, tol):
     from nbodykit_b200.pmesh.pm import RealField
@@ -490,7 +492,7 @@ def test_route_kernels_vs_numpy(cuda):
             start += cnt[r]
 
 
-@pytest.mark.parametrize("shape", [(16, 32, 8), (64, 128, 8), (128, 64, 32)])
+@pytest.mark.parametrize("shape", [(16, 32, 8), (64, 128, 8), (128, 64, 32), (4, 256, 8), (256, 512, 4), (2, 1024, 16)])
 @pytest.mark.parametrize("dtype", ["f8", "f4"])
 def test_fft_scatter_transpose_two_virtual_ranks(cuda, dtype, shape):
     """nbk_fft_z_forward + nbk_fft_lines_scatter + nbk_fft_lines_oop == r2c, with the slab transpose done by the y
