@@ -633,15 +633,16 @@ template <int R, typename C> __device__ __forceinline__ void dftR(C (&a)[R]) {
     else { static_assert(R == 4, "combine radix"); dft4(a[0], a[1], a[2], a[3]); }
 }
 
-template <typename T, int R, bool PEER>
-__global__ void __launch_bounds__(32 * R)
+template <typename T, int R, int B, int NT, bool PEER>
+__global__ void __launch_bounds__(NT)
 k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *dst, PeerPtrs<typename C2<T>::type> peers,
                 const typename C2<T>::type *__restrict__ twg, int64_t line_stride, int64_t n_inner, int64_t tiles_inner,
                 int64_t n_tiles, int64_t outer_stride, int n_per, int64_t d_total, int64_t outer_start, int inverse, T scale,
                 int NS) {
     typedef typename C2<T>::type C;
-    constexpr int B = 128 / (int)sizeof(C);      // side-by-side lines: 8 (c16) / 16 (c8) = 128-byte rows
-    constexpr int S = 64, N = S * R, NT = 32 * R, SLOT = S * B;
+    // B side-by-side lines: 128-byte rows (8 c16 / 16 c8), or 64-byte rows at N = 1024 so that TWO CTAs share an SM
+    constexpr int S = 64, N = S * R, NW = NT / 32, SLOT = S * B;
+    static_assert((8 * B) % 32 == 0 && R % NW == 0, "tile geometry");
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     C *ring = reinterpret_cast<C *>(smem_raw);                 // [NS][64][B]
     C *twN = ring + (size_t)NS * SLOT;                         // W_N^i, i < N
@@ -679,8 +680,8 @@ k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *
         const int64_t inner0 = (tile - outer * tiles_inner) * B;
         const int bvalid = (int)((n_inner - inner0) < B ? (n_inner - inner0) : B);
         // ---- 64-point FFT of my row group (warp-local: two radix-8 stages in place)
-        {
-            const int g = it * R + warp, slot = g % NS;
+        for (int gw = warp; gw < R; gw += NW) {
+            const int g = it * R + gw, slot = g % NS;
             fm_mbar_wait(&bars[slot], (unsigned)((g / NS) & 1));
             C *sl = ring + (size_t)slot * SLOT;
             constexpr int IT = (8 * B) / 32;
@@ -960,6 +961,144 @@ k_fft_z_r2c_rg(const T *__restrict__ real, typename C2<T>::type *__restrict__ cp
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// z pass forward, warp-per-row with TMA bulk row copies (Nz = 2M, M in {128, 256, 512}).  Every warp owns a private ring of
+// row buffers: one lane streams the next rows of the warp in with `cp.async.bulk` (one 1-D copy of the whole row, SASS
+// UBLKCP) + an mbarrier per buffer while the warp transforms the row that has landed -- packed-pair M-point FFT (radix 8,
+// 8, M/64, in place, __syncwarp between the stages), Hermitian split, coalesced stores of the Nz/2+1 modes.  No CTA
+// barrier after the twiddle staging, so the warps of an SM drift apart and the loads never stop.
+// Shared-memory positions are XOR-swizzled, pos(e) = e ^ ((e >> 3) & 7) (a permutation inside each aligned group of 8
+// elements = one 128-byte line of c16), which makes the stride-8 accesses of the later stages and the natural-order
+// write of the last stage bank-conflict free; the copy engine lands the row unswizzled and the first stage re-places it.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fm_bulk_g2s(void *sdst, const void *gsrc, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(fm_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(fm_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ int fm_sw(int e) { return e ^ ((e >> 3) & 7); }
+
+template <typename T, int LM, int NW>
+__global__ void __launch_bounds__(32 * NW)
+k_fft_z_r2c_tma(const T *__restrict__ real, typename C2<T>::type *__restrict__ cplx,
+                const typename C2<T>::type *__restrict__ twN_g, int64_t rows, T scale, int nbuf) {
+    typedef typename C2<T>::type C;
+    constexpr int M = 1 << LM, Nz = 2 * M, Nzc = M + 1;
+    constexpr int R3 = M / 64;                    // last radix: 8 / 4 / 2
+    constexpr int Q1 = M / 8;                     // butterflies of the radix-8 stages
+    constexpr int I1 = (Q1 + 31) / 32;            // ... per lane
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    C *twN = reinterpret_cast<C *>(smem_raw);                         // W_N^i, i <= M  (Hermitian split)
+    C *tw1 = twN + Nz;                                                // [7][Q1]  W_M^{q m}: lanes along q, unit stride
+    C *tw2 = tw1 + 7 * Q1;                                            // [7][R3]  W_{8 R3}^{q m}
+    C *bufs = tw2 + 7 * 8;                                            // [NW][nbuf][M]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bufs + (size_t)NW * nbuf * M);   // [NW][nbuf]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < Nz; i += 32 * NW) twN[i] = twN_g[i];
+    // (a strided twN[2 m q] / twN[16 m q] puts the lanes of a quarter warp on the same banks: 8-way conflicts that made
+    // the twiddle reads cost more shared-memory wavefronts than the data)
+    for (int i = threadIdx.x; i < 7 * Q1; i += 32 * NW) { const int m = i / Q1 + 1, q = i % Q1; tw1[i] = twN_g[2 * m * q]; }
+    for (int i = threadIdx.x; i < 7 * R3; i += 32 * NW) { const int m = i / R3 + 1, q = i % R3; tw2[i] = twN_g[(16 * m * q) % Nz]; }
+    if (lane == 0) {
+        for (int i = 0; i < nbuf; i++) fm_mbar_init(&bars[warp * nbuf + i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int64_t gw = (int64_t)blockIdx.x * NW + warp, GW = (int64_t)gridDim.x * NW;
+    const int64_t my_rows = gw < rows ? (rows - gw + GW - 1) / GW : 0;
+    C *wbuf = bufs + (size_t)warp * nbuf * M;
+    uint64_t *wbar = bars + warp * nbuf;
+    const unsigned row_bytes = (unsigned)(M * sizeof(C));
+    auto issue = [&](int64_t i) {     // lane 0 only
+        const int sidx = (int)(i % nbuf);
+        fm_mbar_expect_tx(&wbar[sidx], row_bytes);
+        fm_bulk_g2s(wbuf + (size_t)sidx * M, real + (gw + i * GW) * (int64_t)Nz, row_bytes, &wbar[sidx]);
+    };
+    if (lane == 0) for (int64_t i = 0; i < nbuf && i < my_rows; i++) issue(i);
+    const T h = (T)0.5 * scale;
+    for (int64_t i = 0; i < my_rows; i++) {
+        const int sidx = (int)(i % nbuf);
+        fm_mbar_wait(&wbar[sidx], (unsigned)((i / nbuf) & 1));
+        C *z = wbuf + (size_t)sidx * M;
+        // ---- stage 1 (radix 8 over elements q + Q1 j): reads the landed (unswizzled) row, writes swizzled
+        {
+            C a[I1][8];
+#pragma unroll
+            for (int it = 0; it < I1; it++) {
+                const int q = lane + 32 * it;
+                if (q < Q1) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) a[it][j] = z[q + Q1 * j];
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < I1; it++) {
+                const int q = lane + 32 * it;
+                if (q < Q1) {
+                    radix8(a[it]);
+                    z[fm_sw(q)] = a[it][0];
+#pragma unroll
+                    for (int m = 1; m < 8; m++) z[fm_sw(q + Q1 * m)] = cmul(a[it][m], tw1[(m - 1) * Q1 + q]);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- stage 2 (radix 8 inside the 8 blocks of Q1 elements: elements blk Q1 + q + R3 j), in place
+#pragma unroll
+        for (int it = 0; it < I1; it++) {
+            const int t = lane + 32 * it;
+            if (t < Q1) {
+                const int blk = t / R3, q = t - blk * R3;
+                const int e0 = blk * Q1 + q;
+                C a[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) a[j] = z[fm_sw(e0 + R3 * j)];
+                radix8(a);
+                z[fm_sw(e0)] = a[0];
+#pragma unroll
+                for (int m = 1; m < 8; m++) z[fm_sw(e0 + R3 * m)] = cmul(a[m], tw2[(m - 1) * R3 + q]);      // W_{8 R3}^{q m}
+            }
+        }
+        __syncwarp();
+        // ---- stage 3 (radix R3 over elements R3 t + j, 64 butterflies); outputs go to NATURAL frequency positions:
+        // position R3 t + m3 holds frequency (t / 8) + 8 (t % 8) + 64 m3
+        {
+            C a[2][R3];
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int t = lane + 32 * it;
+#pragma unroll
+                for (int j = 0; j < R3; j++) a[it][j] = z[fm_sw(R3 * t + j)];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 2; it++) {
+                const int t = lane + 32 * it;
+                if constexpr (R3 == 8) radix8(a[it]);
+                else if constexpr (R3 == 4) dft4(a[it][0], a[it][1], a[it][2], a[it][3]);
+                else { C x0 = a[it][0], x1 = a[it][1]; a[it][0] = cadd(x0, x1); a[it][1] = csub(x0, x1); }
+                const int k0 = (t >> 3) + 8 * (t & 7);
+#pragma unroll
+                for (int m = 0; m < R3; m++) z[fm_sw(k0 + 64 * m)] = a[it][m];
+            }
+        }
+        __syncwarp();
+        // ---- Hermitian split, lanes along k:  X[k] = 1/2 [ (Z[k] + conj Z[M-k]) - i W_N^k (Z[k] - conj Z[M-k]) ]
+        C *drow = cplx + (gw + i * GW) * (int64_t)Nzc;
+        for (int k = lane; k < Nzc; k += 32) {
+            const C zk = z[fm_sw(k & (M - 1))];
+            const C zm = cconj(z[fm_sw((M - k) & (M - 1))]);
+            const C e = cadd(zk, zm), o = csub(zk, zm);
+            const C wo = cmul(twN[k], o);
+            drow[k] = C{(e.x + wo.y) * h, (e.y - wo.x) * h};
+        }
+        // ---- the buffer is free: fetch the row that will use it next
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && i + nbuf < my_rows) issue(i + nbuf);
+    }
+}
+
 // z pass backward: complex rows [rows][Nz/2+1] -> real rows [rows][Nz], unnormalised
 //   E = (X[k] + conj X[M-k])/2, O = conj(W_N^k) (X[k] - conj X[M-k])/2, Z[k] = E + i O, k < M
 //   x[2n] + i x[2n+1] = 2 * sum_k Z[k] e^{+2 pi i k n / M} = 2 * conj(FFT_M(conj Z))[n]
@@ -1100,7 +1239,14 @@ static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, 
     nbk_encode_tiled_fn enc = get_tensor_map_encoder();
     if (!enc) return NBK_OK;
     const int R = N / 64;
-    constexpr int B = 128 / (int)sizeof(C);
+    // tile width: 128-byte rows.  (64-byte rows -- half the ring, two CTAs per SM at N = 1024 -- are selectable with
+    // NBK_FFT_TMA_B = columns; measured slower: the x pass of 1024^3 f8 takes 7.2 ms instead of 4.1.)
+    static int knob_b = -1, knob_ns = -1;
+    if (knob_b < 0) { const char *e = getenv("NBK_FFT_TMA_B"); knob_b = e ? atoi(e) : 0; }
+    if (knob_ns < 0) { const char *e = getenv("NBK_FFT_TMA_NS"); knob_ns = e ? atoi(e) : 0; }
+    const int Bfull = 128 / (int)cs;
+    int B = Bfull;
+    if (N != 256 && (knob_b == Bfull || knob_b == Bfull / 2)) B = knob_b;
     CUtensorMap tmap;
     const cuuint64_t gdim[4] = {(cuuint64_t)(2 * n_inner), (cuuint64_t)R, 64, (cuuint64_t)n_outer};
     const cuuint64_t gstr[3] = {(cuuint64_t)line_stride * cs, (cuuint64_t)R * line_stride * cs, (cuuint64_t)ostride * cs};
@@ -1114,17 +1260,17 @@ static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, 
     void *tw;
     int rc = get_twiddle(N, dtype, s, &tw);
     if (rc) return rc;
-    // ring: R slots of the tile being transformed + P prefetch slots; 1 CTA / SM at N = 1024, 2 at 512, 3 at 256
-    static int knob_ns = -1;
-    if (knob_ns < 0) { const char *e = getenv("NBK_FFT_TMA_NS"); knob_ns = e ? atoi(e) : 0; }
-    int NS = R == 16 ? 24 : R == 8 ? 12 : 8;
-    if (knob_ns >= R + 1 && knob_ns <= 26) NS = knob_ns;
-    const size_t slot = (size_t)64 * B * cs;                   // 8 KB
-    const size_t smem = (size_t)NS * slot + (size_t)(N + 64) * cs + (size_t)NS * 8 + 64;
-    NBK_CHECK_ARG(smem <= 227 * 1024, "fft_lines: ring of %d slots does not fit in shared memory", NS);
-    int per_sm = (int)((227 * 1024) / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 3) per_sm = 3;
+    // ring: R slots of the tile being transformed + P prefetch slots, sized for 2 CTAs / SM (3 at N = 256); the wide
+    // tile at N = 1024 takes the whole SM
+    const size_t slot = (size_t)64 * B * cs;
+    const size_t fixed = (size_t)(N + 64) * cs + 26 * 8 + 64;
+    int per_sm = (R == 16 && B == Bfull) ? 1 : (R == 4 ? 3 : 2);
+    int NS = (int)(((size_t)(226 * 1024) / per_sm - 1024 - fixed) / slot);
+    if (NS > 26) NS = 26;
+    if (NS > 2 * R) NS = 2 * R;
+    if (knob_ns >= R + 1 && knob_ns <= NS) NS = knob_ns;
+    NBK_CHECK_ARG(NS >= R + 1, "fft_lines: the slot ring does not fit in shared memory (N = %d)", N);
+    const size_t smem = (size_t)NS * slot + fixed;
     const int64_t tiles_inner = (n_inner + B - 1) / B;
     const int64_t n_tiles = tiles_inner * n_outer;
     const int64_t g = n_tiles < (int64_t)NBK_SM_COUNT * per_sm ? n_tiles : (int64_t)NBK_SM_COUNT * per_sm;
@@ -1132,18 +1278,21 @@ static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, 
     for (int i = 0; i < NBK_MAX_PEERS; i++) peers.p[i] = (peer_host && i < P) ? (C *)peer_host[i] : nullptr;
     const int n_per = peer_host ? N / P : N;
     const int64_t d_total = d_total_override ? d_total_override : (peer_host ? n_outer * P : 0);
-#define LAUNCH_TMA(RR, PEERF)                                                                                          \
+#define LAUNCH_TMA2(RR, BB, NTT, PEERF)                                                                                \
     do {                                                                                                               \
-        NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_tma<T, RR, PEERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_fft_lines_tma<T, RR, PEERF><<<(int)g, 32 * RR, smem, s>>>(tmap, (C *)dst, peers, (const C *)tw, line_stride, n_inner, \
+        NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_tma<T, RR, BB, NTT, PEERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_fft_lines_tma<T, RR, BB, NTT, PEERF><<<(int)g, NTT, smem, s>>>(tmap, (C *)dst, peers, (const C *)tw, line_stride, n_inner, \
             tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale, NS);                  \
     } while (0)
-    if (peer_host) {
-        if (R == 16) LAUNCH_TMA(16, true); else if (R == 8) LAUNCH_TMA(8, true); else LAUNCH_TMA(4, true);
-    } else {
-        if (R == 16) LAUNCH_TMA(16, false); else if (R == 8) LAUNCH_TMA(8, false); else LAUNCH_TMA(4, false);
-    }
+#define LAUNCH_TMA(RR, BB, NTT) do { if (peer_host) LAUNCH_TMA2(RR, BB, NTT, true); else LAUNCH_TMA2(RR, BB, NTT, false); } while (0)
+    constexpr int BF = 128 / (int)sizeof(C), BH = BF / 2;
+    if (R == 16 && B == BF) LAUNCH_TMA(16, BF, 512);
+    else if (R == 16) LAUNCH_TMA(16, BH, 256);
+    else if (R == 8 && B == BF) LAUNCH_TMA(8, BF, 256);
+    else if (R == 8) LAUNCH_TMA(8, BH, 256);
+    else LAUNCH_TMA(4, BF, 128);
 #undef LAUNCH_TMA
+#undef LAUNCH_TMA2
     NBK_LAUNCHED();
     *done = true;
     return NBK_OK;
@@ -1397,6 +1546,32 @@ static int launch_z(const void *in, void *out, int64_t rows, int Nz, bool forwar
     if (rc) return rc;
     rc = get_twiddle(Nz, dtype, s, &twN);
     if (rc) return rc;
+    if (forward && lines_mode() == 2 && (M == 128 || M == 256 || M == 512) && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+        ((size_t)Nz * sizeof(T)) % 16 == 0) {
+        // warp-per-row TMA pass: 12 warps, per-warp ring of row buffers filling the SM's shared memory
+        constexpr int NWZ = 12;
+        const size_t rowb = (size_t)M * sizeof(C);
+        const size_t twb = ((size_t)Nz + 7 * (M / 8) + 56) * sizeof(C);       // W_N | stage-1 table | stage-2 table
+        int nbuf = (int)(((size_t)224 * 1024 - twb - 1024) / (NWZ * rowb));
+        if (nbuf > 4) nbuf = 4;
+        if (nbuf < 2) nbuf = 2;
+        static int knob_nb = -1;
+        if (knob_nb < 0) { const char *e = getenv("NBK_FFT_Z_NBUF"); knob_nb = e ? atoi(e) : 0; }
+        if (knob_nb >= 1 && knob_nb <= nbuf) nbuf = knob_nb;
+        const size_t smem = twb + (size_t)NWZ * nbuf * rowb + (size_t)NWZ * nbuf * 8 + 128;
+        NBK_CHECK_ARG(smem <= 227 * 1024, "fft z pass: Nz=%d does not fit in shared memory", Nz);
+        int64_t g = (rows + NWZ - 1) / NWZ;
+        if (g > NBK_SM_COUNT) g = NBK_SM_COUNT;
+#define LAUNCH_ZT(LMM)                                                                                            \
+        do {                                                                                                      \
+            NBK_CUDA(cudaFuncSetAttribute(k_fft_z_r2c_tma<T, LMM, NWZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            k_fft_z_r2c_tma<T, LMM, NWZ><<<(int)g, 32 * NWZ, smem, s>>>((const T *)in, (C *)out, (const C *)twN, rows, (T)scale, nbuf); \
+        } while (0)
+        if (M == 512) LAUNCH_ZT(9); else if (M == 256) LAUNCH_ZT(8); else LAUNCH_ZT(7);
+#undef LAUNCH_ZT
+        NBK_LAUNCHED();
+        return NBK_OK;
+    }
     if (forward && M >= 64 && M <= 256 * (sizeof(T) == 4 ? 16 : 8) && use_reg_lines(M)) {   // the tile must fit the registers
         // register-I/O variant: 256 threads hold the whole tile across the last stage (M * B <= 256 V)
         const int V = sizeof(T) == 4 ? 16 : 8;

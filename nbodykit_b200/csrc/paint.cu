@@ -550,7 +550,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
 }
 
 // workspace header words
-enum { HDR_QUEUE = 0, HDR_ABSMAX = 1, HDR_MODE = 2, HDR_WORDS = 64 };
+enum { HDR_QUEUE = 0, HDR_ABSMAX = 1, HDR_MODE = 2, HDR_DEFER = 3, HDR_WORDS = 64 };
 
 struct BucketPlan {          // one bucketing configuration (host side, by value)
     int mode;                // value of the probe flag that selects this configuration
@@ -559,6 +559,8 @@ struct BucketPlan {          // one bucketing configuration (host side, by value
     int64_t chunk;           // particles per chunk, multiple of 4
     int staged;              // particle coordinates staged by TMA bulk copies (needs a 16-byte aligned array)
     int nst;                 // slots of the staging ring
+    int wstage;              // scatter pass: records leave through a per-warp shared-memory transposition (coalesced stores)
+    int stage_off;           // ... byte offset of the warps' staging areas in dynamic shared memory
 };
 
 // Is the catalogue spatially coherent in array order?  256 threads sample neighbouring pairs (i, i+1): coherent pairs
@@ -872,13 +874,39 @@ k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int 
                     if (out) slot[u] = offsets[t[u]] + cnt_w[t[u]] + so;     // outliers follow the windowed shares
                 }
             }
+            if (bp.wstage) {
+                // Coalesced record stores.  A lane's quad is 12 words at 4 (mostly consecutive) slots: written straight
+                // from the registers, every STG of the warp touches ~30 sectors (4 bytes each, 48 bytes apart) and the L1
+                // store path -- not DRAM -- bounds the pass.  Instead the warp parks its 128 records (+ their slots) in
+                // shared memory and writes them back word-by-word in record order: consecutive lanes then hold
+                // consecutive words of consecutive slots, i.e. 128 contiguous bytes per STG inside a run of equal tiles.
+                unsigned *st = reinterpret_cast<unsigned *>(s_raw + bp.stage_off) + (threadIdx.x >> 5) * 512;
+                const int lane = threadIdx.x & 31;
+                uint4 *sv = reinterpret_cast<uint4 *>(st + 12 * lane);
+                sv[0] = make_uint4(r[0][0], r[0][1], r[0][2], r[1][0]);
+                sv[1] = make_uint4(r[1][1], r[1][2], r[2][0], r[2][1]);
+                sv[2] = make_uint4(r[2][2], r[3][0], r[3][1], r[3][2]);
+                reinterpret_cast<uint4 *>(st + 384)[lane] = make_uint4(t[0] >= 0 ? slot[0] : 0xffffffffu, t[1] >= 0 ? slot[1] : 0xffffffffu,
+                                                                        t[2] >= 0 ? slot[2] : 0xffffffffu, t[3] >= 0 ? slot[3] : 0xffffffffu);
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 12; j++) {
+                    const int w = j * 32 + lane;
+                    const int rid = w / 3;
+                    const unsigned sl = st[384 + rid];
+                    if (sl != 0xffffffffu) recs[3 * (size_t)sl + (unsigned)(w - 3 * rid)] = st[w];
+                }
+                __syncwarp();                                  // the next round overwrites the staging area
+            }
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if (t[u] >= 0) {
-                    // 12-byte records, three 4-byte stores: a 16-byte record (one vector store / load) makes THIS pass
-                    // 10 % faster but the tile pass 25 % slower -- it is the DRAM bytes that count (profiles/r02_paint.md)
-                    unsigned *dst = recs + 3 * (size_t)slot[u];
-                    dst[0] = r[u][0]; dst[1] = r[u][1]; dst[2] = r[u][2];
+                    // 12-byte records (a 16-byte record, one vector store / load, makes the tile pass 25 % slower: it is
+                    // the DRAM bytes that count)
+                    if (!bp.wstage) {
+                        unsigned *dst = recs + 3 * (size_t)slot[u];
+                        dst[0] = r[u][0]; dst[1] = r[u][1]; dst[2] = r[u][2];
+                    }
                     if (mass) {
                         if (mass_f4) ((float *)smass)[slot[u]] = ((const float *)mass)[b + j0 + u];
                         else ((double *)smass)[slot[u]] = ((const double *)mass)[b + j0 + u];
@@ -985,6 +1013,12 @@ __device__ __forceinline__ double limbs_to_double(unsigned lo, unsigned hi) {
     return __fma_rn(dhi, 4294967296.0, dlo);
 }
 
+__host__ __device__ constexpr int tile_plane_pitch(int sup, int flush, int R, int RP) {
+    int ps = R * RP;
+    if (sup == 2 && flush == 0) ps += (8 - (ps & 31) + 32) & 31;     // even: R * RP and 8 are
+    return ps;
+}
+
 // FLUSH 0: ordered write-back: of all tiles touching a cell the first in queue order stores it (plain coalesced
 //          stores), the later ones add (REDG, L2-resident) after the earlier tiles have published their stores; no
 //          cleared mesh needed, every cell is written exactly once.  Interior tiles (the common case) store their own
@@ -998,14 +1032,18 @@ template <int SUP, typename MT, typename FT, bool SHIFTED, int FLUSH>
 __global__ void __launch_bounds__(256, FLUSH == 0 ? 4 : 1)
 k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, TileGeom tg,
              const unsigned *__restrict__ offsets, unsigned *__restrict__ hdr, unsigned *__restrict__ flags,
-             unsigned epoch, int knobs, FT *__restrict__ mesh) {
+             unsigned epoch, int knobs, FT *__restrict__ mesh, unsigned *__restrict__ d_off, FT *__restrict__ d_val,
+             unsigned d_cap) {
     extern __shared__ __align__(16) unsigned s_all[];
     const int spread = knobs & 1;                  // diagnosis knobs: bit 0 = spread lanes, bit 1 = acquire-load polling
     const bool poll_relaxed = !(knobs & 2);
     constexpr int R = TILE + SUP - 1 + (SHIFTED ? 1 : 0);   // == tg.R
     // row pitch in cells: the TMA write-back needs rows that start 16-byte aligned, the ordered one 8-byte cell pairs
     constexpr int RP = FLUSH == 0 ? ((R + 1) & ~1) : ((R + 3) & ~3);
-    constexpr int NC = R * R * RP;
+    // x-plane pitch.  CIC, ordered write-back: padded so that the 8 corners of a stencil fall into 8 different banks
+    // (offsets {0, 1, RP, RP+1} + {0, PS}: PS = 8 mod 32 with RP = 18), see the rotated deposit order in accumulate()
+    constexpr int PS = tile_plane_pitch(SUP, FLUSH, R, RP);
+    constexpr int NC = R * PS;
     constexpr int BUFW = (2 * NC + 3) & ~3;                  // words of the accumulator (lo | hi limbs)
     constexpr int H = R - TILE;   // cells with a local coordinate < H are also written by the preceding tile
     constexpr int CAP = R * R * R - TILE * TILE * TILE;      // halo cells = what an interior tile adds
@@ -1030,6 +1068,14 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
     const bool small_mesh = (int64_t)tg.gm.x_n * tg.gm.n[1] * tg.gm.n[2] < (1ll << 32);   // 32-bit stash offsets
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
+    constexpr bool ROT = (SUP == 2 && FLUSH == 0);
+    const int rot = ROT ? (int)(lane & 7) : 0;
+    int coff[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int c = j ^ rot;
+        coff[j] = (c >> 2) * PS + ((c >> 1) & 1) * RP + (c & 1);
+    }
     // deposits of the records [b, e) of one bucket into the accumulator
     auto accumulate = [&](unsigned b, unsigned e) {
         // Particle -> thread map.  spread == 0: thread p takes records p, p + NT, ... (coalesced).  spread != 0: the
@@ -1070,7 +1116,20 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                 double fr = (__hiloint2double(0x43300000, (int)u[d]) - 4503599627370496.0) * 2.3283064365386963e-10;
                 WinD<SUP>::eval(WinD<SUP>::DMIN != 0.0 ? WinD<SUP>::DMIN + fr : fr, w[d]);
             }
-            const int base0 = (l[0] * R + l[1]) * RP + l[2];
+            if (ROT) {
+                // lane-rotated corner order: this lane deposits corner j ^ rot at step j (weights exchanged per axis, offsets
+                // in coff): the neighbouring records of a spatially coherent catalogue share their stencil cells, and in the
+                // same order all their lanes would hit the same word in every ATOMS; rotated, eight neighbours hit the eight
+                // corners, which the padded plane pitch keeps in eight different banks
+#pragma unroll
+                for (int d = 0; d < 3; d++) {
+                    const bool sw = (rot >> (2 - d)) & 1;
+                    const double w0 = w[d][0], w1 = w[d][SUP - 1];
+                    w[d][0] = sw ? w1 : w0;
+                    w[d][SUP - 1] = sw ? w0 : w1;
+                }
+            }
+            const int base0 = l[0] * PS + l[1] * RP + l[2];
             const double m = smass ? (double)mcur : 1.0;
             const double mS = m * S;
             double wz[SUP];
@@ -1086,7 +1145,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
 #pragma unroll
                         for (int rz = 0; rz < SUP; rz++) {
                             unsigned q = (unsigned)__double2loint(__fma_rn(wxy, wz[rz], 4503599627370496.0));
-                            fixed_add_pos(s_lo, s_hi, base0 + (rx * R + ry) * RP + rz, q);
+                            fixed_add_pos(s_lo, s_hi, base0 + (ROT ? coff[(rx * 2 + ry) * 2 + rz] : rx * PS + ry * RP + rz), q);
                         }
                     }
             } else {
@@ -1097,7 +1156,8 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                         double wxy = w[0][rx] * w[1][ry];
 #pragma unroll
                         for (int rz = 0; rz < SUP; rz++)
-                            fixed_add(s_lo, s_hi, base0 + (rx * R + ry) * RP + rz, __double2ll_rn(wxy * wz[rz]));
+                            fixed_add(s_lo, s_hi, base0 + (ROT ? coff[(rx * 2 + ry) * 2 + rz] : rx * PS + ry * RP + rz),
+                                      __double2ll_rn(wxy * wz[rz]));
                     }
             }
         }
@@ -1191,6 +1251,25 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
         __syncwarp();
         if (poll_relaxed) fence_acq_rel_gpu();
     };
+    // one look at the same flags, no waiting (warp-uniform result)
+    auto earlier_ready = [&](const TileBox &bx) -> bool {
+        bool ok = true;
+        if (lane < 27) {
+            int sel[3] = {(int)lane % 3, ((int)lane / 3) % 3, (int)lane / 9};
+            int nb[3];
+            bool valid = lane != 0;
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                if (sel[d] == 0) nb[d] = bx.tc[d];
+                else if (sel[d] == 1) { nb[d] = bx.tc[d] + 1; valid = valid && bx.fhi[d] < R; }
+                else { nb[d] = tg.nt[d] - 1; valid = valid && bx.flo[d] > 0 && bx.tc[d] != tg.nt[d] - 1; }
+            }
+            if (valid) ok = ld_relaxed(&flags[(nb[0] * tg.nt[1] + nb[1]) * tg.nt[2] + nb[2]]) >= epoch;
+        }
+        ok = __all_sync(0xffffffffu, ok);
+        if (ok) fence_acq_rel_gpu();
+        return ok;
+    };
     // warp-aggregated append of (mesh offset, value) to the stash
     auto stash_push = [&](bool keep, unsigned off, FT val, unsigned *counter) {
         const unsigned mask = __ballot_sync(0xffffffffu, keep);
@@ -1218,9 +1297,35 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
         // accumulation phase to publish, so the flag poll is almost never a wait
         if (t >= 0) accumulate(offsets[t], offsets[t + 1]);
         if (pending) {
-            poll_earlier(pbox);
+            // The parked set goes onto blocks that EARLIER tiles store.  Normally they have published long ago; where one
+            // has not (a dense neighbour still accumulating), the warp does not wait: it moves its share of the set to the
+            // deferred list, which k_apply_deferred adds after this kernel.  (List full: wait as before.)
             const unsigned n = s_nst[pbuf];
-            for (unsigned i = threadIdx.x; i < n; i += NT) atomicAdd(mesh + s_soff[i], s_sval[i]);
+            const bool ready = earlier_ready(pbox);
+            bool defer = false;
+            unsigned dbase = 0;
+            if (!ready && d_cap) {
+                unsigned tot = 0;
+                for (unsigned i0 = wid * 32; i0 < n; i0 += NT) tot += min(32u, n - i0);
+                if (lane == 0 && tot) dbase = atomicAdd(&hdr[HDR_DEFER], tot);
+                dbase = __shfl_sync(0xffffffffu, dbase, 0);
+                defer = true;
+                if (dbase + tot > d_cap || dbase + tot < dbase) {         // does not fit: neutral entries up to the cap, then wait
+                    for (unsigned j = dbase + lane; j < d_cap && j - dbase < tot; j += 32) { d_off[j] = 0u; d_val[j] = (FT)0; }
+                    defer = false;
+                }
+            }
+            if (defer) {
+                unsigned run = dbase;
+                for (unsigned i0 = wid * 32; i0 < n; i0 += NT) {
+                    const unsigned i = i0 + lane;
+                    if (i < n) { d_off[run + lane] = s_soff[i]; d_val[run + lane] = s_sval[i]; }
+                    run += min(32u, n - i0);
+                }
+            } else {
+                if (!ready) poll_earlier(pbox);
+                for (unsigned i = threadIdx.x; i < n; i += NT) atomicAdd(mesh + s_soff[i], s_sval[i]);
+            }
         }
         if (t < 0) break;
         __syncthreads();                                                 // barrier 1 of 2
@@ -1236,7 +1341,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
             {
                 const int row0 = (int)threadIdx.x >> 3, cz = ((int)threadIdx.x & 7) * 2;
                 const int cy = row0 & 15, cx0 = row0 >> 4;
-                int si = (cx0 * R + cy) * RP + cz;
+                int si = cx0 * PS + cy * RP + cz;
                 int lx = bx.o[0] + cx0;                                   // slab-local x (full mesh: the global one)
                 int64_t o64 = ((int64_t)lx * tg.gm.n[1] + (bx.o[1] + cy)) * tg.gm.n[2] + (bx.o[2] + cz);
                 const int64_t ostep = 2 * (int64_t)tg.gm.n[1] * tg.gm.n[2];
@@ -1251,7 +1356,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                         if (sizeof(FT) == 8) *reinterpret_cast<double2 *>(mesh + o64) = make_double2((double)v0, (double)v1);
                         else *reinterpret_cast<float2 *>(mesh + o64) = make_float2((float)v0, (float)v1);
                     }
-                    si += 2 * R * RP;
+                    si += 2 * PS;
                     lx += 2;
                     o64 += ostep;
                 }
@@ -1264,7 +1369,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                 FT val = (FT)0;
                 if (HK > 0 && hcell[k] >= 0) {
                     const int cx = hcell[k] >> 16, cy = (hcell[k] >> 8) & 255, cz = hcell[k] & 255;
-                    const int si = (cx * R + cy) * RP + cz;
+                    const int si = cx * PS + cy * RP + cz;
                     const unsigned lo = s_lo[si], hi = s_hi[si];
                     if ((lo | hi) != 0u) {
                         s_lo[si] = 0u;
@@ -1311,7 +1416,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                                            cz >= bx.flo[2] && cz < bx.fhi[2];
                         int64_t o64;
                         if ((first == (pass == 0) || (pass == 0 && park)) && locate(cx, cy, cz, o64)) {
-                            const int si = (cx * R + cy) * RP + cz;
+                            const int si = cx * PS + cy * RP + cz;
                             const unsigned lo = s_lo[si], hi = s_hi[si];
                             val = (FT)(limbs_to_double(lo, hi) * invS);
                             if (first) mesh[o64] = val;
@@ -1342,6 +1447,19 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
         if (threadIdx.x == 0) st_release(&flags[t], epoch);              // cumulative over the CTA's stores (bar.sync)
         if (pending) { pbox = bx; pbuf = cbuf; }
         t = tg.ntiles - 1 - s_tile;
+    }
+}
+
+// adds the deferred halo sets (see k_tile_paint) once every tile has stored
+template <typename FT>
+__global__ void __launch_bounds__(256)
+k_apply_deferred(const unsigned *__restrict__ hdr, const unsigned *__restrict__ d_off, const FT *__restrict__ d_val, unsigned d_cap,
+                 FT *__restrict__ mesh) {
+    unsigned n = hdr[HDR_DEFER];
+    if (n > d_cap) n = d_cap;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const FT v = d_val[i];
+        if (v != (FT)0) atomicAdd(mesh + d_off[i], v);
     }
 }
 
@@ -1409,6 +1527,11 @@ static void make_plans(int64_t n, const int *nt, int ntiles, size_t pos_size, bo
     size_t ring = (size_t)coh.nst * 4 * threads_coh * 3 * pos_size;
     coh.staged = (aligned && env_int("NBK_PAINT_STAGED", 0) && align128((size_t)coh.W * 4) + ring <= 224 * 1024) ? 1 : 0;
     smem_coh = align128((size_t)coh.W * 4) + (coh.staged ? ring : 0);
+    coh.wstage = env_int("NBK_PAINT_WSTAGE", 1) ? 1 : 0;          // per-warp record transposition (2 KB per warp)
+    coh.stage_off = (int)smem_coh;
+    if (coh.wstage) smem_coh += (size_t)(threads_coh / 32) * 2048;
+    sca.wstage = 0;                                                // scattered input: every record goes to another tile anyway
+    sca.stage_off = 0;
     sca.mode = 0;
     sca.W = ntiles < NBK_BLK_SMEM / 4 ? ntiles : NBK_BLK_SMEM / 4;
     plan_chunks(sca, n, NBK_CHUNKS_SCATTERED);
@@ -1417,6 +1540,14 @@ static void make_plans(int64_t n, const int *nt, int ntiles, size_t pos_size, bo
     ring = (size_t)sca.nst * 4 * threads_sca * 3 * pos_size;
     sca.staged = (aligned && env_int("NBK_PAINT_STAGED", 0) && align128((size_t)sca.W * 4) + ring <= 224 * 1024) ? 1 : 0;
     smem_sca = align128((size_t)sca.W * 4) + (sca.staged ? ring : 0);
+}
+
+// capacity of the deferred-add list: a quarter of the tiles may park a full CIC halo (anything beyond waits instead)
+static size_t nbk_defer_cap(int64_t ntiles) {
+    size_t c = (size_t)ntiles * 208;
+    if (c < (1u << 20)) c = 1u << 20;
+    if (c > 0xfff00000u) c = 0xfff00000u;
+    return c;
 }
 
 extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_dtype, const int64_t *nmesh,
@@ -1432,6 +1563,7 @@ extern "C" int64_t nbk_paint_tiled_workspace(int64_t n, int pos_dtype, int mass_
     bytes += align256(sizeof(unsigned) * (size_t)blk);                   // per-chunk bucket shares
     bytes += align256((size_t)n * 12);                                   // 12-byte records
     if (mass_dtype) bytes += align256((size_t)n * (mass_dtype == NBK_F4 ? 4 : 8));
+    bytes += 2 * align256((size_t)nbk_defer_cap(nt) * 8);                // deferred halo adds: offsets (u32) and values (<= f8)
     return (int64_t)bytes;
 }
 
@@ -1465,6 +1597,10 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     }
     unsigned *recs = (unsigned *)w; w += align256((size_t)n * 12);
     MT *smass = mass ? (MT *)w : nullptr;
+    if (mass) w += align256((size_t)n * sizeof(MT));
+    const unsigned d_cap = env_int("NBK_PAINT_DEFER", 1) ? (unsigned)nbk_defer_cap(tg.ntiles) : 0u;
+    unsigned *d_off = (unsigned *)w; w += align256((size_t)nbk_defer_cap(tg.ntiles) * 8);
+    FT *d_val = (FT *)w; w += align256((size_t)nbk_defer_cap(tg.ntiles) * 8);
     const int mass_f4 = sizeof(MT) == 4;
     int force_mode;
     {
@@ -1482,15 +1618,16 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     // Coherent plan: every resident CTA gets the same number of chunks in BOTH passes (their occupancies differ:
     // the scatter pass needs more registers), else the last partial wave runs at a fraction of the machine.
     int occ_c = 1, occ_s = 1;
+    const size_t sm_cnt = coh.wstage ? (size_t)coh.stage_off : sm_c;      // the count pass does not need the record staging
     if (coh.staged) {
         NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
         NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, true>, th_c, sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, true>, th_c, sm_cnt));
         NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, true>, th_c, sm_c));
     } else {
         NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
         NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, false>, th_c, sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, false>, th_c, sm_cnt));
         NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, false>, th_c, sm_c));
     }
     if (occ_c < 1) occ_c = 1;
@@ -1506,14 +1643,14 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     const int grid_c = coh.nchunks < occ_c * NBK_SM_COUNT ? coh.nchunks : occ_c * NBK_SM_COUNT;
     const int grid_cs = coh.nchunks < occ_s * NBK_SM_COUNT ? coh.nchunks : occ_s * NBK_SM_COUNT;
     const int grid_s = sca.nchunks < NBK_SM_COUNT ? sca.nchunks : NBK_SM_COUNT;
-#define LAUNCH_BUCKET(KERN, GRIDC, ...)                                                                                      \
+#define LAUNCH_BUCKET(KERN, GRIDC, SMC, ...)                                                                                      \
     do {                                                                                                              \
         if (coh.staged) {                                                                                             \
-            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c)); \
-            KERN<SUP, PT, true><<<GRIDC, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                         \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMC))); \
+            KERN<SUP, PT, true><<<GRIDC, th_c, SMC, s>>>(__VA_ARGS__, coh);                                          \
         } else {                                                                                                      \
-            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c)); \
-            KERN<SUP, PT, false><<<GRIDC, th_c, sm_c, s>>>(__VA_ARGS__, coh);                                        \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMC))); \
+            KERN<SUP, PT, false><<<GRIDC, th_c, SMC, s>>>(__VA_ARGS__, coh);                                         \
         }                                                                                                             \
         NBK_LAUNCHED();                                                                                               \
         if (sca.staged) {                                                                                             \
@@ -1528,10 +1665,10 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         NBK_LAUNCHED();                                                                                               \
     } while (0)
     // (the plan is the LAST kernel argument of both passes so that one macro serves them)
-    LAUNCH_BUCKET(k_bucket_count, grid_c, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, cnt_w, cnt_o, blk, win_lo);
+    LAUNCH_BUCKET(k_bucket_count, grid_c, sm_cnt, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, cnt_w, cnt_o, blk, win_lo);
     k_tile_scan<<<1, 1024, 0, s>>>(cnt_w, cnt_o, offsets, cur_o, flags, hdr, tg.ntiles);
     NBK_LAUNCHED();
-    LAUNCH_BUCKET(k_bucket_scatter, grid_cs, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
+    LAUNCH_BUCKET(k_bucket_scatter, grid_cs, sm_c, (const PT *)pos, mass, mass_f4, n, tg, ft, hdr, offsets, cnt_w, cur_o, blk, win_lo, recs,
                   (void *)smass);
 #undef LAUNCH_BUCKET
     int spread_mode;
@@ -1545,7 +1682,7 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
 #define LAUNCH_TP(SH, FL, MESHP, EPOCH)                                                                                \
     do {                                                                                                              \
         const int Rr = TILE + SUP - 1 + ((SH) ? 1 : 0), RPr = (FL) == 0 ? ((Rr + 1) & ~1) : ((Rr + 3) & ~3);                       \
-        size_t smem = (size_t)((2 * Rr * Rr * RPr + 3) & ~3) * sizeof(unsigned);                                      \
+        size_t smem = (size_t)((2 * Rr * tile_plane_pitch(SUP, FL, Rr, RPr) + 3) & ~3) * sizeof(unsigned);            \
         if ((FL) == 0) smem += (size_t)(Rr * Rr * Rr - TILE * TILE * TILE) * (sizeof(FT) + sizeof(unsigned));        \
         NBK_CUDA(cudaFuncSetAttribute(k_tile_paint<SUP, MT, FT, SH, FL>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                       (int)smem));                                                                    \
@@ -1555,13 +1692,19 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
         int grid = NBK_SM_COUNT * per_sm;                                                                             \
         if (grid > tg.ntiles) grid = tg.ntiles;                                                                       \
         k_tile_paint<SUP, MT, FT, SH, FL><<<grid, 256, smem, s>>>(recs, smass, tg, offsets, hdr, flags, EPOCH,         \
-                                                                  spread_mode, (FT *)(MESHP));                        \
+                                                                  spread_mode, (FT *)(MESHP), d_off, d_val,           \
+                                                                  (FL) == 0 ? d_cap : 0u);                            \
         NBK_LAUNCHED();                                                                                               \
+        if ((FL) == 0 && d_cap) {                                                                                     \
+            k_apply_deferred<FT><<<NBK_SM_COUNT * 4, 256, 0, s>>>(hdr, d_off, d_val, d_cap, (FT *)(MESHP));           \
+            NBK_LAUNCHED();                                                                                           \
+        }                                                                                                             \
     } while (0)
     if (shift != 0.0) { if (clear) LAUNCH_TP(true, 0, mesh, 1u); else LAUNCH_TP(true, 1, mesh, 1u); }
     else { if (clear) LAUNCH_TP(false, 0, mesh, 1u); else LAUNCH_TP(false, 1, mesh, 1u); }
     if (mesh2) {
         NBK_CUDA(cudaMemsetAsync(&hdr[HDR_QUEUE], 0, sizeof(unsigned), s));
+        NBK_CUDA(cudaMemsetAsync(&hdr[HDR_DEFER], 0, sizeof(unsigned), s));
         if (clear) LAUNCH_TP(true, 0, mesh2, 2u); else LAUNCH_TP(true, 1, mesh2, 2u);
     }
 #undef LAUNCH_TP
