@@ -201,7 +201,7 @@ int nbk_interlace_combine(void *c1, const void *c2, int dtype, const int64_t *nm
  * hermitian == 0).  coord_unit_host: per-axis coordinate of index 1 (NULL -> 2 pi / L, the wavenumbers; FFTCorr
  * passes the cell size L/N so that coordinates are the wrapped separations).
  * Outputs (device, ACCUMULATED into; zero first), nb = (Nx+2)*(Nmu+2):
- *   nsum int64[nb]; xsum, musum double[nb]; ysum double[Nell][nb][2] (re, im). */
+ *   nsum int64[nb]; xsum, musum double[nb]; ysum double[Nell][nb][2] (re, im).  * musum may be NULL when the caller never reads the per-bin sum of mu (FFTPower mode='1d'): that reduction is then skipped. */
 int nbk_power_bin(const void *c1, const void *c2, int dtype, int is_p3d, double volume,
                   int clear_zero, const int64_t *nmesh_host, const double *boxsize_host,
                   int transposed, int64_t start, int64_t count, int coord_dtype,

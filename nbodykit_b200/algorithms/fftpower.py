@@ -151,7 +151,8 @@ class FFTPower(FFTBase):
         coords = [kcoords, None]
         result, pole_result = project_to_basis_device(
             c1, edges, poles=self.attrs['poles'], los=self.attrs['los'], second=None if c2 is c1 else c2,
-            is_p3d=False, volume=float(self.attrs['BoxSize'].prod()), compensation=self._deferred_compensation)
+            is_p3d=False, volume=float(self.attrs['BoxSize'].prod()), compensation=self._deferred_compensation,
+            need_mu=(self.attrs['mode'] != "1d"))
 
         if self.attrs['mode'] == "1d":
             cols = ['k', 'power', 'modes']
@@ -283,7 +284,8 @@ def _los_coord_mode(los, coord_dtype):
 
 
 def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4", is_p3d=True, second=None,
-                            volume=1.0, compensation=(None, None), clear_zero=True, antihermitian=False, mirror=None):
+                            volume=1.0, compensation=(None, None), clear_zero=True, antihermitian=False, mirror=None,
+                            need_mu=True):
     """
     project_to_basis (fftpower.py:507-701) for a device ComplexField.
 
@@ -358,7 +360,7 @@ def project_to_basis_device(y3d, edges, los=[0, 0, 1], poles=[], coord_dtype="f4
             _los_coord_mode(los, coord_dtype), _lib.darr(x2edges), Nx, _lib.darr(muedges), Nmu, _lib.darr(los_f),
             _lib.i32arr(_poles), Nell, herm, _lib.COMP.get(compensation[0], 0),
             _lib.COMP.get(compensation[1], 0), 1 if is_real else 0, coord_unit,
-            _ptr(nsum), _ptr(xsum), _ptr(musum), _ptr(ysum), _stream()), "nbk_power_bin")
+            _ptr(nsum), _ptr(xsum), _ptr(musum) if need_mu else None, _ptr(ysum), _stream()), "nbk_power_bin")
     with stage("H:bin_reduce"):
         if comm.size > 1:
             comm.allreduce_tensor(nsum)

@@ -312,6 +312,8 @@ struct BinParams {
     int stage_edges; // the k edges fit in shared memory
     const void *c3;  // optional: the field that stands for c2 at the UNSTORED mirror mode -k (see nbk_power_bin2)
     int estride;     // 2: complex input (re, im interleaved)   1: real input (a RealField statistic, FFTCorr)
+    int need_mu;     // accumulate sum(mu) per bin (musum != NULL); FFTPower mode='1d' never reads it
+    int real_stat;   // the statistic is real by construction (auto power c1 conj(c1), no mirror field): no imaginary reduction
     double volume;
 };
 
@@ -549,11 +551,11 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                 for (int o = 16; o > 0; o >>= 1) {
                     wcnt += __shfl_xor_sync(0xffffffffu, wcnt, o);
                     xs += __shfl_xor_sync(0xffffffffu, xs, o);
-                    ms += __shfl_xor_sync(0xffffffffu, ms, o);
+                    if (P.need_mu) ms += __shfl_xor_sync(0xffffffffu, ms, o);
 #pragma unroll
                     for (int l = 0; l < NELL; l++) {
                         yr[l] += __shfl_xor_sync(0xffffffffu, yr[l], o);
-                        yi[l] += __shfl_xor_sync(0xffffffffu, yi[l], o);
+                        if (!P.real_stat) yi[l] += __shfl_xor_sync(0xffffffffu, yi[l], o);
                     }
                 }
             } else {
@@ -575,13 +577,19 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     bool take = (lane + o < 32) && (so == seg);
                     unsigned c_o = __shfl_down_sync(0xffffffffu, wcnt, o);
                     double x_o = __shfl_down_sync(0xffffffffu, xs, o);
-                    double m_o = __shfl_down_sync(0xffffffffu, ms, o);
-                    if (take) { wcnt += c_o; xs += x_o; ms += m_o; }
+                    if (take) { wcnt += c_o; xs += x_o; }
+                    if (P.need_mu) {
+                        double m_o = __shfl_down_sync(0xffffffffu, ms, o);
+                        if (take) ms += m_o;
+                    }
 #pragma unroll
                     for (int l = 0; l < NELL; l++) {
                         double r_o = __shfl_down_sync(0xffffffffu, yr[l], o);
-                        double i_o = __shfl_down_sync(0xffffffffu, yi[l], o);
-                        if (take) { yr[l] += r_o; yi[l] += i_o; }
+                        if (take) yr[l] += r_o;
+                        if (!P.real_stat) {
+                            double i_o = __shfl_down_sync(0xffffffffu, yi[l], o);
+                            if (take) yi[l] += i_o;
+                        }
                     }
                 }
             }
@@ -589,7 +597,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                 if (SMEM_ACC) atomicAdd(&s_n[key], wcnt);
                 else atomicAdd(&g_nsum[key], (unsigned long long)wcnt);
                 acc_add<SMEM_ACC>(&a_x[key], xs);
-                acc_add<SMEM_ACC>(&a_m[key], ms);
+                if (P.need_mu) acc_add<SMEM_ACC>(&a_m[key], ms);
 #pragma unroll
                 for (int l = 0; l < NELL; l++) {
                     acc_add<SMEM_ACC>(&a_y[((size_t)l * P.nb + key) * 2], yr[l]);
@@ -606,7 +614,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
             unsigned c = s_n[i];
             if (c) atomicAdd(&g_nsum[i], (unsigned long long)c);
             if (s_x[i] != 0.0) atomicAdd(&g_xsum[i], s_x[i]);
-            if (s_m[i] != 0.0) atomicAdd(&g_musum[i], s_m[i]);
+            if (P.need_mu && s_m[i] != 0.0) atomicAdd(&g_musum[i], s_m[i]);
         }
         for (int i = threadIdx.x; i < NELL * P.nb * 2; i += blockDim.x)
             if (s_y[i] != 0.0) atomicAdd(&g_ysum[i], s_y[i]);
@@ -746,6 +754,8 @@ static int power_bin_impl(const void *c1, const void *c2, const void *c3, int dt
     P.has_c2 = (c2 != nullptr && c2 != c1) ? 1 : 0;
     P.c3 = (c3 != nullptr && hermitian && !is_p3d && !real_input) ? c3 : nullptr;
     P.volume = volume;
+    P.need_mu = musum != nullptr ? 1 : 0;
+    P.real_stat = (!is_p3d && !real_input && !P.has_c2 && P.c3 == nullptr) ? 1 : 0;    // |c1|^2 V: the imaginary part is exactly 0
     cudaStream_t s = (cudaStream_t)stream;
     double *d_k2, *d_mu;
     if ((rc = get_edges(k2edges, Nx + 1, s, &d_k2))) return rc;

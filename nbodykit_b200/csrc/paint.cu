@@ -450,7 +450,17 @@ template <int SUP, typename PT>
 __device__ __forceinline__ int tile_fast(const PT *x, const TileGeom &tg, const FastTile &ft, bool &ok) {
     ok = sizeof(PT) == 4;
     int c[3] = {0, 0, 0};
-    if (sizeof(PT) == 4) {
+    if (sizeof(PT) == 4 && ft.pow2) {
+        // N/L a power of two: g = x * scale (and g + 1/2) is exact in float32, so floor(g) IS the f8 result -- no margin test
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            float g = (float)x[d] * ft.sc[d];
+            if (WinOff<SUP>::A != 0.f) g += WinOff<SUP>::A;
+            ok = ok && (fabsf(g) < 4194304.0f);                  // also false for NaN / inf
+            c[d] = __float2int_rd(g) + WinOff<SUP>::B;
+            ok = ok && ((unsigned)c[d] < (unsigned)tg.gm.n[d]);
+        }
+    } else if (sizeof(PT) == 4) {
 #pragma unroll
         for (int d = 0; d < 3; d++) {
             float g = (float)x[d] * ft.sc[d];
