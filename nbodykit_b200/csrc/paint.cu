@@ -430,9 +430,7 @@ __device__ __forceinline__ int make_record_pow2(const float *x, const TileGeom &
             u28 += 1u << 27;
             if (u28 >= (1u << 28)) { u28 -= 1u << 28; ci += 1; }
         }
-        int cc = ci + WinOff<SUP>::B;
-        if (cc < 0) cc += tg.gm.n[d];
-        else if (cc >= tg.gm.n[d]) cc -= tg.gm.n[d];
+        const int cc = ci + WinOff<SUP>::B;                  // a stencil that starts outside [0, n) wraps in the exact path
         ok = ok && ((unsigned)cc < (unsigned)tg.gm.n[d]);
         c[d] = cc;
         u[d] = u28 << 4;
@@ -887,24 +885,28 @@ k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int 
             if (bp.wstage) {
                 // Coalesced record stores.  A lane's quad is 12 words at 4 (mostly consecutive) slots: written straight
                 // from the registers, every STG of the warp touches ~30 sectors (4 bytes each, 48 bytes apart) and the L1
-                // store path -- not DRAM -- bounds the pass.  Instead the warp parks its 128 records (+ their slots) in
-                // shared memory and writes them back word-by-word in record order: consecutive lanes then hold
-                // consecutive words of consecutive slots, i.e. 128 contiguous bytes per STG inside a run of equal tiles.
+                // store path -- not DRAM -- bounds the pass.  Instead the warp parks its 128 records (+ their word
+                // offsets) in shared memory and writes them back with consecutive lanes on consecutive records.  (Word-by-
+                // word order -- 128 contiguous bytes per STG -- needs a division by 3 per word and measured issue-bound.)
                 unsigned *st = reinterpret_cast<unsigned *>(s_raw + bp.stage_off) + (threadIdx.x >> 5) * 512;
                 const int lane = threadIdx.x & 31;
-                uint4 *sv = reinterpret_cast<uint4 *>(st + 12 * lane);
-                sv[0] = make_uint4(r[0][0], r[0][1], r[0][2], r[1][0]);
-                sv[1] = make_uint4(r[1][1], r[1][2], r[2][0], r[2][1]);
-                sv[2] = make_uint4(r[2][2], r[3][0], r[3][1], r[3][2]);
-                reinterpret_cast<uint4 *>(st + 384)[lane] = make_uint4(t[0] >= 0 ? slot[0] : 0xffffffffu, t[1] >= 0 ? slot[1] : 0xffffffffu,
-                                                                        t[2] >= 0 ? slot[2] : 0xffffffffu, t[3] >= 0 ? slot[3] : 0xffffffffu);
-                __syncwarp();
+                // three word planes [k][record] + the records' word offsets 3 * slot (0xffffffff: no record)
 #pragma unroll
-                for (int j = 0; j < 12; j++) {
-                    const int w = j * 32 + lane;
-                    const int rid = w / 3;
-                    const unsigned sl = st[384 + rid];
-                    if (sl != 0xffffffffu) recs[3 * (size_t)sl + (unsigned)(w - 3 * rid)] = st[w];
+                for (int k = 0; k < 3; k++)
+                    reinterpret_cast<uint4 *>(st + 128 * k)[lane] = make_uint4(r[0][k], r[1][k], r[2][k], r[3][k]);
+                reinterpret_cast<uint4 *>(st + 384)[lane] = make_uint4(t[0] >= 0 ? 3u * slot[0] : 0xffffffffu, t[1] >= 0 ? 3u * slot[1] : 0xffffffffu,
+                                                                        t[2] >= 0 ? 3u * slot[2] : 0xffffffffu, t[3] >= 0 ? 3u * slot[3] : 0xffffffffu);
+                __syncwarp();
+                // lane <-> record rid = 32 jj + lane: consecutive lanes hold consecutive slots inside a run of equal tiles,
+                // so a warp store covers a 384-byte span (12 sectors) instead of 32 scattered sectors
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    const int rid = jj * 32 + lane;
+                    const unsigned o3 = st[384 + rid];
+                    if (o3 != 0xffffffffu) {
+                        unsigned *dst = recs + (size_t)o3;
+                        dst[0] = st[rid]; dst[1] = st[128 + rid]; dst[2] = st[256 + rid];
+                    }
                 }
                 __syncwarp();                                  // the next round overwrites the staging area
             }
@@ -1023,6 +1025,8 @@ __device__ __forceinline__ double limbs_to_double(unsigned lo, unsigned hi) {
     return __fma_rn(dhi, 4294967296.0, dlo);
 }
 
+template <bool V> struct BoolTag { static constexpr bool value = V; };
+
 __host__ __device__ constexpr int tile_plane_pitch(int sup, int flush, int R, int RP) {
     int ps = R * RP;
     if (sup == 2 && flush == 0) ps += (8 - (ps & 31) + 32) & 31;     // even: R * RP and 8 are
@@ -1078,19 +1082,38 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
     const bool small_mesh = (int64_t)tg.gm.x_n * tg.gm.n[1] * tg.gm.n[2] < (1ll << 32);   // 32-bit stash offsets
     const unsigned lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
-    constexpr bool ROT = (SUP == 2 && FLUSH == 0);
-    const int rot = ROT ? (int)(lane & 7) : 0;
-    int coff[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const int c = j ^ rot;
-        coff[j] = (c >> 2) * PS + ((c >> 1) & 1) * RP + (c & 1);
-    }
-    // deposits of the records [b, e) of one bucket into the accumulator
-    auto accumulate = [&](unsigned b, unsigned e) {
+    // Lane-rotated corner order (CIC, ordered write-back): this lane deposits corner j ^ rot at step j.  The neighbouring
+    // records of a spatially coherent catalogue share their stencil cells, and in the same order all their lanes would hit
+    // the same word in every ATOMS; rotated, eight neighbours hit the eight corners, which the padded plane pitch keeps in
+    // eight different banks.  The rotation lives in three signed byte strides and the byte address of the lane's first
+    // corner (four lane constants); the weights of an axis are exchanged where its stride is negative.
+#ifndef NBK_PAINT_ROT
+#define NBK_PAINT_ROT 0      // lane bits that rotate the corner order (x = 4, y = 2, z = 1); 0: fixed order (measured: 7, 1 and 0
+                             // take the same time -- the rotation removes a third of the shared-memory wavefronts but the pass is
+                             // issue-bound, profiles/r02_paint.md)
+#endif
+    constexpr bool ROT = (SUP == 2 && FLUSH == 0 && NBK_PAINT_ROT != 0);
+    const unsigned rot = ROT ? (lane & (unsigned)NBK_PAINT_ROT) : 0u;
+    const int sX = (rot & 4u) ? -4 * PS : 4 * PS, sY = (rot & 2u) ? -4 * RP : 4 * RP, sZ = (rot & 1u) ? -4 : 4;
+    const unsigned sbase = smem_u32(s_lo) + ((rot & 4u) ? 4u * PS : 0u) + ((rot & 2u) ? 4u * RP : 0u) + ((rot & 1u) ? 4u : 0u);
+    constexpr unsigned HIOFF = 4u * (unsigned)NC;          // low limb -> high limb, bytes
+    // non-negative deposit q <= 2^31 at the low limb `addr` (shared-window byte address); the carry goes to the high limb
+    auto deposit = [&](unsigned addr, unsigned q) {
+        // (one asm block: the carry add stays a PREDICATED instruction; as C++ `if` it became a branch + reconvergence pair)
+        asm volatile("{\n"
+                     ".reg .pred p;\n"
+                     ".reg .u32 o, t;\n"
+                     "atom.shared.add.u32 o, [%0], %1;\n"
+                     "add.u32 t, o, %1;\n"
+                     "setp.lt.u32 p, t, o;\n"
+                     "@p red.shared.add.u32 [%2], 1;\n"
+                     "}\n" :: "r"(addr), "r"(q), "r"(addr + HIOFF) : "memory");
+    };
+    // deposits of the records [b, e) of one bucket into the accumulator (HM: the catalogue carries masses)
+    auto accumulate_t = [&](unsigned b, unsigned e, auto hm_tag) {
+        constexpr bool HM = decltype(hm_tag)::value;
         // Particle -> thread map.  spread == 0: thread p takes records p, p + NT, ... (coalesced).  spread != 0: the
-        // lanes of a warp walk 32 separate segments of the bucket, so that the neighbouring (same-cell) particles of a
-        // spatially coherent catalogue do not meet in one ATOMS instruction.
+        // lanes of a warp walk 32 separate segments of the bucket (diagnosis knob).
         const unsigned cnt = e - b;
         const unsigned seg = (cnt + 31) / 32;               // records per lane segment (spread mode)
         unsigned idx = spread ? wid : threadIdx.x;          // spread: position within the lane's segment
@@ -1102,7 +1125,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
         if (idx < lim) {
             const unsigned *rp = recs + 3 * (size_t)(base + idx);
             rn[0] = rp[0]; rn[1] = rp[1]; rn[2] = rp[2];
-            if (smass) mn = smass[base + idx];
+            if (HM) mn = smass[base + idx];
         }
         for (; idx < lim; idx += step) {
             const unsigned r0 = rn[0], r1 = rn[1], r2 = rn[2];
@@ -1110,7 +1133,7 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
             if (idx + step < lim) {                          // next round's record is requested before the deposits
                 const unsigned *rp = recs + 3 * (size_t)(base + idx + step);
                 rn[0] = rp[0]; rn[1] = rp[1]; rn[2] = rp[2];
-                if (smass) mn = smass[base + idx + step];
+                if (HM) mn = smass[base + idx + step];
             }
             unsigned u[3] = {r0 << 4, r1 << 4, r2 << 4};
             int l[3] = {(int)(r0 >> 28), (int)(r1 >> 28), (int)(r2 >> 28)};
@@ -1127,50 +1150,54 @@ k_tile_paint(const unsigned *__restrict__ recs, const MT *__restrict__ smass, Ti
                 WinD<SUP>::eval(WinD<SUP>::DMIN != 0.0 ? WinD<SUP>::DMIN + fr : fr, w[d]);
             }
             if (ROT) {
-                // lane-rotated corner order: this lane deposits corner j ^ rot at step j (weights exchanged per axis, offsets
-                // in coff): the neighbouring records of a spatially coherent catalogue share their stencil cells, and in the
-                // same order all their lanes would hit the same word in every ATOMS; rotated, eight neighbours hit the eight
-                // corners, which the padded plane pitch keeps in eight different banks
 #pragma unroll
                 for (int d = 0; d < 3; d++) {
-                    const bool sw = (rot >> (2 - d)) & 1;
+                    const bool sw = (rot >> (2 - d)) & 1u;
                     const double w0 = w[d][0], w1 = w[d][SUP - 1];
                     w[d][0] = sw ? w1 : w0;
                     w[d][SUP - 1] = sw ? w0 : w1;
                 }
             }
-            const int base0 = l[0] * PS + l[1] * RP + l[2];
-            const double m = smass ? (double)mcur : 1.0;
+            const unsigned a0 = sbase + 4u * (unsigned)(l[0] * PS + l[1] * RP + l[2]);
+            const double m = HM ? (double)mcur : 1.0;
             const double mS = m * S;
             double wz[SUP];
 #pragma unroll
             for (int rz = 0; rz < SUP; rz++) wz[rz] = w[2][rz] * mS;
-            if (m >= 0.0) {
+            if (!HM || m >= 0.0) {
                 // all deposits are in [0, 2^31]: round-to-nearest integer = low word of fma(wxy, wz, 2^52)
 #pragma unroll
                 for (int rx = 0; rx < SUP; rx++)
 #pragma unroll
                     for (int ry = 0; ry < SUP; ry++) {
-                        double wxy = w[0][rx] * w[1][ry];
+                        const double wxy = w[0][rx] * w[1][ry];
+                        const unsigned axy = ROT ? a0 + (unsigned)(rx * sX + ry * sY) : a0 + 4u * (unsigned)(rx * PS + ry * RP);
 #pragma unroll
                         for (int rz = 0; rz < SUP; rz++) {
-                            unsigned q = (unsigned)__double2loint(__fma_rn(wxy, wz[rz], 4503599627370496.0));
-                            fixed_add_pos(s_lo, s_hi, base0 + (ROT ? coff[(rx * 2 + ry) * 2 + rz] : rx * PS + ry * RP + rz), q);
+                            const unsigned q = (unsigned)__double2loint(__fma_rn(wxy, wz[rz], 4503599627370496.0));
+                            deposit(ROT ? axy + (unsigned)(rz * sZ) : axy + 4u * (unsigned)rz, q);
                         }
                     }
             } else {
+                const int base0 = l[0] * PS + l[1] * RP + l[2];       // negative weights: signed 64-bit deposits, unrotated
 #pragma unroll
                 for (int rx = 0; rx < SUP; rx++)
 #pragma unroll
                     for (int ry = 0; ry < SUP; ry++) {
-                        double wxy = w[0][rx] * w[1][ry];
+                        const int jx = (ROT && (rot & 4u)) ? SUP - 1 - rx : rx, jy = (ROT && (rot & 2u)) ? SUP - 1 - ry : ry;
+                        const double wxy = w[0][rx] * w[1][ry];
 #pragma unroll
-                        for (int rz = 0; rz < SUP; rz++)
-                            fixed_add(s_lo, s_hi, base0 + (ROT ? coff[(rx * 2 + ry) * 2 + rz] : rx * PS + ry * RP + rz),
-                                      __double2ll_rn(wxy * wz[rz]));
+                        for (int rz = 0; rz < SUP; rz++) {
+                            const int jz = (ROT && (rot & 1u)) ? SUP - 1 - rz : rz;
+                            fixed_add(s_lo, s_hi, base0 + jx * PS + jy * RP + jz, __double2ll_rn(wxy * wz[rz]));
+                        }
                     }
             }
         }
+    };
+    auto accumulate = [&](unsigned b, unsigned e) {
+        if (smass) accumulate_t(b, e, BoolTag<true>());
+        else accumulate_t(b, e, BoolTag<false>());
     };
 
     if (FLUSH == 1) {
@@ -1537,7 +1564,7 @@ static void make_plans(int64_t n, const int *nt, int ntiles, size_t pos_size, bo
     size_t ring = (size_t)coh.nst * 4 * threads_coh * 3 * pos_size;
     coh.staged = (aligned && env_int("NBK_PAINT_STAGED", 0) && align128((size_t)coh.W * 4) + ring <= 224 * 1024) ? 1 : 0;
     smem_coh = align128((size_t)coh.W * 4) + (coh.staged ? ring : 0);
-    coh.wstage = env_int("NBK_PAINT_WSTAGE", 1) ? 1 : 0;          // per-warp record transposition (2 KB per warp)
+    coh.wstage = (env_int("NBK_PAINT_WSTAGE", 1) && n < 1400000000ll) ? 1 : 0;   // per-warp record transposition (2 KB per warp; 32-bit word offsets)
     coh.stage_off = (int)smem_coh;
     if (coh.wstage) smem_coh += (size_t)(threads_coh / 32) * 2048;
     sca.wstage = 0;                                                // scattered input: every record goes to another tile anyway
