@@ -1635,7 +1635,12 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     unsigned *recs = (unsigned *)w; w += align256((size_t)n * 12);
     MT *smass = mass ? (MT *)w : nullptr;
     if (mass) w += align256((size_t)n * sizeof(MT));
-    const unsigned d_cap = env_int("NBK_PAINT_DEFER", 1) ? (unsigned)nbk_defer_cap(tg.ntiles) : 0u;
+    // NBK_PAINT_DEFER=0: wait for unpublished neighbours instead of deferring; NBK_PAINT_DEFER_CAP: smaller list (tests the overflow path)
+    unsigned d_cap = env_int("NBK_PAINT_DEFER", 1) ? (unsigned)nbk_defer_cap(tg.ntiles) : 0u;
+    {
+        const int c = env_int("NBK_PAINT_DEFER_CAP", 0);
+        if (c > 0 && (unsigned)c < d_cap) d_cap = (unsigned)c;
+    }
     unsigned *d_off = (unsigned *)w; w += align256((size_t)nbk_defer_cap(tg.ntiles) * 8);
     FT *d_val = (FT *)w; w += align256((size_t)nbk_defer_cap(tg.ntiles) * 8);
     const int mass_f4 = sizeof(MT) == 4;

@@ -304,6 +304,31 @@ def test_paint_tiled_vs_oracle(cuda, resampler, mesh_dtype, pos_dtype, weighted)
     np.testing.assert_allclose(got, direct, rtol=0, atol=max(tol, 2e-5 if mesh_dtype == "f4" else 0) * amax)
 
 
+@pytest.mark.parametrize("resampler,pos_dtype,weighted", [("cic", "f4", False), ("cic", "f8", True), ("tsc", "f4", True),
+                                                          ("pcs", "f4", False), ("nnb", "f8", False)])
+@pytest.mark.parametrize("knobs", [{}, {"NBK_PAINT_WSTAGE": "0"}, {"NBK_PAINT_DEFER": "0"}, {"NBK_PAINT_DEFER_CAP": "700"},
+                                   {"NBK_PAINT_W": "16"}])
+def test_paint_tiled_coherent_plan_variants(cuda, monkeypatch, resampler, pos_dtype, weighted, knobs):
+    """the coherent bucketing plan (windowed histogram, per-warp record transposition) and the write-back variants of the
+    tile pass (deferred halo list, its overflow -> wait fallback, plain waiting): cell-sorted input, and the same plan forced
+    onto unsorted input; NBK_PAINT_W=16 shrinks the tile window below the 48 tiles of this mesh, so most particles take the
+    out-of-window (global atomic) route; all must reproduce the oracle"""
+    N, L = [64, 48, 64], [128., 96., 128.]                # power-of-two N/L on x and z, not on y: both record paths
+    pos = _particles(250000, L, pos_dtype)
+    mass = np.random.RandomState(11).uniform(-1.0, 2.0, size=len(pos)) if weighted else None
+    g = np.floor(pos.astype("f8") * (np.array(N) / np.array(L))).astype("i8")
+    order = np.lexsort((g[:, 2], g[:, 1], g[:, 0]))        # generator-like cell order
+    pm = _pm(N, L, "f8")
+    want = po.paint(pos, mass, N, L, resampler, dtype="f8")
+    amax = np.abs(want).max()
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("NBK_PAINT_BUCKET", "coherent")
+    for idx in (order, np.arange(len(pos))):
+        got = pm.paint(pos[idx], mass=mass[idx] if weighted else 1.0, resampler=resampler, method='tiled').numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-7 * amax)
+
+
 def test_paint_tiled_is_order_independent(cuda):
     """fixed-point accumulation: any particle order gives the same bits (the REDG path cannot promise that)"""
     N, L = 64, 200.
