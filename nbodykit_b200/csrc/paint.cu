@@ -719,8 +719,10 @@ __device__ __forceinline__ int chunk_window_lo(const PT *__restrict__ cpos, int 
     return *s_lo;
 }
 
-template <int SUP, typename PT, bool STAGED>
-__global__ void __launch_bounds__(1024)
+// MAXT: 512 (coherent plan: three CTAs per SM -- the register cap that goes with it is what keeps the count pass at 40
+// registers) or 1024 (scattered plan: one CTA per SM around a 200 KB histogram)
+template <int SUP, typename PT, bool STAGED, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 512 ? 3 : 1)
 k_bucket_count(const PT *__restrict__ pos, const void *__restrict__ mass, int mass_f4, int64_t n, TileGeom tg, FastTile ft,
                unsigned *__restrict__ hdr, unsigned *__restrict__ cnt_w, unsigned *__restrict__ cnt_o,
                unsigned *__restrict__ blk, int *__restrict__ win_lo, BucketPlan bp) {
@@ -828,8 +830,8 @@ k_tile_scan(const unsigned *__restrict__ cnt_w, const unsigned *__restrict__ cnt
     if (threadIdx.x == 0) { offsets[ntiles] = carry; hdr[HDR_QUEUE] = 0; }
 }
 
-template <int SUP, typename PT, bool STAGED>
-__global__ void __launch_bounds__(1024)
+template <int SUP, typename PT, bool STAGED, int MAXT>
+__global__ void __launch_bounds__(MAXT, MAXT == 512 ? 2 : 1)
 k_bucket_scatter(const PT *__restrict__ pos, const void *__restrict__ mass, int mass_f4, int64_t n, TileGeom tg, FastTile ft,
                  const unsigned *__restrict__ hdr, const unsigned *__restrict__ offsets,
                  const unsigned *__restrict__ cnt_w, unsigned *__restrict__ cur_o, const unsigned *__restrict__ blk,
@@ -1558,6 +1560,7 @@ static void make_plans(int64_t n, const int *nt, int ntiles, size_t pos_size, bo
     coh.W = ntiles < w ? ntiles : (int)w;
     plan_chunks(coh, n, NBK_CHUNKS_COHERENT);        // refined by the caller once the occupancy is known
     threads_coh = env_int("NBK_PAINT_THREADS", 512);
+    if (threads_coh > 512 || threads_coh < 64 || threads_coh % 32) threads_coh = 512;     // the coherent kernels are built for <= 512 threads
     coh.nst = env_int("NBK_PAINT_NST", 2);
     if (coh.nst < 2) coh.nst = 2;
     if (coh.nst > 8) coh.nst = 8;
@@ -1662,15 +1665,15 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
     int occ_c = 1, occ_s = 1;
     const size_t sm_cnt = coh.wstage ? (size_t)coh.stage_off : sm_c;      // the count pass does not need the record staging
     if (coh.staged) {
-        NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-        NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, true>, th_c, sm_cnt));
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, true>, th_c, sm_c));
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, true, 512>, th_c, sm_cnt));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, true, 512>, th_c, sm_c));
     } else {
-        NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-        NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, false>, th_c, sm_cnt));
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, false>, th_c, sm_c));
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_count<SUP, PT, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaFuncSetAttribute(k_bucket_scatter<SUP, PT, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_c));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_c, k_bucket_count<SUP, PT, false, 512>, th_c, sm_cnt));
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_bucket_scatter<SUP, PT, false, 512>, th_c, sm_c));
     }
     if (occ_c < 1) occ_c = 1;
     if (occ_s < 1) occ_s = 1;
@@ -1688,21 +1691,19 @@ static int run_tiled(const void *pos, const void *mass, int64_t n, const PaintGe
 #define LAUNCH_BUCKET(KERN, GRIDC, SMC, ...)                                                                                      \
     do {                                                                                                              \
         if (coh.staged) {                                                                                             \
-            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMC))); \
-            KERN<SUP, PT, true><<<GRIDC, th_c, SMC, s>>>(__VA_ARGS__, coh);                                          \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMC))); \
+            KERN<SUP, PT, true, 512><<<GRIDC, th_c, SMC, s>>>(__VA_ARGS__, coh);                                     \
         } else {                                                                                                      \
-            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMC))); \
-            KERN<SUP, PT, false><<<GRIDC, th_c, SMC, s>>>(__VA_ARGS__, coh);                                         \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMC))); \
+            KERN<SUP, PT, false, 512><<<GRIDC, th_c, SMC, s>>>(__VA_ARGS__, coh);                                    \
         }                                                                                                             \
         NBK_LAUNCHED();                                                                                               \
         if (sca.staged) {                                                                                             \
-            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                          (int)(sm_s > sm_c ? sm_s : sm_c)));                                         \
-            KERN<SUP, PT, true><<<grid_s, th_s, sm_s, s>>>(__VA_ARGS__, sca);                                         \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s)); \
+            KERN<SUP, PT, true, 1024><<<grid_s, th_s, sm_s, s>>>(__VA_ARGS__, sca);                                   \
         } else {                                                                                                      \
-            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
-                                          (int)(sm_s > sm_c ? sm_s : sm_c)));                                         \
-            KERN<SUP, PT, false><<<grid_s, th_s, sm_s, s>>>(__VA_ARGS__, sca);                                        \
+            NBK_CUDA(cudaFuncSetAttribute(KERN<SUP, PT, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_s)); \
+            KERN<SUP, PT, false, 1024><<<grid_s, th_s, sm_s, s>>>(__VA_ARGS__, sca);                                  \
         }                                                                                                             \
         NBK_LAUNCHED();                                                                                               \
     } while (0)
