@@ -407,8 +407,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "parity": parity,
-        "roofline": {"kernel": "paint = nbk_paint_tiled (k_bucket_probe, k_bucket_count, k_tile_scan, k_bucket_scatter, "
-                               "k_tile_paint), all paint launches of a step summed" + ("; rank 0's slab" if world > 1 else ""),
+        "roofline": {"kernel": "paint = nbk_paint_tiled (k_bucket_probe, k_bucket_count, k_tile_scan*, k_bucket_scatter, "
+                               "k_tile_paint, k_apply_deferred), all paint launches of a step summed" + ("; rank 0's slab" if world > 1 else ""),
                      "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm, "peak_source": which, "algorithmic_bytes": alg_bytes,
                      "kernel_ms": paint_ms, "traffic": traffic, "traffic_source": traffic_src,
