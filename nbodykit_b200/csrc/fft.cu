@@ -592,6 +592,11 @@ __device__ __forceinline__ void fm_tma_load_4d(void *sdst, const CUtensorMap *tm
                  :: "r"(fm_smem_u32(sdst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(fm_smem_u32(bar)) : "memory");
 }
 
+__device__ __forceinline__ void fm_tma_prefetch_4d(const CUtensorMap *tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 :: "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
 template <typename C> struct W16c;      // cos(pi/8), sin(pi/8)
 template <> struct W16c<float2> { static __device__ __forceinline__ float c() { return 0.92387953251128675613f; }
                                   static __device__ __forceinline__ float s() { return 0.38268343236508977173f; } };
@@ -638,7 +643,7 @@ __global__ void __launch_bounds__(NT)
 k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *dst, PeerPtrs<typename C2<T>::type> peers,
                 const typename C2<T>::type *__restrict__ twg, int64_t line_stride, int64_t n_inner, int64_t tiles_inner,
                 int64_t n_tiles, int64_t outer_stride, int n_per, int64_t d_total, int64_t outer_start, int inverse, T scale,
-                int NS) {
+                int NS, int l2_ahead) {
     typedef typename C2<T>::type C;
     // B side-by-side lines: 128-byte rows (8 c16 / 16 c8), or 64-byte rows at N = 1024 so that TWO CTAs share an SM
     constexpr int S = 64, N = S * R, NW = NT / 32, SLOT = S * B;
@@ -670,9 +675,23 @@ k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *
         fm_mbar_expect_tx(&bars[slot], (unsigned)(SLOT * sizeof(C)));
         fm_tma_load_4d(ring + (size_t)slot * SLOT, &tmap, (int)(2 * inner0), j, 0, (int)outer, &bars[slot]);
     };
+    // L2 prefetch of the boxes one tile beyond what the ring can hold: they need no slot, and when the slots free up the
+    // real loads find their rows in L2 instead of queueing behind the stores in DRAM
+    int fetched = 0;
+    auto prefetch = [&](int g) {
+        const int it = g / R, j = g - it * R;
+        const int64_t tile = first + (int64_t)it * gridDim.x;
+        const int64_t outer = tile / tiles_inner;
+        const int64_t inner0 = (tile - outer * tiles_inner) * B;
+        fm_tma_prefetch_4d(&tmap, (int)(2 * inner0), j, 0, (int)outer);
+    };
     if (tid == 0) {
         const int upto = G < NS ? G : NS;
         for (; issued < upto; issued++) issue(issued);
+        if (l2_ahead) {
+            int pf = issued + R < G ? issued + R : G;
+            for (fetched = issued; fetched < pf; fetched++) prefetch(fetched);
+        }
     }
     for (int it = 0; it < my_tiles; it++) {
         const int64_t tile = first + (int64_t)it * gridDim.x;
@@ -747,6 +766,11 @@ k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *
             int upto = (it + 1) * R + NS;
             if (upto > G) upto = G;
             for (; issued < upto; issued++) issue(issued);
+            if (l2_ahead) {
+                int pf = issued + R < G ? issued + R : G;
+                if (fetched < issued) fetched = issued;
+                for (; fetched < pf; fetched++) prefetch(fetched);
+            }
         }
     }
 }
@@ -1241,7 +1265,8 @@ static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, 
     const int R = N / 64;
     // tile width: 128-byte rows.  (64-byte rows -- half the ring, two CTAs per SM at N = 1024 -- are selectable with
     // NBK_FFT_TMA_B = columns; measured slower: the x pass of 1024^3 f8 takes 7.2 ms instead of 4.1.)
-    static int knob_b = -1, knob_ns = -1;
+    static int knob_b = -1, knob_ns = -1, l2_ahead = -1;
+    if (l2_ahead < 0) { const char *e = getenv("NBK_FFT_TMA_L2"); l2_ahead = (e && e[0] == '0') ? 0 : 1; }   // L2 prefetch one tile ahead
     if (knob_b < 0) { const char *e = getenv("NBK_FFT_TMA_B"); knob_b = e ? atoi(e) : 0; }
     if (knob_ns < 0) { const char *e = getenv("NBK_FFT_TMA_NS"); knob_ns = e ? atoi(e) : 0; }
     const int Bfull = 128 / (int)cs;
@@ -1282,7 +1307,7 @@ static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, 
     do {                                                                                                               \
         NBK_CUDA(cudaFuncSetAttribute(k_fft_lines_tma<T, RR, BB, NTT, PEERF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
         k_fft_lines_tma<T, RR, BB, NTT, PEERF><<<(int)g, NTT, smem, s>>>(tmap, (C *)dst, peers, (const C *)tw, line_stride, n_inner, \
-            tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale, NS);                  \
+            tiles_inner, n_tiles, outer_stride, n_per, d_total, outer_start, inverse, (T)scale, NS, l2_ahead);        \
     } while (0)
 #define LAUNCH_TMA(RR, BB, NTT) do { if (peer_host) LAUNCH_TMA2(RR, BB, NTT, true); else LAUNCH_TMA2(RR, BB, NTT, false); } while (0)
     constexpr int BF = 128 / (int)sizeof(C), BH = BF / 2;

@@ -6,6 +6,8 @@ T0=$(date +%s)
 timeout 1500 python -m pytest tests -x -q -m gpu > $O/t22.log 2>&1; echo "rc=$?" >> $O/t22.log; tail -n 3 $O/t22.log
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -n 2
 echo "elapsed $(( $(date +%s) - T0 )) s"
+for a in "1024 f8" "512 f8"; do timeout 200 python tools/fft_probe.py $a 2>&1 | tail -n 2; done
+NBK_FFT_TMA_L2=0 timeout 200 python tools/fft_probe.py 1024 f8 2>&1 | tail -n 2
 timeout 300 python tools/paint_bench.py 1e9 1024 cic f8 --only-sorted 2>&1 | grep -v "sum =\|identical"
 timeout 900 python bench.py --steps 10 --warmup 3 > $O/bench22_headline.json 2> $O/bench22_headline.err; echo "bench rc=$?"
 python - <<PY
