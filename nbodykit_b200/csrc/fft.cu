@@ -675,8 +675,7 @@ k_fft_lines_tma(const __grid_constant__ CUtensorMap tmap, typename C2<T>::type *
         fm_mbar_expect_tx(&bars[slot], (unsigned)(SLOT * sizeof(C)));
         fm_tma_load_4d(ring + (size_t)slot * SLOT, &tmap, (int)(2 * inner0), j, 0, (int)outer, &bars[slot]);
     };
-    // L2 prefetch of the boxes one tile beyond what the ring can hold: they need no slot, and when the slots free up the
-    // real loads find their rows in L2 instead of queueing behind the stores in DRAM
+    // optional (l2_ahead, off by default: measured slower): L2 prefetch of the boxes one tile beyond what the ring can hold
     int fetched = 0;
     auto prefetch = [&](int g) {
         const int it = g / R, j = g - it * R;
@@ -1266,7 +1265,9 @@ static int launch_lines_tma(const void *src, void *dst, void *const *peer_host, 
     // tile width: 128-byte rows.  (64-byte rows -- half the ring, two CTAs per SM at N = 1024 -- are selectable with
     // NBK_FFT_TMA_B = columns; measured slower: the x pass of 1024^3 f8 takes 7.2 ms instead of 4.1.)
     static int knob_b = -1, knob_ns = -1, l2_ahead = -1;
-    if (l2_ahead < 0) { const char *e = getenv("NBK_FFT_TMA_L2"); l2_ahead = (e && e[0] == '0') ? 0 : 1; }   // L2 prefetch one tile ahead
+    // NBK_FFT_TMA_L2=1: L2 tensor prefetch one tile ahead of the ring.  Off: measured SLOWER (1024^3 f8: y 4.22 -> 5.36 ms, x 4.07
+    // -> 5.57 ms; 512^3: x 0.43 -> 0.61 ms) -- the prefetches compete with the demand loads and stores for DRAM.
+    if (l2_ahead < 0) { const char *e = getenv("NBK_FFT_TMA_L2"); l2_ahead = (e && e[0] == '1') ? 1 : 0; }
     if (knob_b < 0) { const char *e = getenv("NBK_FFT_TMA_B"); knob_b = e ? atoi(e) : 0; }
     if (knob_ns < 0) { const char *e = getenv("NBK_FFT_TMA_NS"); knob_ns = e ? atoi(e) : 0; }
     const int Bfull = 128 / (int)cs;
