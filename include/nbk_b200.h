@@ -260,6 +260,12 @@ int nbk_fft_lines_pack(const void *src, void *send, int dtype, int64_t n_line, i
                        int inverse, double scale, void *stream);
 int nbk_slab_push(const void *send, void *const *peer_ptrs_host, int dtype, int64_t rows_per_peer, int64_t n_outer,
                   int64_t n_inner, int64_t outer_start, int P, int rank, void *stream);
+/* the same two steps restricted to the outer sub-range [o0, o0 + o_cnt) of the slab (planes of x in r2c, base/mesh.py:237):
+ * the caller pushes one part over NVLink on a second stream while the line pass of the next part runs */
+int nbk_fft_lines_pack_range(const void *src, void *send, int dtype, int64_t n_line, int64_t n_inner, int64_t n_outer,
+                             int64_t o0, int64_t o_cnt, int P, int inverse, double scale, void *stream);
+int nbk_slab_push_range(const void *send, void *const *peer_ptrs_host, int dtype, int64_t rows_per_peer, int64_t n_outer,
+                        int64_t n_inner, int64_t outer_start, int64_t o0, int64_t o_cnt, int P, int rank, void *stream);
 
 /* Fourier-space resampling to another mesh size: pmesh `Field.resample`, called by MeshSource.compute(Nmesh=...)
  * (base/mesh.py:317-327).  Modes both meshes represent are copied (same integer frequency label per axis, Nyquist

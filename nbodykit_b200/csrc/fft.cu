@@ -1934,6 +1934,49 @@ extern "C" int nbk_fft_lines_pack(const void *src, void *send, int dtype, int64_
     return launch_lines_scatter<double>(src, blocks, (int)n_line, n_inner, n_outer, 0, P, inverse, scale, s, n_outer);
 }
 
+// the same line pass restricted to the outer sub-range [o0, o0 + o_cnt) of the slab (the send blocks keep their full
+// [kl][n_outer][inner] shape): lets the caller push one part of the slab while the next part is still being transformed
+extern "C" int nbk_fft_lines_pack_range(const void *src, void *send, int dtype, int64_t n_line, int64_t n_inner,
+                                        int64_t n_outer, int64_t o0, int64_t o_cnt, int P, int inverse, double scale,
+                                        void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "fft_lines_pack_range: bad dtype %d", dtype);
+    NBK_CHECK_ARG(is_pow2(n_line) && n_line >= 2 && n_line <= 8192, "fft_lines_pack_range: line length %lld unsupported", (long long)n_line);
+    NBK_CHECK_ARG(P >= 1 && P <= NBK_MAX_PEERS && n_line % P == 0, "fft_lines_pack_range: bad peer count %d", P);
+    NBK_CHECK_ARG(o0 >= 0 && o_cnt >= 0 && o0 + o_cnt <= n_outer, "fft_lines_pack_range: bad sub-range");
+    if (n_inner <= 0 || o_cnt <= 0) return NBK_OK;
+    const size_t cs = dtype == NBK_F4 ? 8 : 16;
+    const size_t block = (size_t)(n_line / P) * n_outer * n_inner * cs;
+    void *blocks[NBK_MAX_PEERS];
+    for (int p = 0; p < P; p++) blocks[p] = (char *)send + (size_t)p * block;
+    const char *sub = (const char *)src + (size_t)o0 * n_line * n_inner * cs;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == NBK_F4)
+        return launch_lines_scatter<float>(sub, blocks, (int)n_line, n_inner, o_cnt, o0, P, inverse, scale, s, n_outer);
+    return launch_lines_scatter<double>(sub, blocks, (int)n_line, n_inner, o_cnt, o0, P, inverse, scale, s, n_outer);
+}
+
+// nbk_slab_push for the outer sub-range [o0, o0 + o_cnt) of every row
+extern "C" int nbk_slab_push_range(const void *send, void *const *peer_ptrs_host, int dtype, int64_t rows_per_peer,
+                                   int64_t n_outer, int64_t n_inner, int64_t outer_start, int64_t o0, int64_t o_cnt, int P,
+                                   int rank, void *stream) {
+    NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "slab_push_range: bad dtype %d", dtype);
+    NBK_CHECK_ARG(P >= 1 && P <= NBK_MAX_PEERS && rank >= 0 && rank < P, "slab_push_range: bad peer count / rank");
+    NBK_CHECK_ARG(o0 >= 0 && o_cnt >= 0 && o0 + o_cnt <= n_outer, "slab_push_range: bad sub-range");
+    if (rows_per_peer <= 0 || o_cnt <= 0 || n_inner <= 0) return NBK_OK;
+    const size_t cs = dtype == NBK_F4 ? 8 : 16;
+    const size_t spitch = (size_t)n_outer * n_inner * cs;           // one kl row of my block
+    const size_t dpitch = spitch * P;                               // the same row of the destination field
+    const size_t width = (size_t)o_cnt * n_inner * cs;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int i = 0; i < P; i++) {
+        const int p = (rank + i) % P;                               // every rank starts with a different peer
+        const char *srcp = (const char *)send + (size_t)p * rows_per_peer * spitch + (size_t)o0 * n_inner * cs;
+        char *dstp = (char *)peer_ptrs_host[p] + (size_t)(outer_start + o0) * n_inner * cs;
+        NBK_CUDA(cudaMemcpy2DAsync(dstp, dpitch, srcp, spitch, width, (size_t)rows_per_peer, cudaMemcpyDeviceToDevice, s));
+    }
+    return NBK_OK;
+}
+
 extern "C" int nbk_slab_push(const void *send, void *const *peer_ptrs_host, int dtype, int64_t rows_per_peer,
                              int64_t n_outer, int64_t n_inner, int64_t outer_start, int P, int rank, void *stream) {
     NBK_CHECK_ARG(dtype == NBK_F4 || dtype == NBK_F8, "slab_push: bad dtype %d", dtype);

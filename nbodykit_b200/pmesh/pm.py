@@ -104,6 +104,27 @@ class Layout(object):
 _PEER_STAGE_CACHE = {}
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_streams(device):
+    """two side streams per device for the NVLink copies of the pipelined slab exchange"""
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(2)]
+    return _COPY_STREAMS[key]
+
+
+def _push_chunks(x_n):
+    """parts the slab exchange of r2c is pipelined in (NBK_FFT_PUSH_CHUNKS, default 4; 1 = y pass, then all copies)"""
+    import os
+    try:
+        n = int(os.environ.get("NBK_FFT_PUSH_CHUNKS", "4"))
+    except ValueError:
+        n = 4
+    return max(1, min(n, int(x_n)))
+
+
 def _transpose_mode():
     """how the slab transpose of a distributed FFT crosses NVLink: 'push' (line pass into send blocks + one strided bulk
     copy per peer, default) or 'stores' (the line pass stores every 128..256-byte run straight into the peer's field);
@@ -883,13 +904,38 @@ class RealField(Field):
                 if _transpose_mode() == "push":
                     # y pass into P contiguous send blocks, then one strided bulk copy per peer over NVLink
                     send = torch.empty((P, pm.y_n, pm.x_n, Nzc), dtype=out.value.dtype, device=out.value.device)
-                    with stage("fft_y_pack"):
-                        check(_L().nbk_fft_lines_pack(_ptr(work), _ptr(send), code, Ny, Nzc, pm.x_n, P, 0, 1.0, _stream()),
-                              "fft_lines_pack")
-                    hdl.barrier(channel=0)
-                    with stage("fft_y_scatter"):
-                        check(_L().nbk_slab_push(_ptr(send), ptrs, code, pm.y_n, pm.x_n, Nzc, pm.x_start, P, pm.comm.rank,
-                                                 _stream()), "slab_push")
+                    nchunk = _push_chunks(pm.x_n)
+                    if nchunk <= 1:
+                        with stage("fft_y_pack"):
+                            check(_L().nbk_fft_lines_pack(_ptr(work), _ptr(send), code, Ny, Nzc, pm.x_n, P, 0, 1.0, _stream()),
+                                  "fft_lines_pack")
+                        hdl.barrier(channel=0)
+                        with stage("fft_y_scatter"):
+                            check(_L().nbk_slab_push(_ptr(send), ptrs, code, pm.y_n, pm.x_n, Nzc, pm.x_start, P, pm.comm.rank,
+                                                     _stream()), "slab_push")
+                    else:
+                        # pipelined: the slab is transformed in `nchunk` parts of x planes; part c travels over NVLink on a
+                        # copy stream (two of them, alternating: two copy engines) while part c + 1 is transformed
+                        hdl.barrier(channel=0)          # every rank is past its previous x pass: the staging buffers are free
+                        main = torch.cuda.current_stream()
+                        copies = _copy_streams(out.value.device)
+                        per = (pm.x_n + nchunk - 1) // nchunk
+                        with stage("fft_y_scatter"):    # (the y pass of all parts + the exposed tail of the copies)
+                            for c in range(nchunk):
+                                o0 = c * per
+                                oc = min(per, pm.x_n - o0)
+                                if oc <= 0:
+                                    break
+                                check(_L().nbk_fft_lines_pack_range(_ptr(work), _ptr(send), code, Ny, Nzc, pm.x_n, o0, oc, P, 0, 1.0,
+                                                                    _stream()), "fft_lines_pack_range")
+                                ev = torch.cuda.Event()
+                                ev.record(main)
+                                cs = copies[c % len(copies)]
+                                cs.wait_event(ev)
+                                check(_L().nbk_slab_push_range(_ptr(send), ptrs, code, pm.y_n, pm.x_n, Nzc, pm.x_start, o0, oc, P,
+                                                               pm.comm.rank, ctypes.c_void_p(cs.cuda_stream)), "slab_push_range")
+                            for cs in copies:
+                                main.wait_stream(cs)
                 else:
                     hdl.barrier(channel=0)
                     with stage("fft_y_scatter"):
