@@ -354,8 +354,10 @@ __device__ __forceinline__ void acc_add(double *p, double v) {
 // segmented shuffle reduction leaves one shared-memory atomic per run and quantity (f64 shared atomics are
 // CAS loops on sm_100a -- same-address collisions inside a warp are what make them slow, and the run
 // reduction removes exactly those).  Mode counts come from the run length (no shuffle).
-template <typename T, int NELL, bool SMEM_ACC, bool SYM>
-__global__ void __launch_bounds__(256)
+// LEAN: the FFTPower auto-power case (complex Hermitian field, no second / mirror field, float32 coordinates) with the
+// run-time switches of the general kernel folded at compile time
+template <typename T, int NELL, bool SMEM_ACC, bool SYM, bool LEAN>
+__global__ void __launch_bounds__(256, (LEAN && NELL <= 3) ? 3 : 1)
 k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, const double *__restrict__ k2edges,
             const double *__restrict__ muedges, unsigned long long *__restrict__ g_nsum, double *__restrict__ g_xsum,
             double *__restrict__ g_musum, double *__restrict__ g_ysum, double kmin, double inv_dk, int uniform,
@@ -363,6 +365,13 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
     // ct0/ct1/ctz: per-axis products of the two fields' reciprocal window factors (first stored axis, second
     // stored axis, z); null when no compensation is fused
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int estride = LEAN ? 2 : P.estride;
+    const int coord_mode = LEAN ? 4 : P.coord_mode;
+    const bool is_p3d = LEAN ? false : (P.is_p3d != 0);
+    const bool has_c2 = LEAN ? false : (P.has_c2 != 0);
+    const void *c3p = LEAN ? nullptr : P.c3;
+    const bool herm = LEAN ? true : (P.hermitian != 0);
+    const int anti = LEAN ? 0 : P.anti;
     // shared layout: k2edges[Nx+1] | muedges[Nmu+1] | (if SMEM_ACC) xsum[nb] musum[nb] ysum[NELL][nb][2] nsum[nb](u32)
     // the k edges are staged in shared memory when they fit; with very many edges (dk = 0: one bin per distinct |k|,
     // ~N^2 of them) they stay in global memory (L2-resident) and the accumulators are global too
@@ -418,7 +427,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
         double kp2_64 = kx64 * kx64 + ky64 * ky64;
         double lp_64 = kx64 * P.los64[0] + ky64 * P.los64[1];
         double lp_48 = (double)kx32 * P.los64[0] + (double)ky32 * P.los64[1];
-        const int64_t rowlen = (int64_t)g.Nzc * P.estride;
+        const int64_t rowlen = (int64_t)g.Nzc * estride;
         int64_t roff[4];
         roff[0] = ((int64_t)i0 * g.D1 + i1) * rowlen;
         roff[1] = ((int64_t)i0 * g.D1 + m1) * rowlen;
@@ -438,7 +447,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                 if (q == 1 && !use1) continue;
                 if (q == 2 && !use2) continue;
                 if (q == 3 && !use3) continue;
-                if (P.estride == 2) v[q] = *reinterpret_cast<const V2 *>(c1 + roff[q] + 2 * kz);
+                if (estride == 2) v[q] = *reinterpret_cast<const V2 *>(c1 + roff[q] + 2 * kz);
                 else v[q].x = c1[roff[q] + kz];
             }
         };
@@ -454,7 +463,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
             if (kz < g.Nzc) {
                 int jz = nbk_freq(kz, g.N[2]);
                 double k2d, knorm, mu;
-                if (P.coord_mode == 8) {
+                if (coord_mode == 8) {
                     double kzv = (double)jz * P.kf64[2];
                     k2d = kp2_64 + kzv * kzv;
                     knorm = sqrt(k2d);
@@ -466,7 +475,7 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     float kn = sqrtf(k2);   // IEEE sqrt; numpy `** 0.5` on float32 is sqrtf
                     k2d = (double)k2;
                     knorm = (double)kn;
-                    if (P.coord_mode == 4) {
+                    if (coord_mode == 4) {
                         float m = (lp_32 + kzv * P.los32[2]) / kn;
                         mu = (kn == 0.0f) ? 0.0 : (double)m;
                     } else {
@@ -487,34 +496,34 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                 int dm = 0;
                 for (int i = 0; i <= P.Nmu; i++) dm += (s_mu[i] <= mu) ? 1 : 0;
                 key = b * (P.Nmu + 2) + dm;
-                bool nonsing = P.hermitian && (jz > 0);
+                bool nonsing = herm && (jz > 0);
                 double wH = (nonsing ? 2.0 : 1.0) * (double)mult;
                 wcnt = (nonsing ? 2u : 1u) * (unsigned)mult;
                 xs = knorm * wH;
                 ms = mu * wH;
                 double yre = 0.0, yim = 0.0, zre = 0.0, zim = 0.0;     // z: c1 * conj(c3), the statistic of the mirror mode
-                const bool mirror = nonsing && P.c3 != nullptr;
+                const bool mirror = nonsing && c3p != nullptr;
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
                     if (q == 1 && !use1) continue;
                     if (q == 2 && !use2) continue;
                     if (q == 3 && !use3) continue;
                     double a = (double)cur[q].x, bb = (double)cur[q].y;
-                    if (P.is_p3d) { yre += a; yim += bb; }
+                    if (is_p3d) { yre += a; yim += bb; }
                     else {
                         double c = a, d = bb;
-                        if (P.has_c2) { const T *p2 = c2 + roff[q] + 2 * kz; c = (double)p2[0]; d = (double)p2[1]; }
+                        if (has_c2) { const T *p2 = c2 + roff[q] + 2 * kz; c = (double)p2[0]; d = (double)p2[1]; }
                         yre += a * c + bb * d;      // c1 * conj(c2)
                         yim += bb * c - a * d;
                         if (mirror) {
-                            const T *p3 = reinterpret_cast<const T *>(P.c3) + roff[q] + 2 * kz;
+                            const T *p3 = reinterpret_cast<const T *>(c3p) + roff[q] + 2 * kz;
                             const double c3r = (double)p3[0], c3i = (double)p3[1];
                             zre += a * c3r + bb * c3i;
                             zim += bb * c3r - a * c3i;
                         }
                     }
                 }
-                if (!P.is_p3d) {
+                if (!is_p3d) {
                     double vol = ct0 ? vol_row * ctz[kz] : vol_row;   // V [* window compensation of both fields]
                     yre *= vol;
                     yim *= vol;
@@ -528,11 +537,11 @@ k_power_bin(const T *__restrict__ c1, const T *__restrict__ c2, BinParams P, con
                     double f = legendre(ell, mu) * (2.0 * ell + 1.0);
                     double re = f * yre, im = f * yim;
                     if (mirror) {    // add the mirror mode from its own statistic: Leg(l)(-mu) * (+/-) conj(z)
-                        const double sg = ((ell & 1) != P.anti) ? -1.0 : 1.0;
+                        const double sg = ((ell & 1) != anti) ? -1.0 : 1.0;
                         re += sg * f * zre;
                         im -= sg * f * zim;
                     } else if (nonsing) {   // add the mirror mode: Leg(l)(-mu) * (+/-) conj(y)
-                        if ((ell & 1) != P.anti) { re = 0.0; im *= 2.0; }
+                        if ((ell & 1) != anti) { re = 0.0; im *= 2.0; }
                         else { re *= 2.0; im = 0.0; }
                     }
                     yr[l] = re;
@@ -680,20 +689,25 @@ static int launch_bin(const void *c1, const void *c2, const BinParams &P, const 
     if (grid < 1) grid = 1;
     // mirror symmetry is usable when mu does not depend on kx, ky (line of sight along z)
     const bool sym = (P.los64[0] == 0.0 && P.los64[1] == 0.0);
-#define LAUNCH_BIN(ACC, SYMV)                                                                                        \
+#define LAUNCH_BIN(ACC, SYMV, LEANV)                                                                                        \
     do {                                                                                                             \
-        NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, ACC, SYMV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+        NBK_CUDA(cudaFuncSetAttribute(k_power_bin<T, NELL, ACC, SYMV, LEANV>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                                       (int)smem));                                                                   \
         int occ = 1;   /* persistent row loop: exactly one wave of resident CTAs */                                   \
-        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_power_bin<T, NELL, ACC, SYMV>, 256, smem));    \
+        NBK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_power_bin<T, NELL, ACC, SYMV, LEANV>, 256, smem));    \
         if (occ < 1) occ = 1;                                                                                        \
         if ((int64_t)grid > (int64_t)NBK_SM_COUNT * occ) grid = NBK_SM_COUNT * occ;                                   \
-        k_power_bin<T, NELL, ACC, SYMV><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, Pk, d_k2, d_mu,         \
+        k_power_bin<T, NELL, ACC, SYMV, LEANV><<<grid, 256, smem, s>>>((const T *)c1, (const T *)c2, Pk, d_k2, d_mu,         \
                                                                 (unsigned long long *)nsum, xsum, musum, ysum, kmin, \
                                                                 inv_dk, uniform, ct0, ct1, ctz);                      \
     } while (0)
-    if (smem_acc) { if (sym) LAUNCH_BIN(true, true); else LAUNCH_BIN(true, false); }
-    else { if (sym) LAUNCH_BIN(false, true); else LAUNCH_BIN(false, false); }
+    static int lean_knob = -1;
+    if (lean_knob < 0) { const char *e = getenv("NBK_BIN_LEAN"); lean_knob = (e && e[0] == '0') ? 0 : 1; }   // 0: always the general kernel
+    const bool lean = lean_knob && smem_acc && !P.is_p3d && !P.has_c2 && P.c3 == nullptr && P.estride == 2 && P.coord_mode == 4 &&
+                      P.hermitian == 1 && P.anti == 0;
+    if (lean) { if (sym) LAUNCH_BIN(true, true, true); else LAUNCH_BIN(true, false, true); }
+    else if (smem_acc) { if (sym) LAUNCH_BIN(true, true, false); else LAUNCH_BIN(true, false, false); }
+    else { if (sym) LAUNCH_BIN(false, true, false); else LAUNCH_BIN(false, false, false); }
 #undef LAUNCH_BIN
     NBK_LAUNCHED();
     return NBK_OK;

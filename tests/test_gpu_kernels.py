@@ -551,3 +551,49 @@ def test_fft_scatter_transpose_two_virtual_ranks(cuda, dtype, shape):
         got = out.cpu().numpy()                                  # [y_n][Nx][Nzc]
         ref = np.transpose(want[:, r * y_n:(r + 1) * y_n, :], (1, 0, 2))
         assert np.abs(got - ref).max() <= tol * np.sqrt((np.abs(want) ** 2).mean()) * 10
+
+
+@pytest.mark.parametrize("shape,chunks", [((16, 32, 8), 4), ((8, 256, 16), 3), ((256, 64, 4), 5)])
+@pytest.mark.parametrize("dtype", ["f8", "f4"])
+def test_fft_pack_push_range_two_virtual_ranks(cuda, dtype, shape, chunks):
+    """the pipelined slab exchange of the distributed r2c: nbk_fft_lines_pack_range (y pass of a part of the slab into the
+    send blocks) + nbk_slab_push_range (strided bulk copies of that part into the owners' transposed fields), part by part,
+    must give the transposed field of the one-shot y pass -- two virtual ranks on one GPU, uneven last part included"""
+    import ctypes
+    import torch
+    from nbodykit_b200 import _lib
+    (Nx, Ny, Nz), P = shape, 2
+    Nzc = Nz // 2 + 1
+    rng = np.random.RandomState(23)
+    real = rng.standard_normal((Nx, Ny, Nz)).astype(dtype)
+    want = np.fft.rfftn(real.astype("f8")) / real.size
+    cdt = torch.complex64 if dtype == "f4" else torch.complex128
+    code = 4 if dtype == "f4" else 8
+    Lb = _lib.lib()
+    x_n, y_n = Nx // P, Ny // P
+    stage = [torch.zeros((y_n, Nx, Nzc), dtype=cdt, device="cuda") for _ in range(P)]
+    ptrs = (ctypes.c_void_p * P)(*[t.data_ptr() for t in stage])
+    per = (x_n + chunks - 1) // chunks
+    for r in range(P):
+        slab = torch.from_numpy(real[r * x_n:(r + 1) * x_n].copy()).cuda()
+        work = torch.empty((x_n, Ny, Nzc), dtype=cdt, device="cuda")
+        send = torch.zeros((P, y_n, x_n, Nzc), dtype=cdt, device="cuda")
+        _lib.check(Lb.nbk_fft_z_forward(ctypes.c_void_p(slab.data_ptr()), ctypes.c_void_p(work.data_ptr()), code, x_n * Ny, Nz, None))
+        for c in range(chunks):
+            o0 = c * per
+            oc = min(per, x_n - o0)
+            if oc <= 0:
+                break
+            _lib.check(Lb.nbk_fft_lines_pack_range(ctypes.c_void_p(work.data_ptr()), ctypes.c_void_p(send.data_ptr()), code, Ny, Nzc,
+                                                   x_n, o0, oc, P, 0, 1.0, None))
+            _lib.check(Lb.nbk_slab_push_range(ctypes.c_void_p(send.data_ptr()), ptrs, code, y_n, x_n, Nzc, r * x_n, o0, oc, P, r, None))
+    torch.cuda.synchronize()
+    tol = 1e-13 if dtype == "f8" else 2e-6
+    for r in range(P):
+        out = torch.empty_like(stage[r])
+        _lib.check(Lb.nbk_fft_lines_oop(ctypes.c_void_p(stage[r].data_ptr()), ctypes.c_void_p(out.data_ptr()), code, Nx, Nzc, Nzc,
+                                        y_n, Nx * Nzc, 0, 1.0 / real.size, None))
+        torch.cuda.synchronize()
+        got = out.cpu().numpy()
+        ref = np.transpose(want[:, r * y_n:(r + 1) * y_n, :], (1, 0, 2))
+        assert np.abs(got - ref).max() <= tol * np.sqrt((np.abs(want) ** 2).mean()) * 10
