@@ -2,17 +2,20 @@
 // source/mesh/catalog.py:341-351).  Forward is normalised by 1/prod(N), backward is not
 // (source/mesh/array.py:36-37, fftpower.py:126-128).
 //
-// Structure: three shared-memory line passes, each one read + one write of the field (HBM-bound):
+// Structure: three line passes, each one read + one write of the field (HBM-bound):
 //   z pass  : rows are contiguous; real row of Nz -> packed complex FFT of Nz/2 -> Nz/2+1 modes
-//   y pass  : lines strided by Nzc, tiles of B adjacent kz columns  (B*sizeof(cplx) >= 64 B runs)
+//   y pass  : lines strided by Nzc, tiles of B adjacent kz columns  (B * sizeof(cplx) = 128-byte runs)
 //   x pass  : lines strided by Ny*Nzc, tiles of B adjacent (y,kz) elements
-// Every pass works on tiles of B side-by-side lines ([N][B+1] in shared memory, B * sizeof(complex) = 128 bytes) with
-// a decimation-in-frequency FFT whose radix-8 butterflies live in registers (+ one radix-4 / radix-2 stage for the
-// remainder of log2 N).  The default kernels (k_fft_lines_rg, k_fft_z_r2c_rg; N >= 64) load the first stage straight
-// from global memory and store the last stage straight to the digit-reversed frequency rows, so shared memory only
-// carries the exchanges between stages; the older kernels (k_fft_lines with cp.async double buffering, k_fft_z_r2c,
-// k_fft_z_c2r) stage whole tiles and serve short lines, the backward z pass and NBK_FFT_LINES=smem.
-// Twiddles: f8-accurate table built on the device with sincospi, staged in shared memory.  Sizes: 2^k.
+// Default kernels (round 2), built around the copy engine so that the warps only run butterflies:
+//   k_fft_lines_tma   lines of 256 / 512 / 1024: row groups stream through a ring of shared-memory slots as 4-D tensor-map
+//                     boxes (cp.async.bulk.tensor + mbarrier), one 64-point FFT per warp, one radix-R combine per tile
+//   k_fft_z_r2c_tma   rows of 256 / 512 / 1024 reals: warp-per-row, private ring of row buffers filled by 1-D bulk copies
+// Older families, still serving short lines, c8 lines whose rows are not 16-byte aligned, the backward z pass and the
+// NBK_FFT_LINES=rg|smem knob: the register-I/O kernels (k_fft_lines_rg, k_fft_z_r2c_rg: first radix-8 stage straight from
+// global memory, last stage straight to the digit-reversed frequency rows, [N][B+1] padded tiles in between) and the
+// shared-memory kernels (k_fft_lines with cp.async double buffering, k_fft_z_r2c, k_fft_z_c2r).
+// Decimation-in-frequency radix-8 butterflies in registers throughout (+ one radix-4 / radix-2 stage for the remainder of
+// log2 N).  Twiddles: f8-accurate table built on the device with sincospi, staged in shared memory.  Sizes: 2^k.
 #include "common.cuh"
 #include <cuda.h>      // CUtensorMap types only: the encoder comes from cudaGetDriverEntryPoint (no -lcuda)
 #include <map>

@@ -236,23 +236,26 @@ static int paint_impl(const void *pos, int pos_dtype, int64_t n, const void *mas
 //   probe   k_bucket_probe    : samples neighbouring particle pairs: is the input spatially coherent (e.g. the
 //                               cell-sorted output of a mock generator)?  Picks the bucketing configuration ON THE
 //                               DEVICE (no host round trip): both configurations are launched, the other one exits.
-//   pass A  k_bucket_count    : every CTA owns contiguous particle chunks, staged into shared memory by the TMA
-//                               engine (cp.async.bulk + mbarrier, double buffered), and histograms the tile ids in a
-//                               shared-memory WINDOW of tile indices (native ATOMS.ADD.U32); one global atomic per
-//                               (chunk, tile) reserves the chunk's share of the tile's bucket.  Particles whose tile
-//                               lies outside the window are counted with (warp-aggregated) global atomics.
-//                               coherent input : window = 16384 tiles (a few x planes of tiles), 2 CTAs / SM
+//   pass A  k_bucket_count    : every CTA owns contiguous particle chunks (aligned quads per thread, 16-byte loads) and
+//                               histograms the tile ids in a shared-memory WINDOW of tile indices (native
+//                               ATOMS.ADD.U32); one global atomic per (chunk, tile) reserves the chunk's share of the
+//                               tile's bucket.  Particles whose tile lies outside the window are counted with
+//                               (warp-aggregated) global atomics.
+//                               coherent input : window = 4 planes of tiles (<= 16384), 512-thread CTAs, 3 per SM
 //                               scattered input: window = all tiles when they fit in 200 KB (<= 51200 tiles)
-//   pass B  k_tile_scan       : exclusive scan of the tile counts -> bucket offsets; clears cursors and flags
-//   pass C  k_bucket_scatter  : same chunks, same windows: evaluates the exact f8 grid coordinate once and emits a
-//                               12-byte record per particle (per axis: 4-bit cell-in-tile | 28-bit fraction)
-//   pass D  k_tile_paint      : persistent CTAs pull tiles from a queue IN TILE ORDER; region = (T + halo)^3 cells in
-//                               shared memory as two u32 limbs.  Write-back without a cleared mesh and without
+//   pass B  k_tile_scan(_totals): exclusive scan of the tile counts over segments of 4096 tiles -> bucket offsets;
+//                               clears cursors and flags
+//   pass C  k_bucket_scatter  : same chunks, same windows: evaluates the exact grid coordinate once and emits a
+//                               12-byte record per particle (per axis: 4-bit cell-in-tile | 28-bit fraction); the
+//                               records of a warp leave through a shared-memory transposition (coalesced stores)
+//   pass D  k_tile_paint      : persistent CTAs pull tiles from a queue IN (descending) TILE ORDER; region = (T + halo)^3
+//                               cells in shared memory as two u32 limbs.  Write-back without a cleared mesh and without
 //                               read-modify-write of DRAM-resident lines: of all tiles touching a cell the FIRST in
-//                               queue order stores it (plain coalesced stores), publishes a per-tile flag
-//                               (release), and the later ones add their share (REDG, L2-resident) after acquiring
-//                               the flags of the earlier tiles they overlap.  hold=True (accumulate into an existing
-//                               mesh) uses one TMA bulk reduce-add per z row instead.
+//                               queue order stores it (plain coalesced stores) and publishes a per-tile flag
+//                               (release); the later ones park their share and add it (REDG, L2-resident) one tile
+//                               later if the earlier tiles have published -- otherwise they hand it to a deferred list
+//                               (k_apply_deferred adds it after the kernel): nobody waits.  hold=True (accumulate into
+//                               an existing mesh) uses one TMA bulk reduce-add per z row instead.
 // A tile owns the particles whose LEFTMOST stencil cell lies in it, so the halo is one-sided.
 // =============================================================================================
 #define TILE 16
