@@ -437,7 +437,7 @@ def run_ours(args):
         sys.exit(3)
 
 
-def cpu_step(pos, cfg, nproc=None):
+def cpu_step(pos, cfg, nproc=None, single=True):
     """one full step of the reference's CPU algorithm (oracle port) on all host cores: C/OpenMP restatement of the
     pmesh scatter over EVERY particle, scipy (pocketfft) r2c with all workers, and the mesh stages (compensation,
     |delta_k|^2 V, project_to_basis -- the reference's own per-slab NumPy code) spread over one process per core the
@@ -459,7 +459,9 @@ def cpu_step(pos, cfg, nproc=None):
     res = opar.power_from_complex(c, None, Nm, Bx, mode=cfg["mode"], Nmu=cfg.get("Nmu", 5), compensation=comp, nproc=nproc)
     t3 = time.time()
     total = t3 - t0
+    single = single_core_sample(pos, c, cfg, comp) if single else None
     return {"value": n / total, "unit": "particles/s", "cores": cores, "kind": "port", "seconds": total,
+            "single_core": single,
             "paint_seconds": t1 - t0, "r2c_seconds": t2 - t1, "mesh_stage_seconds": t3 - t2,
             "paint_particles_per_sec": n / (t1 - t0), "omp_threads": os.environ.get("OMP_NUM_THREADS"),
             "processes_mesh_stages": nproc,
@@ -467,6 +469,49 @@ def cpu_step(pos, cfg, nproc=None):
                       "compensate / power / project_to_basis (NumPy, %d processes over x-slabs) at %d^3"
                       % (n, os.environ.get("OMP_NUM_THREADS"), cores, nproc, cfg["nmesh"]),
             "_result": res}
+
+
+def single_core_sample(pos, c, cfg, comp):
+    """the single-core numbers next to the all-cores ones, on BOUNDED samples of the same workload (never
+    part of `value`): the C scatter of the first 2e7 particles on one OpenMP thread, and the reference's per-slab NumPy
+    mesh stages (compensation, |delta_k|^2 V, project_to_basis) of 4 x-planes in this process, scaled to the mesh."""
+    out = {}
+    try:
+        import ctypes
+        from oracle import build_c, parallel as opar
+        Nm = [cfg["nmesh"]] * 3
+        Bx = [cfg["box"]] * 3
+        ns = int(min(len(pos), 2e7))
+        gomp = None
+        try:
+            gomp = ctypes.CDLL("libgomp.so.1")
+            gomp.omp_set_num_threads(1)
+        except Exception:
+            gomp = None
+        t0 = time.time()
+        build_c.paint(pos[:ns], None, Nm, Bx, cfg["resampler"])
+        dt = time.time() - t0
+        if gomp is not None:
+            gomp.omp_set_num_threads(os.cpu_count() or 1)
+        out["paint_particles_per_sec"] = ns / dt
+        out["paint_threads"] = 1 if gomp is not None else None
+        planes = min(4, c.shape[0])
+        t0 = time.time()
+        opar._G.update(c=c, c2=None, N=(np.asarray(Nm, dtype="i8")), L=np.asarray(Bx, dtype="f8"), comp=comp, coord_dtype="f4",
+                       edges=[np.arange(0., np.pi * cfg["nmesh"] / cfg["box"] + np.pi / cfg["box"], 2 * np.pi / cfg["box"]),
+                              np.linspace(-1, 1, (1 if cfg["mode"] == "1d" else cfg.get("Nmu", 5)) + 1)],
+                       los=(0, 0, 1), poles=[])
+        try:
+            opar._worker((0, planes))
+        finally:
+            opar._G.clear()
+        dt = time.time() - t0
+        out["mesh_stage_seconds_projected"] = dt * c.shape[0] / planes
+        out["sample"] = ("scatter of the first %d particles on 1 thread; mesh stages of %d of %d x-planes in one process, "
+                         "scaled by the plane count" % (ns, planes, c.shape[0]))
+    except Exception as e:      # a diagnostic, never worth the bench line
+        out["error"] = repr(e)
+    return out
 
 
 def run_reference(args):
@@ -505,7 +550,10 @@ def run_reference(args):
     last = None
     for i in range(want):
         t0 = time.time()
-        last = cpu_step(pos, cfg)
+        step_i = cpu_step(pos, cfg, single=(i == 0))
+        if last is not None and step_i.get("single_core") is None:
+            step_i["single_core"] = last.get("single_core")
+        last = step_i
         dt = time.time() - t0
         if done_w < min(args.warmup, 1) and want > 1 and (time.time() - t_start) + 2 * dt < budget:
             done_w += 1                     # at most one warm-up pass (page faults, thread pools), only if affordable
