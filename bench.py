@@ -444,7 +444,10 @@ def cpu_step(pos, cfg, nproc=None, single=True):
     way the reference spreads them over MPI ranks."""
     from oracle import build_c, parallel as opar, pmesh_oracle as po
     cores = os.cpu_count() or 1
-    nproc = nproc or cores
+    # mesh-stage workers are fork()ed from this process, which holds the catalogue, pinned buffers and a CUDA context: every
+    # fork costs ~40-110 ms of page-table copying (measured on the 128-core GPU host: 128 workers were no faster than ONE
+    # process, 4.88 s vs 4.85 s at 512^3).  24 workers balance that cost against the per-slab NumPy work.
+    nproc = nproc or min(cores, int(os.environ.get("NBK_REF_PROCS", "24")))
     Nm = [cfg["nmesh"]] * 3
     Bx = [cfg["box"]] * 3
     n = len(pos)
