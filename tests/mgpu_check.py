@@ -35,8 +35,10 @@ def main():
     cases = [dict(resampler="cic", interlaced=False, dtype="f8", mode="1d", kw={}),
              dict(resampler="tsc", interlaced=True, dtype="f4", mode="2d", kw=dict(Nmu=4, poles=[0, 2])),
              dict(resampler="pcs", interlaced=False, dtype="f8", mode="1d", kw={})]
-    for tmode, c in [(t, c) for t in ("push", "stores") for c in cases]:
-        os.environ["NBK_FFT_TRANSPOSE_MODE"] = tmode       # bulk peer copies | fine-grained remote stores
+    for tmode, c in [(t, c) for t in ("push", "push-unpipelined", "stores") for c in cases]:
+        # bulk peer copies pipelined with the y pass (default) | y pass, then all copies | fine-grained remote stores
+        os.environ["NBK_FFT_TRANSPOSE_MODE"] = "stores" if tmode == "stores" else "push"
+        os.environ["NBK_FFT_PUSH_CHUNKS"] = "1" if tmode == "push-unpipelined" else "4"
         cat = ArrayCatalog({"Position": torch.from_numpy(pos_all[mine]).cuda(), "Weight": torch.from_numpy(w_all[mine]).cuda()},
                            comm=comm, BoxSize=L)
         mesh = cat.to_mesh(Nmesh=N, resampler=c["resampler"], interlaced=c["interlaced"], compensated=True, dtype=c["dtype"])
@@ -68,6 +70,7 @@ def main():
             if not ok:
                 failures.append(c)
     os.environ.pop("NBK_FFT_TRANSPOSE_MODE", None)
+    os.environ.pop("NBK_FFT_PUSH_CHUNKS", None)
     # ---- a dense catalogue on a 256^3 mesh: tiled paint on slabs (ghost tiles, ordered write-back), both orders
     from nbodykit_b200.cosmology import NoWiggleEHPower
     from nbodykit_b200.lab import LinearMesh, LogNormalCatalog
