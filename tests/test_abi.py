@@ -68,3 +68,32 @@ def test_product_never_imports_oracle():
     out = subprocess.run(["grep", "-rlE", r"^\s*(from|import)\s+oracle|from oracle", os.path.join(ROOT, "nbodykit_b200")],
                          capture_output=True, text=True).stdout.strip()
     assert out == "", "product code imports the oracle: %s" % out
+
+
+def test_binding_argument_counts_match_the_header():
+    """every ctypes signature lists as many arguments as the prototype in include/nbk_b200.h (ABI drift guard)"""
+    from nbodykit_b200 import _lib
+    text = open(os.path.join(ROOT, "include", "nbk_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = dict(re.findall(r"\b(nbk_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S))
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, args in protos.items():
+        args = args.strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        assert n == len(_lib.SIGNATURES[name][0]), "%s: header has %d parameters, the binding %d" % (
+            name, n, len(_lib.SIGNATURES[name][0]))
+
+
+def test_range_exchange_entry_points_validate_before_cuda():
+    """nbk_fft_lines_pack_range / nbk_slab_push_range reject bad sub-ranges, peers and dtypes without touching the GPU"""
+    from nbodykit_b200 import _lib
+    L = _lib.lib()
+    ptrs = (ctypes.c_void_p * 2)(None, None)
+    assert L.nbk_fft_lines_pack_range(None, None, 3, 64, 9, 8, 0, 8, 2, 0, 1.0, None) == -1 and b"dtype" in L.nbk_last_error()
+    assert L.nbk_fft_lines_pack_range(None, None, 8, 48, 9, 8, 0, 8, 2, 0, 1.0, None) == -1 and b"line length" in L.nbk_last_error()
+    assert L.nbk_fft_lines_pack_range(None, None, 8, 64, 9, 8, 6, 4, 2, 0, 1.0, None) == -1 and b"sub-range" in L.nbk_last_error()
+    assert L.nbk_fft_lines_pack_range(None, None, 8, 64, 9, 8, 0, 8, 3, 0, 1.0, None) == -1 and b"peer count" in L.nbk_last_error()
+    assert L.nbk_fft_lines_pack_range(None, None, 8, 64, 9, 8, 4, 0, 2, 0, 1.0, None) == 0          # empty part: nothing to do
+    assert L.nbk_slab_push_range(None, ptrs, 8, 32, 8, 9, 0, 6, 4, 2, 0, None) == -1 and b"sub-range" in L.nbk_last_error()
+    assert L.nbk_slab_push_range(None, ptrs, 8, 32, 8, 9, 0, 0, 8, 2, 5, None) == -1 and b"rank" in L.nbk_last_error()
+    assert L.nbk_slab_push_range(None, ptrs, 8, 32, 8, 9, 0, 4, 0, 2, 0, None) == 0
